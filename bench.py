@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the wav2vec-S encoder forward path (BASELINE.json metric: audio-seconds encoded per
+second, wav2vec-S large, bf16).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one pass of the hot path (`extract_features`) over one batch of synthetic waveforms.
+Workloads (BASELINE.json configs): large_64x20s (default; configs[2], the largest single-GPU
+config of the model the metric is quoted on), base_32x15s (configs[1]), large_64x30s (configs[4]).
+With N > 1 (torchrun, one rank per GPU) every rank encodes its own batch -- utterances are
+independent, no collective sits in the data path ("scaling": "weak"); NCCL only carries the
+barrier and the max-over-ranks timing.
+
+One JSON line is printed by rank 0.  `value` = device-resident throughput, `e2e` = the same metric
+through the public API with pinned-host input and device->host read of the result inside the
+timed region, `roofline` = the tcgen05 GEMM kernel (all launches of a step) against the measured
+bf16 peak, `cpu_baseline` = the oracle port (reference algorithm in PyTorch) on the host cores.
+`--impl reference` times that CPU implementation alone on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (model, B per GPU, seconds)
+    "large_64x20s": ("large", 64, 20),
+    "base_32x15s": ("base", 32, 15),
+    "large_64x30s": ("large", 64, 30),
+    "large_8x20s": ("large", 8, 20),
+    "tiny_4x2s": ("tiny", 4, 2),
+}
+SR = 16000
+
+
+def model_cfg(kind):
+    if kind == "large":
+        return dict(extractor_mode="layer_norm", encoder_layers=24, encoder_embed_dim=1024,
+                    encoder_ffn_embed_dim=4096, encoder_attention_heads=16, layer_norm_first=True,
+                    conv_bias=True, pos_type="sin", main_context=16, right_context=8)
+    if kind == "base":
+        return dict(extractor_mode="layer_norm", encoder_layers=12, encoder_embed_dim=768,
+                    encoder_ffn_embed_dim=3072, encoder_attention_heads=12, layer_norm_first=False,
+                    conv_bias=False, pos_type="sin", main_context=16, right_context=8)
+    return dict(extractor_mode="layer_norm", encoder_layers=3, encoder_embed_dim=128,
+                encoder_ffn_embed_dim=256, encoder_attention_heads=2, layer_norm_first=True,
+                conv_bias=True, pos_type="sin", main_context=16, right_context=8,
+                conv_feature_layers="[(64,10,5)] + [(64,3,2)]*4 + [(64,2,2)]*2")
+
+
+def conv_spec(cfg):
+    s = cfg.get("conv_feature_layers", "[(512, 10, 5)] + [(512, 3, 2)] * 4 + [(512,2,2)] + [(512,2,2)]")
+    return list(eval(s))
+
+
+def flops_per_utt(cfg, L):
+    """Algorithmic FLOPs (2*MAC, mask-aware attention) of one utterance; SURVEY.md section 8(d)."""
+    spec = conv_spec(cfg)
+    t, cin = L, 1
+    conv = 0.0
+    lens = []
+    for (c, k, s) in spec:
+        t = (t - k) // s + 1
+        lens.append(t)
+        conv += 2.0 * cin * c * k * t
+        cin = c
+    T = lens[-1]
+    D, F, Ly = cfg["encoder_embed_dim"], cfg["encoder_ffn_embed_dim"], cfg["encoder_layers"]
+    main, rc = cfg["main_context"], cfg["right_context"]
+    T2 = T + (-T) % 2
+    nb = T2 // main
+    M = T2 + nb * rc
+    P = 0
+    for tt in range(T2):
+        b = tt // main
+        P += min(main * (b + 1), T2) + (rc if b < nb else 0)
+    for b in range(nb):
+        P += rc * (min(main * (b + 1), T2) + rc)
+    proj = 2.0 * cin * D * T if cin != D else 0.0
+    linear = Ly * M * (8.0 * D * D + 4.0 * D * F)
+    attn = Ly * 4.0 * D * P
+    gemm = (conv - 2.0 * spec[0][0] * spec[0][1] * lens[0]) + proj + linear   # what the GEMM kernel executes
+    return dict(total=conv + proj + linear + attn, conv=conv, proj=proj, linear=linear, attn=attn,
+                gemm=gemm, T=T, M=M)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        busy = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def cpu_reference_run(cfg_kind, B, seconds, steps, warmup):
+    """Time the oracle port (reference algorithm, PyTorch CPU, fp32) on the host cores."""
+    import torch
+    from oracle import synth
+    from oracle import w2vs_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.default_cfg(**model_cfg(cfg_kind))
+    sd = synth.make_state_dict(cfg, 0)
+    wav = synth.make_waveform(B, seconds * SR, 1234)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.extract_features(sd, cfg, wav, None)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    t = statistics.median(times)
+    return dict(value=B * seconds / t, unit="audio-s/s", cores=cores, kind="port",
+                sample=f"{cfg_kind} fp32, {B} x {seconds} s, oracle port on torch CPU, median of {steps} after {warmup} warm-up",
+                ms_per_step=t * 1e3)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="large_64x20s", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-batch", type=int, default=1)
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    kind, B, seconds = WORKLOADS[a.workload]
+    cfg = model_cfg(kind)
+    L = seconds * SR
+    metric = f"audio-sec encoded/sec (wav2vec-S {kind}, {a.dtype})"
+    config = {"workload": f"wav2vec-S {kind} encoder forward, batch {B} x {seconds} s per GPU, {a.dtype}, "
+                          f"main_context 16 / right_context 8, random-init weights",
+              "name": a.workload, "batch_per_gpu": B, "utterance_s": seconds,
+              "l2_policy": "inputs_larger_than_l2 (activations and weights exceed the 126 MB L2)"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_run(kind, a.cpu_sample_batch, seconds, a.steps, a.warmup)
+        line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": "audio-s/s",
+                "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import wav2vec_s_b200 as W
+    from wav2vec_s_b200 import cabi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.bfloat16 if a.dtype == "bf16" else torch.float32
+
+    torch.manual_seed(0)
+    model = W.Wav2VecSModel(cfg)
+    # random-init weights of the reference's scales, non-trivial biases / affine parameters
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for n_, p in model.named_parameters():
+            if n_.endswith("bias"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+            elif p.dim() == 1 and n_.endswith("weight"):
+                p.copy_(1.0 + 0.1 * torch.randn(p.shape, generator=g))
+            elif "feature_extractor" not in n_ and p.dim() == 2:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.04)
+    model = model.to(dev, dtype).eval()
+
+    gw = torch.Generator().manual_seed(1234 + rank)
+    wav_host = torch.randn(B, L, generator=gw)
+    wav_host = (wav_host - wav_host.mean(1, keepdim=True)) / wav_host.std(1, keepdim=True)
+    wav_host = wav_host.pin_memory()
+    wav_dev = wav_host.to(dev, non_blocking=True).to(dtype)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        return model.extract_features(wav_dev, None)[0]
+
+    out_host = None
+
+    def step_e2e():
+        nonlocal out_host
+        x = wav_host.to(dev, non_blocking=True)
+        y = model.extract_features(x, None)[0]
+        if out_host is None:
+            out_host = torch.empty(y.shape, dtype=y.dtype, pin_memory=True)
+        out_host.copy_(y, non_blocking=True)
+        return y
+
+    for _ in range(a.warmup):
+        y = step_device()
+    barrier()
+    assert torch.isfinite(y.float()).all(), "non-finite encoder output"
+
+    # ---- timed region: device-resident throughput -------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    cabi.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        step_device()
+    e1.record()
+    barrier()
+    launches = cabi.launch_count(reset=True)
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- timed region: end to end through the public API (pinned host in, host out) ---------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(a.steps):
+        step_e2e()
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+
+    # ---- per-kernel-class device time of one step (CUDA events on the launching stream) -----
+    prof = None
+    if hasattr(cabi.lib(), "w2vs_prof_enable"):
+        prof = cabi.profile_step(step_device, reps=2)
+    barrier()
+
+    if rank == 0:
+        audio_s = B * seconds * world
+        ms_step = ms / a.steps
+        fl = flops_per_utt(cfg, L)
+        pk, pk_kind = peaks()
+        line = {
+            "metric": metric, "value": audio_s / (ms_step / 1e3), "unit": "audio-s/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic", "config": config,
+            "clocks": clocks,
+            "e2e": {"value": audio_s / (ms_e2e / a.steps / 1e3), "unit": "audio-s/s",
+                    "h2d_bytes_per_step": wav_host.numel() * wav_host.element_size(),
+                    "d2h_bytes_per_step": out_host.numel() * out_host.element_size()},
+            "gpu_launches": int(launches),
+            "step_tflops": fl["total"] * B / (ms_step / 1e3) / 1e12,
+            "step_frac_of_bf16_sustained": fl["total"] * B / (ms_step / 1e3) / 1e12 / pk["bf16_tflops_sustained"],
+        }
+        if prof is not None and prof.get("gemm", {}).get("count"):
+            gm = prof["gemm"]
+            ach = fl["gemm"] * B / (gm["ms"] / 1e3) / 1e12
+            line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (all launches of one step)",
+                                "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                                "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
+                                "peak_source": pk_kind + " (sustained: timed inside a long step)",
+                                "launches_per_step": gm["count"], "ms_per_step": gm["ms"]}
+            line["kernel_ms_per_step"] = {k: round(v["ms"], 3) for k, v in prof.items()}
+        else:
+            line["roofline"] = None
+        if not a.no_cpu_baseline:
+            r = cpu_reference_run(kind, a.cpu_sample_batch, seconds, 2, 1)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

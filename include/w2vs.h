@@ -1,0 +1,194 @@
+/*
+ * w2vs.h -- C ABI of the B200-native wav2vec-S streaming-encoder forward path.
+ *
+ * This is the drop-in boundary for ONE hot path of biaofuxmu/wav2vec-S: the encoder forward
+ *   waveform -> 7x strided Conv1d (+GroupNorm/LayerNorm, GELU) -> LayerNorm -> Linear ->
+ *   positional embedding -> block/chunk-masked Transformer encoder
+ * in full-utterance mode (w2vs_encode) and chunk-by-chunk incremental mode (w2vs_stream_*).
+ * Reference interfaces replaced (paths relative to the reference repository root):
+ *   fairseq/fairseq/models/wav2vec/wav2vec2.py:544-603,667-669   Wav2Vec2Model.forward / extract_features
+ *   fairseq/fairseq/models/wav2vec/wav2vec2.py:773-781           ConvFeatureExtractionModel.forward
+ *   fairseq/fairseq/models/wav2vec/wav2vec_S.py:355-440,444-489  BlockwiseTransformerEncoder / gen_block_attn_mask
+ *   rain/layers/unidirect_w2v2_encoder.py:485-531,254-330        BlockWiseWav2Vec2Model.forward
+ *   rain/simul/transducer_agent.py:138-167                       OnlineModels.fwd_encoder (streaming driver)
+ *
+ * Conventions follow the reference's own native precedent (warp_transducer/include/rnnt.h):
+ * extern "C", an int status enum, the CUDA stream passed by the caller, caller-owned workspace
+ * sized by *_size() queries, and no device allocation, no host synchronisation and no global
+ * state inside the library.  All pointers named `d_*` are device pointers; everything else is
+ * host memory.  The library is re-entrant per (stream, workspace, state).
+ */
+#ifndef W2VS_H_
+#define W2VS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define W2VS_MAX_CONV 8
+#define W2VS_ABI_VERSION 1
+
+typedef enum {
+  W2VS_OK = 0,
+  W2VS_INVALID_VALUE = 1,      /* bad shape / config / NULL pointer; nothing was launched */
+  W2VS_UNSUPPORTED = 2,        /* valid reference config this build does not implement */
+  W2VS_WORKSPACE_TOO_SMALL = 3,
+  W2VS_CUDA_ERROR = 4          /* a launch or driver call failed */
+} w2vs_status_t;
+
+typedef enum { W2VS_F32 = 0, W2VS_BF16 = 1 } w2vs_dtype_t;
+typedef enum { W2VS_EXTRACTOR_DEFAULT = 0, W2VS_EXTRACTOR_LAYER_NORM = 1 } w2vs_extractor_mode_t;
+typedef enum { W2VS_POS_SIN = 0, W2VS_POS_CONV = 1 } w2vs_pos_type_t;
+typedef enum { W2VS_LAYOUT_BTD = 0, W2VS_LAYOUT_TBD = 1 } w2vs_layout_t;
+
+/* Model hyper-parameters; field meaning = the reference config fields of the same name
+ * (Wav2VecSConfig, wav2vec_S.py:43-311). */
+typedef struct {
+  int32_t abi_version;                 /* W2VS_ABI_VERSION */
+  int32_t dtype;                       /* w2vs_dtype_t: arithmetic/activation type of the model */
+  int32_t n_conv;                      /* conv_feature_layers */
+  int32_t conv_dim[W2VS_MAX_CONV];
+  int32_t conv_kernel[W2VS_MAX_CONV];
+  int32_t conv_stride[W2VS_MAX_CONV];
+  int32_t conv_bias;                   /* conv_bias */
+  int32_t extractor_mode;              /* w2vs_extractor_mode_t */
+  int32_t layer_norm_num;              /* wav2vec2.py:317: 1 if encoder_layers==12 else 7 */
+  int32_t embed_dim;                   /* encoder_embed_dim */
+  int32_t ffn_dim;                     /* encoder_ffn_embed_dim */
+  int32_t heads;                       /* encoder_attention_heads */
+  int32_t layers;                      /* encoder_layers */
+  int32_t layer_norm_first;            /* 1 = pre-LN (large), 0 = post-LN (base) */
+  int32_t pos_type;                    /* w2vs_pos_type_t */
+  int32_t conv_pos;                    /* kernel of the positional conv (128) */
+  int32_t conv_pos_groups;             /* 16 */
+  int32_t seq_multiple;                /* required_seq_len_multiple (2) */
+  int32_t sin_rows;                    /* rows of the sinusoidal table handed to pack (>= T+2) */
+  int32_t reserved[7];
+} w2vs_config;
+
+/* ---- reference tensors handed to w2vs_weights_pack -------------------------------------
+ * fp32 device tensors in the reference's own state_dict layout, in this order
+ * (key names: SURVEY.md section 8(a)#1; absent optional tensors are skipped, not NULL-padded):
+ *   for i in 0..n_conv-1:  feature_extractor.conv_layers.{i}.0.weight [C_out,C_in,k]
+ *                          [.0.bias [C_out]]                       if conv_bias
+ *                          [norm .weight,.bias [C_out]]            LayerNorm (.2.1) if layer_norm mode and
+ *                                                                  i < layer_norm_num; GroupNorm (.2) if default mode and i==0
+ *   layer_norm.weight, layer_norm.bias [C_last]
+ *   [post_extract_proj.weight [D,C_last], .bias [D]]              if C_last != D
+ *   pos_type==SIN : sinusoidal table [sin_rows, D] (sinusoidal_positional_embedding.py:36-59)
+ *   pos_type==CONV: encoder.pos_conv.0.bias [D], .weight_g [1,1,k], .weight_v [D,D/groups,k]
+ *   for n in 0..layers-1:  self_attn.{q,k,v,out}_proj.{weight [D,D], bias [D]}  (q,k,v,out order)
+ *                          self_attn_layer_norm.{weight,bias}, fc1.{weight [F,D],bias}, fc2.{weight [D,F],bias},
+ *                          final_layer_norm.{weight,bias}
+ *   encoder.layer_norm.weight, .bias [D]
+ */
+int32_t w2vs_num_ref_tensors(const w2vs_config* cfg);
+w2vs_status_t w2vs_packed_weights_size(const w2vs_config* cfg, size_t* bytes);
+/* Repack (transpose conv taps to K-major, concatenate q/k/v, fold weight-norm, cast) on `stream`. */
+w2vs_status_t w2vs_weights_pack(const w2vs_config* cfg, const void* const* d_ref_tensors,
+                                int32_t n_tensors, void* d_packed, size_t packed_bytes,
+                                void* stream);
+
+/* ---- derived integer geometry (bit-exact; host only) -----------------------------------
+ * frames       T  = conv stack output length for L samples (wav2vec2.py:725, no padding)
+ * frames_pad   T' = T rounded up to seq_multiple            (wav2vec_S.py:375-385)
+ * tokens       M  = T' + (T'/main)*rc                        (wav2vec_S.py:444-489)          */
+typedef struct {
+  int32_t frames, frames_pad, n_blocks, tokens;
+  int32_t conv_len[W2VS_MAX_CONV];     /* valid rows per conv layer */
+  int32_t conv_rows[W2VS_MAX_CONV];    /* allocated rows per utterance per layer (>= conv_len) */
+} w2vs_geometry;
+w2vs_status_t w2vs_geometry_of(const w2vs_config* cfg, int32_t L, int32_t main_ctx,
+                               int32_t right_ctx, w2vs_geometry* out);
+
+/* ---- full-utterance forward -------------------------------------------------------------- */
+typedef struct {
+  const void* d_wav;            /* [B, L] samples, row stride L; dtype wav_dtype */
+  int32_t wav_dtype;            /* w2vs_dtype_t */
+  int32_t B, L;
+  /* padding: at most one of d_lengths / d_sample_pad_mask non-NULL; both NULL = no padding mask
+   * (padding_mask=None in the reference). mask_len = padding_mask.size(1) (normally L). */
+  const int32_t* d_lengths;         /* [B] valid samples: mask[b,i] = i >= len_b (data_utils.py:528-532) */
+  const uint8_t* d_sample_pad_mask; /* [B, mask_len] 1 = padding */
+  int32_t mask_len;
+  int32_t main_ctx, right_ctx;  /* block size and look-ahead, in frames */
+  int32_t out_layout;           /* w2vs_layout_t: BTD = fairseq extract_features, TBD = rain forward */
+  int32_t drop_tail_frames;     /* rain is_infer && !finished: right_ctx, else 0 (rain :326-328) */
+  void* d_out;                  /* [B,T_out,D] or [T_out,B,D], dtype = cfg.dtype; T_out = T - drop_tail_frames */
+  uint8_t* d_out_pad_mask;      /* [B, T_out] 1 = padded frame (may be NULL) */
+  /* optional per-stage taps for parity tests (fp32, any may be NULL) */
+  float* d_tap_conv_out;        /* [B, T, C_last] output of the conv stack, channels-last */
+  float* d_tap_post_proj;       /* [B, T, D] after LayerNorm + post_extract_proj */
+  float* d_tap_enc_in;          /* [B, M, D] tokens entering layer 0 (incl. rc copies) */
+  float* d_tap_layers;          /* [layers, B, M, D] residual stream after each layer */
+} w2vs_encode_args;
+
+w2vs_status_t w2vs_get_workspace_size(const w2vs_config* cfg, int32_t B, int32_t L,
+                                      int32_t main_ctx, int32_t right_ctx, size_t* bytes);
+w2vs_status_t w2vs_encode(const w2vs_config* cfg, const void* d_packed_weights,
+                          const w2vs_encode_args* args, void* d_workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* ---- incremental (chunk-by-chunk) forward with cached left context ------------------------
+ * Exact for pos_type=SIN and extractor_mode=LAYER_NORM; other modes
+ * return W2VS_UNSUPPORTED.  B streams advance in lock-step.  Host-side bookkeeping lives in the
+ * caller-owned `host_state` blob, device-side caches in `d_state`. */
+w2vs_status_t w2vs_stream_state_size(const w2vs_config* cfg, int32_t B, int32_t max_frames,
+                                     int32_t max_new_samples, int32_t main_ctx, int32_t right_ctx,
+                                     size_t* host_bytes, size_t* device_bytes,
+                                     size_t* workspace_bytes);
+w2vs_status_t w2vs_stream_init(const w2vs_config* cfg, int32_t B, int32_t max_frames,
+                               int32_t max_new_samples, int32_t main_ctx, int32_t right_ctx,
+                               void* host_state, size_t host_bytes, void* d_state,
+                               size_t device_bytes, void* stream);
+/* Feed n_new samples per stream (d_new_samples [B, n_new], dtype wav_dtype).  Emits every frame
+ * that became final: *n_out frames written to d_out_frames [n_out, B, D] (TBD, dtype cfg.dtype).
+ * finished != 0 flushes the trailing partial block (rain finished=True). */
+w2vs_status_t w2vs_stream_step(const w2vs_config* cfg, const void* d_packed_weights,
+                               void* host_state, void* d_state, const void* d_new_samples,
+                               int32_t wav_dtype, int32_t n_new, int32_t finished,
+                               void* d_out_frames, int32_t out_capacity_frames, int32_t* n_out,
+                               void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---- single operators (unit-test surface for the kernels; same code the forward uses) ------ */
+typedef enum { W2VS_GEMM_AUTO = 0, W2VS_GEMM_SIMT = 1, W2VS_GEMM_TCGEN05 = 2 } w2vs_gemm_impl_t;
+#define W2VS_EPI_GELU 1
+/* C[M,N] = A[M,K] . W[N,K]^T + bias (+GELU) (+residual fp32, may alias C when C is fp32).
+ * dtype_ab = dtype of A and W; dtype_c = dtype of C. lda/ldc in elements; lda may be < K*...
+ * (overlapping rows: the strided-conv-as-GEMM view). */
+w2vs_status_t w2vs_op_gemm(int32_t impl, int32_t dtype_ab, int32_t dtype_c, const void* d_A,
+                           int64_t lda, const void* d_W, const float* d_bias,
+                           const float* d_residual, void* d_C, int64_t ldc, int32_t M, int32_t N,
+                           int32_t K, int32_t epilogue_flags, void* stream);
+/* Row LayerNorm over N (eps 1e-5): y = LN(x)*gamma+beta, optional GELU; writes fp32 and/or
+ * `dtype_act` copies. */
+w2vs_status_t w2vs_op_layernorm(int32_t dtype_in, const void* d_x, int64_t ldx, const float* d_gamma,
+                                const float* d_beta, float* d_out_f32, int32_t dtype_act,
+                                void* d_out_act, int64_t ldo, int32_t rows, int32_t N,
+                                int32_t gelu, void* stream);
+/* Block-masked attention over a token buffer qkv [B, M, 3D] (q|k|v), M = T' + (T'/main)*rc,
+ * key padding [B, M] (1 = masked with -inf).  ctx [B, M, D]. impl: 0 auto, 1 SIMT, 2 tensor-core. */
+w2vs_status_t w2vs_op_attention(int32_t impl, int32_t dtype, const void* d_qkv,
+                                const uint8_t* d_keypad, void* d_ctx, int32_t B, int32_t T_pad,
+                                int32_t main_ctx, int32_t right_ctx, int32_t heads, int32_t D,
+                                void* stream);
+
+const char* w2vs_status_string(int32_t status);
+/* Last CUDA error string recorded on this host thread by a failing call (diagnostics only). */
+const char* w2vs_last_error(void);
+/* Number of kernel launches issued by this host thread since the last reset (bench accounting). */
+int64_t w2vs_launch_count(int32_t reset);
+
+/* Per-launch device timing for bench.py (diagnostics; off by default).  w2vs_prof_enable(1, stream)
+ * starts recording one CUDA event after every launch issued by this host thread; w2vs_prof_collect
+ * waits for them and writes "kernel_name milliseconds launches" lines. */
+void w2vs_prof_enable(int32_t on, void* stream);
+int64_t w2vs_prof_collect(char* buf, int64_t capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* W2VS_H_ */

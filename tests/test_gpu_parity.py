@@ -1,0 +1,124 @@
+"""GPU parity: the CUDA path (through the reference-shaped host classes and the C ABI) against
+(a) golden vectors produced by the unmodified reference and (b) the oracle's per-stage taps, on
+the seeded cases of oracle/cases.py.  Tolerances are the ones BASELINE.json states: max-abs-rel
+1e-4 in fp32 mode, 2e-2 in bf16 mode; bool/int structure bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import wav2vec_s_b200 as W
+from oracle import cases
+from oracle import w2vs_oracle as O
+from helpers import load_golden, case_inputs, valid_rel_err
+
+pytestmark = pytest.mark.gpu
+FP32_TOL = 1e-4
+BF16_TOL = 2e-2
+
+FAIRSEQ = [n for n, c in cases.CASES.items() if c.get("api", "fairseq") == "fairseq"]
+RAIN = [n for n, c in cases.CASES.items() if c.get("api") == "rain"]
+
+
+def build(cls, cfg, sd, dtype):
+    m = cls(cfg)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and set(missing) <= {"mask_emb"}
+    return m.to("cuda", dtype).eval()
+
+
+@pytest.mark.parametrize("name", FAIRSEQ)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_extract_features_vs_reference_golden(name, dtype):
+    g = load_golden(name)
+    cfg, sd, wav, pm, _ = case_inputs(name)
+    m = build(W.Wav2VecSModel, cfg, sd, dtype)
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    taps = {}
+    src = wav.cuda().to(dtype)
+    y, fm = m._encode(src, padding_mask=None if pm is None else pm.cuda(), taps=taps)
+    y2, fm2 = m.extract_features(src, None if pm is None else pm.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(y, y2)
+    assert tuple(y.shape) == g["y"].shape and y.dtype == dtype
+    if g["fmask"].size:
+        assert np.array_equal(fm.cpu().numpy(), g["fmask"])       # bit exact
+        assert np.array_equal(fm2.cpu().numpy(), g["fmask"])
+    else:
+        assert fm is None and fm2 is None
+    fmask = g["fmask"]
+    # stage by stage, so a failure names the stage
+    conv_ref = torch.from_numpy(g["conv_out"]).transpose(1, 2)    # [B,T,C]
+    assert valid_rel_err(taps["conv_out"].cpu(), conv_ref) < tol, "conv stack"
+    if "post_proj" in g:
+        assert valid_rel_err(taps["post_proj"].cpu(), g["post_proj"], fmask) < tol, "post_extract_proj"
+    T2 = m.geometry(wav.size(1)).frames_pad
+    l0 = taps["layers"][0, :, :T2].cpu().transpose(0, 1)           # [T2,B,D] like the reference hook
+    l0_ref = torch.from_numpy(g["layer0"])[:T2]
+    fm_t2 = None
+    if fmask.size:
+        fm_t2 = np.pad(fmask, ((0, 0), (0, T2 - fmask.shape[1])), constant_values=True)
+    elif T2 != g["y"].shape[1]:
+        fm_t2 = np.zeros((y.size(0), T2), dtype=bool)
+        fm_t2[:, g["y"].shape[1]:] = True
+    assert valid_rel_err(l0, l0_ref, fm_t2, time_first=True) < tol, "encoder layer 0"
+    assert valid_rel_err(y.cpu(), g["y"], fmask) < tol, "encoder output"
+
+
+@pytest.mark.parametrize("name", FAIRSEQ)
+def test_all_layers_vs_oracle_fp32(name):
+    """Every layer's residual stream (main tokens) against the oracle, fp32."""
+    cfg, sd, wav, pm, _ = case_inputs(name)
+    m = build(W.Wav2VecSModel, cfg, sd, torch.float32)
+    taps, otaps = {}, {}
+    y, fm = m._encode(wav.cuda(), padding_mask=None if pm is None else pm.cuda(), taps=taps)
+    yo, fmo = O.extract_features(sd, cfg, wav, pm, taps=otaps)
+    T2 = otaps["enc_in"].size(0)
+    fm_t2 = None
+    if fmo is not None:
+        fm_t2 = torch.nn.functional.pad(fmo, (0, T2 - fmo.size(1)), value=True).numpy()
+    elif T2 != yo.size(1):
+        fm_t2 = np.zeros((yo.size(0), T2), dtype=bool)
+        fm_t2[:, yo.size(1):] = True
+    assert valid_rel_err(taps["enc_in"][:, :T2].cpu().transpose(0, 1), otaps["enc_in"], fm_t2, time_first=True) < FP32_TOL
+    for n in range(cfg["encoder_layers"]):
+        ours = taps["layers"][n, :, :T2].cpu().transpose(0, 1)
+        assert valid_rel_err(ours, otaps[f"layer{n}"], fm_t2, time_first=True) < FP32_TOL, f"layer {n}"
+    assert valid_rel_err(y.cpu(), yo, None if fmo is None else fmo.numpy()) < FP32_TOL
+
+
+@pytest.mark.parametrize("name", RAIN)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_rain_forward_vs_reference_golden(name, dtype):
+    g = load_golden(name)
+    cfg, sd, wav, pm, lens = case_inputs(name)
+    m = build(W.BlockWiseWav2Vec2Model, cfg, sd, dtype)
+    kw = cases.CASES[name].get("kwargs", {})
+    out = m(wav.cuda().to(dtype), None if pm is None else pm.cuda(), **kw)
+    y, fm = out["encoder_out"][0], out["encoder_padding_mask"][0]
+    assert tuple(y.shape) == g["y"].shape
+    assert np.array_equal(fm.cpu().numpy(), g["fmask"])
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    assert valid_rel_err(y.cpu(), g["y"], g["fmask"], time_first=True) < tol
+    assert set(out) == {"encoder_out", "encoder_padding_mask", "encoder_embedding", "encoder_states",
+                        "src_tokens", "src_lengths", "dec1_state", "dec1_padding_mask"}
+    if lens is not None:
+        # length-based entry (OnlineW2V2TransformerEncoder.forward) gives the same bits as the mask entry
+        out2 = m(wav.cuda().to(dtype), None, src_lengths=lens.cuda(), mask_len=int(lens.max()), **kw)
+        assert torch.equal(out2["encoder_out"][0], y)
+        assert torch.equal(out2["encoder_padding_mask"][0], fm)
+
+
+def test_sample_mask_and_lengths_agree_with_arbitrary_mask():
+    """A sample mask that is not a pure length mask (holes) still follows view(B,T,-1).all(-1)."""
+    cfg = cases.tiny()
+    sd = __import__("oracle.synth", fromlist=["x"]).make_state_dict(cfg, 3)
+    m = build(W.Wav2VecSModel, cfg, sd, torch.float32)
+    g = torch.Generator().manual_seed(5)
+    wav = torch.randn(2, 9001, generator=g)
+    pm = torch.zeros(2, 9001, dtype=torch.bool)
+    pm[0, 7000:] = True
+    pm[1, 5000:5400] = True       # hole in the middle
+    y, fm = m.extract_features(wav.cuda(), pm.cuda())
+    yo, fmo = O.extract_features(sd, cfg, wav, pm)
+    assert torch.equal(fm.cpu(), fmo)
+    assert valid_rel_err(y.cpu(), yo, fmo.numpy()) < FP32_TOL

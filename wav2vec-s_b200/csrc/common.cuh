@@ -1,0 +1,117 @@
+// Shared device/host helpers for the wav2vec-S sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/w2vs.h"
+
+typedef __nv_bfloat16 bf16;
+
+namespace w2vs {
+
+// ---- per-thread diagnostics ------------------------------------------------------------------
+extern thread_local char g_last_error[512];
+extern thread_local int64_t g_launch_count;
+void set_error(const char* fmt, ...);
+// Optional per-launch device timing (w2vs_prof_*): when enabled on this host thread, every launch is
+// followed by an event record on its stream; consecutive events bracket one kernel.
+extern thread_local bool g_prof_on;
+void prof_mark(const char* what, cudaStream_t st);
+
+#define W2VS_CHECK_LAUNCH(what)                                                        \
+  do {                                                                                 \
+    ++::w2vs::g_launch_count;                                                          \
+    if (::w2vs::g_prof_on) ::w2vs::prof_mark(what, st);                                \
+    cudaError_t e__ = cudaGetLastError();                                              \
+    if (e__ != cudaSuccess) {                                                          \
+      ::w2vs::set_error("%s: %s (%s:%d)", what, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return W2VS_CUDA_ERROR;                                                          \
+    }                                                                                  \
+  } while (0)
+
+#define W2VS_TRY(expr)                      \
+  do {                                      \
+    w2vs_status_t s__ = (expr);             \
+    if (s__ != W2VS_OK) return s__;         \
+  } while (0)
+
+#define W2VS_REQUIRE(cond, msg)                                         \
+  do {                                                                  \
+    if (!(cond)) {                                                      \
+      ::w2vs::set_error("invalid value: %s (%s)", msg, #cond);          \
+      return W2VS_INVALID_VALUE;                                        \
+    }                                                                   \
+  } while (0)
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- dtype helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 p = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(p);
+}
+
+// 8 consecutive elements <-> 8 floats (16 B of bf16 or 32 B of fp32); pointers must be aligned.
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// ---- math --------------------------------------------------------------------------------------
+// erf GELU, x * Phi(x) (torch nn.GELU / fairseq modules/gelu.py:24-25).  erf by Abramowitz-Stegun
+// 7.1.26 (|abs err| <= 1.5e-7) with one MUFU.RCP + one MUFU.EX2: about half the instructions of
+// erff(), which matters because GELU runs in GEMM epilogues that must keep pace with tcgen05.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = exp2f(-z * z * 1.4426950408889634f);
+  const float erf_abs = fmaf(-p, e, 1.0f);          // erf(|x|/sqrt2)
+  const float phi2 = 1.0f + copysignf(erf_abs, x);  // 1 + erf(x/sqrt2)
+  return 0.5f * x * phi2;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace w2vs

@@ -1,0 +1,254 @@
+// Block-mask-aware fused attention on the tensor cores (bf16 operands, fp32 softmax/accumulate).
+//
+// Same contract as k_attn_simt.cu (MultiheadAttention fast path + gen_block_attn_mask,
+// modules/multihead_attention.py:162-194, wav2vec_S.py:444-489): token buffer qkv [B, M, 3D],
+// M = T' + nb*rc, mask derived from (T', main, rc) and the key-padding bytes; key tiles that are
+// invisible to a whole query tile are never loaded.
+//
+// Flash-style schedule: one CTA = 64 query tokens of one (utterance, head), 4 warps x 16 rows.  K/V
+// tiles of 64 keys stream through a 2-stage cp.async pipeline into XOR-swizzled shared memory,
+// S = Q K^T and O += P V run as mma.sync.m16n8k16 (ldmatrix-fed), the running max / sum live in
+// registers.  Query tiles are issued heaviest-first (late blocks see the most keys).
+#include <math.h>
+#include <limits.h>
+#include "common.cuh"
+#include "kernels.h"
+
+namespace w2vs {
+namespace {
+
+constexpr int QT = 64, KT = 64, HD = 64;
+constexpr int TILE_ELEMS = 64 * 64;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// element offset of (row, 16-byte chunk) inside a 64 x 64 bf16 tile with the chunk index XOR-swizzled
+__device__ __forceinline__ int sw(int row, int chunk) { return row * 64 + ((chunk ^ (row & 7)) << 3); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// 64 rows x 128 B from a strided global matrix into a swizzled tile; rows >= n_rows are zero-filled
+__device__ __forceinline__ void load_tile_async(bf16* tile, const bf16* src, int64_t row_stride, int first_row,
+                                                int n_rows, int tid) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int c = tid + 128 * r;
+    const int row = c >> 3, chunk = c & 7;
+    const bool ok = row < n_rows;
+    const bf16* g = src + (size_t)(first_row + (ok ? row : 0)) * row_stride + chunk * 8;
+    cp_async16(smem_addr(tile + sw(row, chunk)), g, ok);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+attn_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ keypad, bf16* __restrict__ ctx,
+                int T2, int M, int main_ctx, int rc, int D, int n_main_tiles, int n_tiles, float scale_log2) {
+  __shared__ __align__(128) bf16 Qs[TILE_ELEMS];
+  __shared__ __align__(128) bf16 Ks[2][TILE_ELEMS];
+  __shared__ __align__(128) bf16 Vs[2][TILE_ELEMS];
+  __shared__ int s_kinfo[2][KT];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int tile_id = n_tiles - 1 - (int)blockIdx.x;  // heaviest first
+  const int nb = T2 / main_ctx;
+  const int rcd = rc > 0 ? rc : 1;
+  const int64_t rs = 3 * (int64_t)D;
+  const bf16* qbase = qkv + (size_t)b * M * rs + (size_t)h * HD;
+  const bf16* kbase = qbase + D;
+  const bf16* vbase = qbase + 2 * D;
+  const uint8_t* kp = keypad + (size_t)b * M;
+
+  int q_first, q_count;
+  if (tile_id < n_main_tiles) { q_first = tile_id * QT; q_count = min(QT, T2 - q_first); }
+  else { q_first = T2 + (tile_id - n_main_tiles) * QT; q_count = min(QT, M - q_first); }
+  auto qblock = [&](int m) { return m < T2 ? m / main_ctx : (m - T2) / rcd; };
+  const int qb_lo = qblock(q_first), qb_hi = qblock(q_first + q_count - 1);
+  const int seg0_end = min(main_ctx * (qb_hi + 1), T2);
+  int seg1_begin = 0, seg1_end = 0;
+  if (rc > 0 && qb_lo <= nb - 1) { seg1_begin = T2 + rc * qb_lo; seg1_end = T2 + rc * (min(qb_hi, nb - 1) + 1); }
+  const int n0 = (seg0_end + KT - 1) / KT;
+  const int n1 = (seg1_end - seg1_begin + KT - 1) / KT;
+  const int n_kt = n0 + n1;
+
+  auto issue_tile = [&](int it, int buf) {
+    const bool s1 = it >= n0;
+    const int k0 = s1 ? seg1_begin + (it - n0) * KT : it * KT;
+    const int cnt = min(KT, (s1 ? seg1_end : seg0_end) - k0);
+    load_tile_async(Ks[buf], kbase, rs, k0, cnt, tid);
+    load_tile_async(Vs[buf], vbase, rs, k0, cnt, tid);
+    if (tid < KT) {
+      int info;
+      if (tid < cnt && !kp[k0 + tid]) info = s1 ? (k0 + tid - T2) / rcd : (k0 + tid) / main_ctx;
+      else info = s1 ? -2 : INT_MAX;
+      s_kinfo[buf][tid] = info;
+    }
+  };
+
+  load_tile_async(Qs, qbase, rs, q_first, q_count, tid);
+  issue_tile(0, 0);
+  cp_async_commit();
+
+  // this thread's two query rows: warp*16 + g and + 8
+  const int r0 = warp * 16 + g, r1 = r0 + 8;
+  const int qb0 = r0 < q_count ? qblock(q_first + r0) : -1;
+  const int qb1 = r1 < q_count ? qblock(q_first + r1) : -1;
+
+  uint32_t qf[4][4];
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  for (int it = 0; it < n_kt; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < n_kt) {
+      issue_tile(it + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (it == 0) {
+      const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) ldsm_x4(smem_addr(Qs + sw(row, kk * 2 + (lane >> 4))), qf[kk]);
+    }
+    const bool seg1 = it >= n0;
+
+    // ---- S = Q K^T : 16 x 64 per warp
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        uint32_t kf[4];
+        const int mi = lane >> 3;
+        const int row = jp * 16 + (lane & 7) + (mi >> 1) * 8;
+        ldsm_x4(smem_addr(Ks[buf] + sw(row, kk * 2 + (mi & 1))), kf);
+        mma_bf16(s[2 * jp], qf[kk], kf[0], kf[1]);
+        mma_bf16(s[2 * jp + 1], qf[kk], kf[2], kf[3]);
+      }
+    }
+    // ---- mask + online softmax
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int ki = s_kinfo[buf][j * 8 + 2 * t4 + e];
+        const bool v0 = seg1 ? (ki == qb0) : (ki <= qb0);
+        const bool v1 = seg1 ? (ki == qb1) : (ki <= qb1);
+        s[j][e] = v0 ? s[j][e] : -INFINITY;
+        s[j][2 + e] = v1 ? s[j][2 + e] : -INFINITY;
+        mx0 = fmaxf(mx0, s[j][e]);
+        mx1 = fmaxf(mx1, s[j][2 + e]);
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float ms0 = mn0 == -INFINITY ? 0.f : mn0 * scale_log2;
+    const float ms1 = mn1 == -INFINITY ? 0.f : mn1 * scale_log2;
+    const float a0 = exp2f(m0 * scale_log2 - ms0), a1 = exp2f(m1 * scale_log2 - ms1);
+    m0 = mn0; m1 = mn1;
+    float sum0 = 0.f, sum1 = 0.f;
+    uint32_t pf[8][2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float p0 = exp2f(fmaf(s[j][0], scale_log2, -ms0)), p1 = exp2f(fmaf(s[j][1], scale_log2, -ms0));
+      const float p2 = exp2f(fmaf(s[j][2], scale_log2, -ms1)), p3 = exp2f(fmaf(s[j][3], scale_log2, -ms1));
+      sum0 += p0 + p1;
+      sum1 += p2 + p3;
+      pf[j][0] = pack_bf16x2(p0, p1);
+      pf[j][1] = pack_bf16x2(p2, p3);
+    }
+    l0 = l0 * a0 + sum0;
+    l1 = l1 * a1 + sum1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o[j][0] *= a0; o[j][1] *= a0; o[j][2] *= a1; o[j][3] *= a1; }
+
+    // ---- O += P V : keys are the contraction dimension
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const uint32_t af[4] = {pf[2 * kk][0], pf[2 * kk][1], pf[2 * kk + 1][0], pf[2 * kk + 1][1]};
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        uint32_t vf[4];
+        const int mi = lane >> 3;
+        const int row = kk * 16 + (lane & 7) + (mi & 1) * 8;
+        ldsm_x4_trans(smem_addr(Vs[buf] + sw(row, jp * 2 + (mi >> 1))), vf);
+        mma_bf16(o[2 * jp], af, vf[0], vf[1]);
+        mma_bf16(o[2 * jp + 1], af, vf[2], vf[3]);
+      }
+    }
+    __syncthreads();  // tile `buf` fully consumed before the next iteration's prefetch overwrites it
+  }
+
+  // ---- normalise, stage through this warp's 16 rows of Qs, 16-byte coalesced stores
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = l0 > 0.f ? 1.0f / l0 : 0.f, i1 = l1 > 0.f ? 1.0f / l1 : 0.f;
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    // columns j*8 + 2*t4, +1  -> chunk j, element offset 2*t4 inside the chunk
+    *reinterpret_cast<uint32_t*>(Qs + sw(r0, j) + 2 * t4) = pack_bf16x2(o[j][0] * i0, o[j][1] * i0);
+    *reinterpret_cast<uint32_t*>(Qs + sw(r1, j) + 2 * t4) = pack_bf16x2(o[j][2] * i1, o[j][3] * i1);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int c = lane + 32 * r;
+    const int row = warp * 16 + (c >> 3), chunk = c & 7;
+    if (row < q_count) {
+      const uint4 v = *reinterpret_cast<const uint4*>(Qs + sw(row, chunk));
+      *reinterpret_cast<uint4*>(ctx + ((size_t)b * M + q_first + row) * D + (size_t)h * HD + chunk * 8) = v;
+    }
+  }
+}
+}  // namespace
+
+w2vs_status_t launch_attention_mma(const AttnArgs& a, cudaStream_t st) {
+  W2VS_REQUIRE(a.D == a.heads * HD, "attention head_dim must be 64");
+  W2VS_REQUIRE(a.D % 8 == 0, "attention D alignment");
+  const int M = a.T2 + (a.rc > 0 ? (a.T2 / a.main_ctx) * a.rc : 0);
+  const int n_main = (a.T2 + QT - 1) / QT, n_rc = (M - a.T2 + QT - 1) / QT;
+  dim3 grid((unsigned)(n_main + n_rc), (unsigned)a.heads, (unsigned)a.B);
+  const float scale_log2 = (1.0f / sqrtf((float)HD)) * 1.4426950408889634f;
+  attn_mma_kernel<<<grid, 128, 0, st>>>((const bf16*)a.qkv, a.keypad, (bf16*)a.ctx, a.T2, M, a.main_ctx, a.rc,
+                                        a.D, n_main, n_main + n_rc, scale_log2);
+  W2VS_CHECK_LAUNCH("attn_mma_kernel");
+  return W2VS_OK;
+}
+
+}  // namespace w2vs

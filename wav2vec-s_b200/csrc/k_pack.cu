@@ -1,0 +1,118 @@
+// Weight repacking (run once per load_state_dict) and the optional convolutional positional
+// embedding (pos_type="conv": wav2vec2.py:791-804; not used by the released wav2vec-S models, kept for
+// API completeness as a straightforward direct kernel).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace w2vs {
+namespace {
+
+template <typename TOut>
+__global__ void pack_copy_kernel(const float* __restrict__ src, TOut* __restrict__ dst, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = from_f32<TOut>(src[i]);
+}
+
+// Conv1d weight [C_out, C_in, k] -> K-major GEMM operand [C_out][j*C_in + ci]
+template <typename TOut>
+__global__ void pack_conv_kernel(const float* __restrict__ src, TOut* __restrict__ dst, int C_out, int C_in, int k) {
+  const int64_t n = (int64_t)C_out * C_in * k;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % C_in);
+    const int j = (int)((i / C_in) % k);
+    const int co = (int)(i / ((int64_t)C_in * k));
+    dst[i] = from_f32<TOut>(src[((size_t)co * C_in + ci) * k + j]);
+  }
+}
+
+// weight_norm(dim=2): w[co,ci,j] = g[j] * v[co,ci,j] / ||v[:,:,j]||_2   (torch.nn.utils.weight_norm)
+// One CTA per tap j; output layout [group][j][ci][co_in_group] so that consecutive output channels are
+// consecutive in memory.
+__global__ void __launch_bounds__(256)
+pack_posconv_kernel(const float* __restrict__ g, const float* __restrict__ v, float* __restrict__ dst, int D,
+                    int groups, int k) {
+  __shared__ float s_red[256];
+  const int j = blockIdx.x, Dg = D / groups;
+  const int64_t n = (int64_t)D * Dg;
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += 256) { const float x = v[i * k + j]; s = fmaf(x, x, s); }
+  s_red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const float scale = g[j] / sqrtf(s_red[0]);
+  for (int64_t i = threadIdx.x; i < n; i += 256) {
+    const int ci = (int)(i % Dg), co = (int)(i / Dg);
+    const int grp = co / Dg, cog = co % Dg;
+    dst[(((size_t)grp * k + j) * Dg + ci) * Dg + cog] = v[i * k + j] * scale;
+  }
+}
+
+// y[b,t,co] = gelu(bias[co] + sum_{j<k} sum_{ci<Dg} w[g][j][ci][cog] * x[b, t + j - k/2, g*Dg + ci]),
+// x = features with padded frames zeroed; output frame T of the (even k) padded conv is dropped (SamePad).
+__global__ void __launch_bounds__(256)
+posconv_kernel(const float* __restrict__ feats, int feat_rows, const uint8_t* __restrict__ frame_pad,
+               const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out, int T,
+               int D, int k, int groups, int t_per_cta) {
+  const int Dg = D / groups;
+  const int grp = blockIdx.y, b = blockIdx.z;
+  const int t_begin = blockIdx.x * t_per_cta;
+  const int n_out = t_per_cta * Dg;
+  for (int idx = threadIdx.x; idx < n_out; idx += blockDim.x) {
+    const int cog = idx % Dg, t = t_begin + idx / Dg;
+    if (t >= T) continue;
+    float acc = bias[grp * Dg + cog];
+    for (int j = 0; j < k; ++j) {
+      const int ts = t + j - k / 2;
+      if (ts < 0 || ts >= T) continue;
+      if (frame_pad && frame_pad[(size_t)b * T + ts]) continue;
+      const float* xr = feats + ((size_t)b * feat_rows + ts) * D + grp * Dg;
+      const float* wr = w + (((size_t)grp * k + j) * Dg) * Dg + cog;
+      for (int ci = 0; ci < Dg; ++ci) acc = fmaf(wr[(size_t)ci * Dg], xr[ci], acc);
+    }
+    out[((size_t)b * T + t) * D + grp * Dg + cog] = gelu_erf(acc);
+  }
+}
+}  // namespace
+
+static int grid_for(int64_t n) {
+  int64_t g = ceil_div64(n, 256);
+  return (int)(g < 1 ? 1 : (g > 8192 ? 8192 : g));
+}
+
+w2vs_status_t launch_pack_copy(const float* src, void* dst, int dst_dtype, int64_t n, cudaStream_t st) {
+  if (n <= 0) return W2VS_OK;
+  if (dst_dtype == W2VS_F32) pack_copy_kernel<float><<<grid_for(n), 256, 0, st>>>(src, (float*)dst, n);
+  else pack_copy_kernel<bf16><<<grid_for(n), 256, 0, st>>>(src, (bf16*)dst, n);
+  W2VS_CHECK_LAUNCH("pack_copy_kernel");
+  return W2VS_OK;
+}
+
+w2vs_status_t launch_pack_conv(const float* src, void* dst, int dst_dtype, int C_out, int C_in, int k,
+                               cudaStream_t st) {
+  const int64_t n = (int64_t)C_out * C_in * k;
+  if (dst_dtype == W2VS_F32) pack_conv_kernel<float><<<grid_for(n), 256, 0, st>>>(src, (float*)dst, C_out, C_in, k);
+  else pack_conv_kernel<bf16><<<grid_for(n), 256, 0, st>>>(src, (bf16*)dst, C_out, C_in, k);
+  W2VS_CHECK_LAUNCH("pack_conv_kernel");
+  return W2VS_OK;
+}
+
+w2vs_status_t launch_pack_posconv(const float* g, const float* v, float* dst, int D, int groups, int k,
+                                  cudaStream_t st) {
+  pack_posconv_kernel<<<k, 256, 0, st>>>(g, v, dst, D, groups, k);
+  W2VS_CHECK_LAUNCH("pack_posconv_kernel");
+  return W2VS_OK;
+}
+
+w2vs_status_t launch_posconv(const PosConvArgs& a, cudaStream_t st) {
+  const int t_per_cta = 16;
+  dim3 grid((unsigned)ceil_div64(a.T, t_per_cta), (unsigned)a.groups, (unsigned)a.B);
+  posconv_kernel<<<grid, 256, 0, st>>>(a.feats, a.feat_rows, a.frame_pad, a.w, a.bias, a.out, a.T, a.D, a.k,
+                                       a.groups, t_per_cta);
+  W2VS_CHECK_LAUNCH("posconv_kernel");
+  return W2VS_OK;
+}
+
+}  // namespace w2vs

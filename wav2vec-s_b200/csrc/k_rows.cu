@@ -1,0 +1,336 @@
+// Row-wise kernels (one warp per row of N <= 2048 channels, the row lives in registers):
+//   * layernorm_rows  : LayerNorm (+GELU) -> fp32 and/or activation-dtype copies
+//                       (Fp32LayerNorm of the conv blocks, wav2vec2.py:739-745; feature LayerNorm
+//                        :556; self_attn_layer_norm / final_layer_norm :936-976)
+//   * prep_masks      : frame padding mask, sinusoidal positions, extended key-padding mask
+//                       (wav2vec2.py:560-565, utils.py:250-260, wav2vec_S.py:470-476) -- integer work,
+//                       bit-exact
+//   * embed_tokens    : zero padded frames, add positional embedding, optional encoder LayerNorm,
+//                       pad to T', append look-ahead copies (wav2vec_S.py:355-389,483-484)
+//   * finalize_rows   : drop look-ahead copies / padding, optional final LayerNorm, BTD or TBD
+//                       (wav2vec_S.py:425-440, wav2vec2.py:828-834, rain :314-330)
+#include "common.cuh"
+#include "kernels.h"
+
+namespace w2vs {
+
+// Normalise a row held as v[NCH][8] (lane owns chunks lane + 32*j of 8 consecutive channels).
+template <int NCH>
+__device__ __forceinline__ void warp_layernorm(float (&v)[NCH][8], int N, int lane,
+                                               const float* __restrict__ gamma,
+                                               const float* __restrict__ beta) {
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NCH; ++j)
+    if ((lane + 32 * j) * 8 < N) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[j][e];
+    }
+  const float mean = warp_sum(s) / (float)N;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NCH; ++j)
+    if ((lane + 32 * j) * 8 < N) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = v[j][e] - mean; q = fmaf(d, d, q); }
+    }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)N + 1e-5f);
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    const int c0 = (lane + 32 * j) * 8;
+    if (c0 < N) {
+      float g[8], bt[8];
+      load8(gamma + c0, g);
+      load8(beta + c0, bt);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[j][e] = (v[j][e] - mean) * rstd * g[e] + bt[e];
+    }
+  }
+}
+
+template <typename TIn, typename TAct, int NCH>
+__global__ void __launch_bounds__(256)
+layernorm_rows_kernel(const TIn* x, int64_t ldx, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, float* out_f32, TAct* out_act, int64_t ldo,
+                      int rows, int N, int gelu) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float v[NCH][8];
+  const TIn* xr = x + (size_t)row * ldx;
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    const int c0 = (lane + 32 * j) * 8;
+    if (c0 < N) load8(xr + c0, v[j]);
+  }
+  warp_layernorm<NCH>(v, N, lane, gamma, beta);
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    const int c0 = (lane + 32 * j) * 8;
+    if (c0 < N) {
+      if (gelu) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[j][e] = gelu_erf(v[j][e]);
+      }
+      if (out_f32) store8(out_f32 + (size_t)row * ldo + c0, v[j]);
+      if (out_act) store8(out_act + (size_t)row * ldo + c0, v[j]);
+    }
+  }
+}
+
+template <typename TIn, typename TAct>
+static w2vs_status_t ln_dispatch(const LayerNormArgs& a, cudaStream_t st) {
+  const int wpb = 8;
+  dim3 grid((unsigned)ceil_div64(a.rows, wpb));
+#define W2VS_LN_CASE(NCH)                                                                      \
+  layernorm_rows_kernel<TIn, TAct, NCH><<<grid, wpb * 32, 0, st>>>(                            \
+      (const TIn*)a.x, a.ldx, a.gamma, a.beta, a.out_f32, (TAct*)a.out_act, a.ldo, a.rows, a.N, a.gelu)
+  if (a.N <= 256) W2VS_LN_CASE(1);
+  else if (a.N <= 512) W2VS_LN_CASE(2);
+  else if (a.N <= 1024) W2VS_LN_CASE(4);
+  else W2VS_LN_CASE(8);
+#undef W2VS_LN_CASE
+  W2VS_CHECK_LAUNCH("layernorm_rows_kernel");
+  return W2VS_OK;
+}
+
+w2vs_status_t launch_layernorm(const LayerNormArgs& a, cudaStream_t st) {
+  W2VS_REQUIRE(a.N % 8 == 0 && a.N >= 8 && a.N <= 2048, "LayerNorm width must be a multiple of 8, <= 2048");
+  W2VS_REQUIRE(a.ldx % 8 == 0 && a.ldo % 8 == 0, "LayerNorm leading dims must be multiples of 8");
+  if (a.rows <= 0) return W2VS_OK;
+  if (a.in_dtype == W2VS_F32)
+    return a.act_dtype == W2VS_F32 ? ln_dispatch<float, float>(a, st) : ln_dispatch<float, bf16>(a, st);
+  return a.act_dtype == W2VS_F32 ? ln_dispatch<bf16, float>(a, st) : ln_dispatch<bf16, bf16>(a, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// prep_masks: one CTA per utterance.
+//   frame_pad[b,t] = all(mask[b, t*w : (t+1)*w]),  w = mask_len / T       (wav2vec2.py:560-565)
+//   pos[b,t]       = frame_pad ? 1 : 1 + #{t' <= t : !frame_pad[b,t']}    (utils.py:250-260, padding_idx=1)
+//   keypad[b,m]    = extended key padding over M = T2 + R tokens           (wav2vec_S.py:470-476)
+__global__ void __launch_bounds__(256)
+prep_masks_kernel(const int32_t* __restrict__ lengths, const uint8_t* __restrict__ sample_mask,
+                  int mask_len, uint8_t* __restrict__ frame_pad, int32_t* __restrict__ pos,
+                  uint8_t* __restrict__ keypad, int T, int T2, int M, int main_ctx, int rc) {
+  __shared__ int s_part[256];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int w = mask_len > 0 ? mask_len / T : 0;
+  const int seg = (T + 255) / 256;
+  const int t_lo = min(tid * seg, T), t_hi = min(t_lo + seg, T);
+  int cnt = 0;
+  for (int t = t_lo; t < t_hi; ++t) {
+    bool pad = false;
+    if (lengths) {
+      pad = (int64_t)t * w >= (int64_t)lengths[b];
+    } else if (sample_mask) {
+      pad = true;
+      const uint8_t* mrow = sample_mask + (size_t)b * mask_len + (size_t)t * w;
+      for (int i = 0; i < w; ++i)
+        if (!mrow[i]) { pad = false; break; }
+    }
+    frame_pad[(size_t)b * T + t] = pad ? 1 : 0;
+    cnt += pad ? 0 : 1;
+  }
+  s_part[tid] = cnt;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int i = 0; i < 256; ++i) { const int c = s_part[i]; s_part[i] = run; run += c; }
+  }
+  __syncthreads();
+  int run = s_part[tid];
+  for (int t = t_lo; t < t_hi; ++t) {
+    const bool pad = frame_pad[(size_t)b * T + t] != 0;
+    if (!pad) ++run;
+    pos[(size_t)b * T + t] = pad ? 1 : 1 + run;
+  }
+  __syncthreads();
+  for (int m = tid; m < M; m += 256) {
+    bool kp;
+    if (m < T2) {
+      kp = m >= T ? true : frame_pad[(size_t)b * T + m] != 0;
+    } else {
+      const int r = m - T2;
+      int src = (r / rc + 1) * main_ctx + (r % rc);
+      const bool oor = src > T2 - 1;
+      src = min(src, T2 - 1);
+      kp = oor || (src >= T ? true : frame_pad[(size_t)b * T + src] != 0);
+    }
+    keypad[(size_t)b * M + m] = kp ? 1 : 0;
+  }
+}
+
+w2vs_status_t launch_prep_masks(const PrepArgs& a, cudaStream_t st) {
+  prep_masks_kernel<<<a.B, 256, 0, st>>>(a.lengths, a.sample_mask, a.mask_len, a.frame_pad, a.pos,
+                                         a.keypad, a.T, a.T2, a.M, a.main_ctx, a.rc);
+  W2VS_CHECK_LAUNCH("prep_masks_kernel");
+  return W2VS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// embed_tokens: one warp per token (b, m).
+template <typename TAct, int NCH>
+__global__ void __launch_bounds__(256)
+embed_tokens_kernel(const float* __restrict__ feats, int feat_rows, const uint8_t* __restrict__ frame_pad,
+                    const int32_t* __restrict__ pos, int pos_offset, const float* __restrict__ sin_table,
+                    const float* __restrict__ posconv, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float* __restrict__ X, TAct* __restrict__ Xa,
+                    int B, int T, int T2, int M, int main_ctx, int rc, int D) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tok = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tok >= (int64_t)B * M) return;
+  const int b = (int)(tok / M), m = (int)(tok % M);
+  int t = m;
+  if (m >= T2) {
+    const int r = m - T2;
+    t = min((r / rc + 1) * main_ctx + (r % rc), T2 - 1);
+  }
+  float v[NCH][8];
+  const bool zero_row = t >= T;  // sequence padding added after the LayerNorm: exact zeros
+  const bool pad = !zero_row && frame_pad != nullptr && frame_pad[(size_t)b * T + t] != 0;
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    const int c0 = (lane + 32 * j) * 8;
+    if (c0 < D) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[j][e] = 0.f;
+      if (!zero_row) {
+        if (!pad) load8(feats + ((size_t)b * feat_rows + t) * D + c0, v[j]);
+        float p[8];
+        if (posconv) {
+          load8(posconv + ((size_t)b * T + t) * D + c0, p);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[j][e] += p[e];
+        } else if (!pad) {
+          const int pi = pos ? pos[(size_t)b * T + t] : t + pos_offset;
+          load8(sin_table + (size_t)pi * D + c0, p);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[j][e] += p[e];
+        }
+      }
+    }
+  }
+  if (gamma != nullptr && !zero_row) warp_layernorm<NCH>(v, D, lane, gamma, beta);
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    const int c0 = (lane + 32 * j) * 8;
+    if (c0 < D) {
+      store8(X + (size_t)tok * D + c0, v[j]);
+      if (Xa) store8(Xa + (size_t)tok * D + c0, v[j]);
+    }
+  }
+}
+
+template <typename TAct>
+static w2vs_status_t embed_dispatch(const EmbedArgs& a, cudaStream_t st) {
+  const int wpb = 8;
+  dim3 grid((unsigned)ceil_div64((int64_t)a.B * a.M, wpb));
+#define W2VS_EMB_CASE(NCH)                                                                        \
+  embed_tokens_kernel<TAct, NCH><<<grid, wpb * 32, 0, st>>>(                                      \
+      a.feats, a.feat_rows, a.frame_pad, a.pos, a.pos_offset, a.sin_table, a.posconv, a.gamma,    \
+      a.beta, a.X, (TAct*)a.Xa, a.B, a.T, a.T2, a.M, a.main_ctx, a.rc, a.D)
+  if (a.D <= 256) W2VS_EMB_CASE(1);
+  else if (a.D <= 512) W2VS_EMB_CASE(2);
+  else if (a.D <= 1024) W2VS_EMB_CASE(4);
+  else W2VS_EMB_CASE(8);
+#undef W2VS_EMB_CASE
+  W2VS_CHECK_LAUNCH("embed_tokens_kernel");
+  return W2VS_OK;
+}
+
+w2vs_status_t launch_embed(const EmbedArgs& a, cudaStream_t st) {
+  return a.act_dtype == W2VS_F32 ? embed_dispatch<float>(a, st) : embed_dispatch<bf16>(a, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize_rows: one warp per output frame (b, t), t < T_out.
+template <typename TOut, int NCH>
+__global__ void __launch_bounds__(256)
+finalize_rows_kernel(const float* __restrict__ X, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, TOut* __restrict__ out, int B, int T_out,
+                     int64_t in_rows_per_utt, int D, int tbd) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= (int64_t)B * T_out) return;
+  const int b = (int)(r / T_out), t = (int)(r % T_out);
+  float v[NCH][8];
+  const float* xr = X + ((size_t)b * in_rows_per_utt + t) * D;
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    const int c0 = (lane + 32 * j) * 8;
+    if (c0 < D) load8(xr + c0, v[j]);
+  }
+  if (gamma != nullptr) warp_layernorm<NCH>(v, D, lane, gamma, beta);
+  TOut* o = out + (tbd ? ((size_t)t * B + b) : ((size_t)b * T_out + t)) * D;
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    const int c0 = (lane + 32 * j) * 8;
+    if (c0 < D) store8(o + c0, v[j]);
+  }
+}
+
+template <typename TOut>
+static w2vs_status_t finalize_dispatch(const FinalizeArgs& a, cudaStream_t st) {
+  const int wpb = 8;
+  dim3 grid((unsigned)ceil_div64((int64_t)a.B * a.T_out, wpb));
+#define W2VS_FIN_CASE(NCH)                                                            \
+  finalize_rows_kernel<TOut, NCH><<<grid, wpb * 32, 0, st>>>(                         \
+      a.X, a.gamma, a.beta, (TOut*)a.out, a.B, a.T_out, a.in_rows_per_utt, a.D, a.tbd)
+  if (a.D <= 256) W2VS_FIN_CASE(1);
+  else if (a.D <= 512) W2VS_FIN_CASE(2);
+  else if (a.D <= 1024) W2VS_FIN_CASE(4);
+  else W2VS_FIN_CASE(8);
+#undef W2VS_FIN_CASE
+  W2VS_CHECK_LAUNCH("finalize_rows_kernel");
+  return W2VS_OK;
+}
+
+w2vs_status_t launch_finalize(const FinalizeArgs& a, cudaStream_t st) {
+  if (a.B * a.T_out <= 0) return W2VS_OK;
+  return a.out_dtype == W2VS_F32 ? finalize_dispatch<float>(a, st) : finalize_dispatch<bf16>(a, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// small utility kernels
+template <typename TIn>
+__global__ void copy_rows_to_f32_kernel(const TIn* __restrict__ src, int64_t src_rows_per_utt,
+                                        float* __restrict__ dst, int B, int T, int C) {
+  const int64_t n = (int64_t)B * T * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t bt = i / C;
+    const int t = (int)(bt % T), b = (int)(bt / T);
+    dst[i] = to_f32(src[((size_t)b * src_rows_per_utt + t) * C + c]);
+  }
+}
+
+w2vs_status_t launch_tap_rows(const void* src, int src_dtype, int64_t src_rows_per_utt, float* dst,
+                              int B, int T, int C, cudaStream_t st) {
+  const int64_t n = (int64_t)B * T * C;
+  if (n <= 0) return W2VS_OK;
+  const int grid = (int)(ceil_div64(n, 256) < 4096 ? ceil_div64(n, 256) : 4096);
+  if (src_dtype == W2VS_F32)
+    copy_rows_to_f32_kernel<float><<<grid, 256, 0, st>>>((const float*)src, src_rows_per_utt, dst, B, T, C);
+  else
+    copy_rows_to_f32_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)src, src_rows_per_utt, dst, B, T, C);
+  W2VS_CHECK_LAUNCH("copy_rows_to_f32_kernel");
+  return W2VS_OK;
+}
+
+__global__ void copy_u8_rows_kernel(const uint8_t* __restrict__ src, int src_ld, uint8_t* __restrict__ dst,
+                                    int dst_ld, int B, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * n; i += gridDim.x * blockDim.x) {
+    const int b = i / n, t = i % n;
+    dst[(size_t)b * dst_ld + t] = src[(size_t)b * src_ld + t];
+  }
+}
+
+w2vs_status_t launch_copy_mask(const uint8_t* src, int src_ld, uint8_t* dst, int dst_ld, int B, int n,
+                               cudaStream_t st) {
+  if (B * n <= 0) return W2VS_OK;
+  copy_u8_rows_kernel<<<(B * n + 255) / 256, 256, 0, st>>>(src, src_ld, dst, dst_ld, B, n);
+  W2VS_CHECK_LAUNCH("copy_u8_rows_kernel");
+  return W2VS_OK;
+}
+
+}  // namespace w2vs

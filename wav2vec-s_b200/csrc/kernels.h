@@ -1,0 +1,95 @@
+// Internal launcher interface between the C ABI (api.cu / stream.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/w2vs.h"
+
+namespace w2vs {
+
+// ---- conv0 ------------------------------------------------------------------------------------
+enum { CONV0_NORM_NONE = 0, CONV0_NORM_LAYER = 1, CONV0_NORM_GROUP = 2 };
+struct Conv0Args {
+  const void* wav; int wav_dtype; int64_t wav_ld;
+  const float *w, *bias, *gamma, *beta;
+  void* out; int out_dtype;
+  int B, T0, rows_per_utt, C, k, stride, norm;
+  double* gn_stats;
+};
+w2vs_status_t launch_conv0(const Conv0Args& a, cudaStream_t st);
+
+// ---- row kernels --------------------------------------------------------------------------------
+struct LayerNormArgs {
+  const void* x; int in_dtype; int64_t ldx;
+  const float *gamma, *beta;
+  float* out_f32; void* out_act; int act_dtype; int64_t ldo;
+  int rows, N, gelu;
+};
+w2vs_status_t launch_layernorm(const LayerNormArgs& a, cudaStream_t st);
+
+struct PrepArgs {
+  const int32_t* lengths; const uint8_t* sample_mask; int mask_len;
+  uint8_t* frame_pad; int32_t* pos; uint8_t* keypad;
+  int B, T, T2, M, main_ctx, rc;
+};
+w2vs_status_t launch_prep_masks(const PrepArgs& a, cudaStream_t st);
+
+struct EmbedArgs {
+  const float* feats; int feat_rows;          // [B*feat_rows, D]
+  const uint8_t* frame_pad; const int32_t* pos; int pos_offset;
+  const float* sin_table; const float* posconv;
+  const float *gamma, *beta;                  // encoder.layer_norm when post-LN, else NULL
+  float* X; void* Xa; int act_dtype;
+  int B, T, T2, M, main_ctx, rc, D;
+};
+w2vs_status_t launch_embed(const EmbedArgs& a, cudaStream_t st);
+
+struct FinalizeArgs {
+  const float* X; const float *gamma, *beta;
+  void* out; int out_dtype;
+  int B, T_out; int64_t in_rows_per_utt; int D, tbd;
+};
+w2vs_status_t launch_finalize(const FinalizeArgs& a, cudaStream_t st);
+
+w2vs_status_t launch_tap_rows(const void* src, int src_dtype, int64_t src_rows_per_utt, float* dst, int B,
+                              int T, int C, cudaStream_t st);
+w2vs_status_t launch_copy_mask(const uint8_t* src, int src_ld, uint8_t* dst, int dst_ld, int B, int n,
+                               cudaStream_t st);
+
+// ---- GEMM ---------------------------------------------------------------------------------------
+struct GemmArgs {
+  const void* A; int64_t lda; int64_t a_rows;   // a_rows: rows of length lda addressable behind A (TMA bound)
+  const void* W;                                // [N, K] row-major
+  const float* bias; const float* residual;     // residual fp32 [M, ldc] (may alias C)
+  void* C; int64_t ldc;
+  int M, N, K; int dtype_ab, dtype_c; int flags;
+};
+w2vs_status_t launch_gemm_simt(const GemmArgs& g, cudaStream_t st);
+w2vs_status_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
+w2vs_status_t launch_gemm(int impl, const GemmArgs& g, cudaStream_t st);  // impl: w2vs_gemm_impl_t
+w2vs_status_t debug_read_tc_fault(int* out);
+
+// ---- attention ------------------------------------------------------------------------------------
+struct AttnArgs {
+  const void* qkv; const uint8_t* keypad; void* ctx; int dtype;
+  int B, T2, main_ctx, rc, heads, D;
+};
+w2vs_status_t launch_attention_simt(const AttnArgs& a, cudaStream_t st);
+w2vs_status_t launch_attention_mma(const AttnArgs& a, cudaStream_t st);
+w2vs_status_t launch_attention(int impl, const AttnArgs& a, cudaStream_t st);
+
+// ---- positional conv + weight packing -----------------------------------------------------------------
+struct PosConvArgs {
+  const float* feats; int feat_rows; const uint8_t* frame_pad;
+  const float* w; const float* bias;            // folded weights [groups][k][Dg_in][Dg_out]
+  float* out;                                   // [B, T, D]
+  int B, T, D, k, groups;
+};
+w2vs_status_t launch_posconv(const PosConvArgs& a, cudaStream_t st);
+
+w2vs_status_t launch_pack_copy(const float* src, void* dst, int dst_dtype, int64_t n, cudaStream_t st);
+w2vs_status_t launch_pack_conv(const float* src, void* dst, int dst_dtype, int C_out, int C_in, int k,
+                               cudaStream_t st);
+w2vs_status_t launch_pack_posconv(const float* g, const float* v, float* dst, int D, int groups, int k,
+                                  cudaStream_t st);
+
+}  // namespace w2vs

@@ -1,0 +1,84 @@
+// Host-side geometry, packed-weight layout and workspace layout.  Pure integer arithmetic; every
+// number here must agree bit-for-bit with the reference's shape arithmetic.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include "../../include/w2vs.h"
+
+namespace w2vs {
+
+struct Geometry {
+  int n_conv;
+  int conv_len[W2VS_MAX_CONV];    // valid output frames per layer (wav2vec2.py:725: (t-k)/s+1)
+  int conv_rows[W2VS_MAX_CONV];   // allocated rows / utterance: rows[i-1] == stride_i * rows[i]
+  int T;                          // frames = conv_len[n_conv-1]
+  int T2;                         // frames padded to seq_multiple (pad_to_multiple, wav2vec_S.py:375)
+  int nb;                         // T2 / main (floor)   (gen_block_attn_mask, wav2vec_S.py:459)
+  int R;                          // nb * rc look-ahead copies
+  int M;                          // tokens per utterance = T2 + R
+  int main_ctx, rc;
+};
+
+w2vs_status_t validate_config(const w2vs_config* cfg);
+w2vs_status_t make_geometry(const w2vs_config* cfg, int L, int main_ctx, int rc, Geometry* g);
+
+// ---- packed weights ----------------------------------------------------------------------------
+// One blob; every offset is 256-byte aligned.  "act" tensors are stored in cfg.dtype (bf16 or fp32),
+// everything else fp32.
+struct ConvW {
+  size_t w;       // layer 0: fp32 [C0][k0];  layers >= 1: act [C_out][k*C_in] (K-major, tap-major inside K)
+  size_t bias;    // fp32 [C_out] or SIZE_MAX
+  size_t norm_w, norm_b;  // fp32 [C_out] or SIZE_MAX
+};
+struct LayerW {
+  size_t wqkv, bqkv;      // act [3D][D], fp32 [3D]
+  size_t wo, bo;          // act [D][D], fp32 [D]
+  size_t ln1_w, ln1_b;    // self_attn_layer_norm
+  size_t w1, b1;          // act [F][D], fp32 [F]
+  size_t w2, b2;          // act [D][F], fp32 [D]
+  size_t ln2_w, ln2_b;    // final_layer_norm
+};
+struct WeightLayout {
+  ConvW conv[W2VS_MAX_CONV];
+  size_t feat_ln_w, feat_ln_b;     // layer_norm [C_last]
+  size_t proj_w, proj_b;           // act [D][C_last], fp32 [D]; SIZE_MAX if C_last == D
+  size_t sin_table;                // fp32 [sin_rows][D]
+  size_t posconv_w, posconv_b;     // fp32 [groups][k][Dg_out][Dg_in] folded weight-norm, fp32 [D]
+  size_t enc_ln_w, enc_ln_b;       // encoder.layer_norm
+  size_t layers_begin;             // LayerW table is computed by layer_at()
+  size_t layer_stride;
+  LayerW layer0;                   // offsets of layer 0; layer n = layer0 + n*layer_stride
+  size_t total;
+};
+static const size_t kNone = (size_t)-1;
+void make_weight_layout(const w2vs_config* cfg, WeightLayout* wl);
+inline LayerW layer_at(const WeightLayout& wl, int n) {
+  LayerW l = wl.layer0;
+  size_t d = (size_t)n * wl.layer_stride;
+  l.wqkv += d; l.bqkv += d; l.wo += d; l.bo += d; l.ln1_w += d; l.ln1_b += d;
+  l.w1 += d; l.b1 += d; l.w2 += d; l.b2 += d; l.ln2_w += d; l.ln2_b += d;
+  return l;
+}
+
+// ---- workspace (full-utterance forward) --------------------------------------------------------
+struct Workspace {
+  size_t conv_a, conv_b;       // act ping/pong [B*rows_i + slack][C_i]
+  size_t conv_tmp;             // fp32 [B*rows_1][C] pre-LayerNorm conv output (bf16 models only)
+  size_t gn_stats;             // double [B][C0][2]
+  size_t feats;                // fp32 [B*rows_last][D]  (post_extract_proj output)
+  size_t frame_pad;            // u8 [B][T]
+  size_t pos;                  // i32 [B][T]
+  size_t keypad;               // u8 [B][M]
+  size_t x;                    // fp32 [B*M][D] residual stream
+  size_t xa;                   // act [B*M][D]
+  size_t qkv;                  // act [B*M][3D]
+  size_t ctx;                  // act [B*M][D]
+  size_t h;                    // act [B*M][F]
+  size_t posconv_tmp;          // fp32 [B][T][D]  (pos_type=conv only)
+  size_t total;
+};
+void make_workspace(const w2vs_config* cfg, const Geometry& g, int B, Workspace* ws);
+
+inline size_t act_size(const w2vs_config* cfg) { return cfg->dtype == W2VS_BF16 ? 2 : 4; }
+
+}  // namespace w2vs
