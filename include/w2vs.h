@@ -145,16 +145,35 @@ w2vs_status_t w2vs_stream_init(const w2vs_config* cfg, int32_t B, int32_t max_fr
                                void* host_state, size_t host_bytes, void* d_state,
                                size_t device_bytes, void* stream);
 /* Feed n_new samples per stream (d_new_samples [B, n_new], dtype wav_dtype).  Emits every frame
- * that became final: *n_out frames written to d_out_frames [n_out, B, D] (TBD, dtype cfg.dtype).
- * finished != 0 flushes the trailing partial block (rain finished=True). */
+ * that became final (whole blocks of main_ctx frames whose right_ctx look-ahead frames exist):
+ * *n_out frames written to d_out_frames [n_out, B, D] (TBD, dtype cfg.dtype).  `flush`:
+ *   W2VS_FLUSH_NONE   only final frames;
+ *   W2VS_FLUSH_FINAL  end of stream: also emits the trailing frames exactly as the offline encoder
+ *                     computes them on the complete utterance (rain finished=True); closes the stream;
+ *   W2VS_FLUSH_PEEK   also emits the trailing frames as the offline encoder computes them on the
+ *                     CURRENT prefix (the reference driver's prefix re-encoding, is_infer=True), without
+ *                     committing them: the next call recomputes them with more context. */
+#define W2VS_FLUSH_NONE 0
+#define W2VS_FLUSH_FINAL 1
+#define W2VS_FLUSH_PEEK 2
 w2vs_status_t w2vs_stream_step(const w2vs_config* cfg, const void* d_packed_weights,
                                void* host_state, void* d_state, const void* d_new_samples,
-                               int32_t wav_dtype, int32_t n_new, int32_t finished,
+                               int32_t wav_dtype, int32_t n_new, int32_t flush,
                                void* d_out_frames, int32_t out_capacity_frames, int32_t* n_out,
                                void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Host-side counters of a stream: samples consumed, frames produced by the conv stack, and frames of
+ * committed (final) blocks.  Any pointer may be NULL. */
+w2vs_status_t w2vs_stream_info(const void* host_state, int64_t* samples, int32_t* frames,
+                               int32_t* final_frames);
+
 /* ---- single operators (unit-test surface for the kernels; same code the forward uses) ------ */
-typedef enum { W2VS_GEMM_AUTO = 0, W2VS_GEMM_SIMT = 1, W2VS_GEMM_TCGEN05 = 2 } w2vs_gemm_impl_t;
+typedef enum {
+  W2VS_GEMM_AUTO = 0,
+  W2VS_GEMM_SIMT = 1,          /* fp32-accurate CUDA-core kernel */
+  W2VS_GEMM_TCGEN05 = 2,       /* tcgen05, one CTA per tile */
+  W2VS_GEMM_TCGEN05_2CTA = 3   /* tcgen05 cta_group::2 CTA pairs, TMA-store epilogue (default for bf16) */
+} w2vs_gemm_impl_t;
 #define W2VS_EPI_GELU 1
 /* C[M,N] = A[M,K] . W[N,K]^T + bias (+GELU) (+residual fp32, may alias C when C is fp32).
  * dtype_ab = dtype of A and W; dtype_c = dtype of C. lda/ldc in elements; lda may be < K*...

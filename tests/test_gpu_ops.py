@@ -26,7 +26,7 @@ def _gemm_ref(A, W, bias, res, gelu):
     return y
 
 
-@pytest.mark.parametrize("impl", [cabi.GEMM_TCGEN05, cabi.GEMM_SIMT])
+@pytest.mark.parametrize("impl", [cabi.GEMM_TCGEN05_2CTA, cabi.GEMM_TCGEN05, cabi.GEMM_SIMT])
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 128, 192), (1000, 512, 1536), (257, 3072, 1024),
                                    (4096, 1024, 4096), (24, 384, 128), (130, 64, 128), (5000, 768, 512)])
 def test_gemm_bf16(impl, M, N, K):
@@ -42,7 +42,7 @@ def test_gemm_bf16(impl, M, N, K):
         assert rel(y, ref) < tol, (impl, M, N, K, gelu, use_res)
 
 
-@pytest.mark.parametrize("impl", [cabi.GEMM_TCGEN05, cabi.GEMM_SIMT])
+@pytest.mark.parametrize("impl", [cabi.GEMM_TCGEN05_2CTA, cabi.GEMM_TCGEN05, cabi.GEMM_SIMT])
 @pytest.mark.parametrize("rows,C,k,s", [(1000, 512, 3, 2), (777, 512, 2, 2), (300, 64, 3, 2), (129, 64, 2, 2)])
 def test_gemm_strided_conv_view(impl, rows, C, k, s):
     """Conv1d(C->C, k, stride s) on channels-last rows == GEMM with lda = s*C < K = k*C."""

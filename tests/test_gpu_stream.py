@@ -1,0 +1,109 @@
+"""Incremental (chunk-by-chunk, cached left context) mode against the reference's streaming driver
+semantics: the reference re-encodes the whole prefix at every step (rain/simul/transducer_agent.py:138-167);
+golden chunks come from exactly that loop run on the unmodified reference (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+import wav2vec_s_b200 as W
+from wav2vec_s_b200.model import EncoderStream
+from oracle import cases
+from oracle import w2vs_oracle as O
+from helpers import load_golden, case_inputs, valid_rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
+STREAM = [n for n, c in cases.CASES.items() if c.get("api") == "stream"]
+
+
+def build(cfg, sd, dtype):
+    m = W.BlockWiseWav2Vec2Model(cfg)
+    m.load_state_dict(sd, strict=False)
+    return m.to("cuda", dtype).eval()
+
+
+@pytest.mark.parametrize("name", STREAM)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_stream_equals_reference_prefix_recompute(name, dtype):
+    g = load_golden(name)
+    cfg, sd, wav, _, _ = case_inputs(name)
+    m = build(cfg, sd, dtype)
+    src = wav.cuda().to(dtype)
+    st = m.open_stream(B=1, max_seconds=4.0, max_new_samples=20000)
+    prefixes = g["prefix_samples"].tolist()
+    outs, pos = [], 0
+    for i, n in enumerate(prefixes):
+        last = i == len(prefixes) - 1
+        y = st.step(src[:, pos:n], EncoderStream.FINAL if last else EncoderStream.NONE)
+        outs.append(y)
+        pos = n
+    assert [int(o.size(0)) for o in outs] == g["chunk_sizes"].tolist()     # same frames at the same steps
+    y = torch.cat(outs, 0).cpu()
+    assert valid_rel_err(y, g["y"]) < TOL[dtype]
+    assert valid_rel_err(y, g["y_offline"]) < TOL[dtype]                    # incremental == offline
+
+
+@pytest.mark.parametrize("name", STREAM)
+def test_stream_irregular_chunks_equal_offline(name):
+    cfg, sd, wav, _, _ = case_inputs(name)
+    m = build(cfg, sd, torch.float32)
+    src = wav.cuda()
+    ref, _ = O.rain_forward(sd, cfg, wav, None, finished=True, is_infer=True)
+    rs = np.random.RandomState(11)
+    st = m.open_stream(B=1, max_seconds=4.0, max_new_samples=9000)
+    outs, pos, L = [], 0, src.size(1)
+    while pos < L:
+        n = min(int(rs.choice([1, 37, 399, 400, 401, 1600, 5120, 8999])), L - pos)
+        outs.append(st.step(src[:, pos:pos + n], EncoderStream.FINAL if pos + n >= L else EncoderStream.NONE))
+        pos += n
+    y = torch.cat(outs, 0).cpu()
+    assert tuple(y.shape) == tuple(ref.shape)
+    assert valid_rel_err(y, ref) < 1e-4
+
+
+def test_stream_batch_lockstep():
+    cfg = cases.tiny(layer_norm_first=True, conv_bias=True)
+    from oracle import synth
+    sd = synth.make_state_dict(cfg, 5)
+    wav = synth.make_waveform(3, 20000, 99)
+    m = build(cfg, sd, torch.float32)
+    st = m.open_stream(B=3, max_seconds=3.0, max_new_samples=8000)
+    outs, pos = [], 0
+    for n in (7760, 5120, 5120, 2000):
+        outs.append(st.step(wav[:, pos:pos + n].cuda(), EncoderStream.FINAL if pos + n >= 20000 else 0))
+        pos += n
+    y = torch.cat(outs, 0).cpu()
+    ref, _ = O.rain_forward(sd, cfg, wav, None, finished=True, is_infer=True)
+    assert tuple(y.shape) == tuple(ref.shape)
+    assert valid_rel_err(y, ref) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_incremental_forward_is_drop_in_for_prefix_recompute(dtype):
+    """forward(prefix, incremental_state=dict, is_infer=True) returns what the reference returns for
+    the same prefix (any prefix length, block aligned or not), computed from cached state."""
+    cfg = cases.tiny(layer_norm_first=True, conv_bias=True)
+    from oracle import synth
+    sd = synth.make_state_dict(cfg, 5)
+    wav = synth.make_waveform(1, 30000, 17)
+    m = build(cfg, sd, dtype)
+    state = {}
+    prefixes = [7760, 8160, 12880, 13000, 17000, 23120, 23121, 28000, 30000]
+    for i, n in enumerate(prefixes):
+        fin = i == len(prefixes) - 1
+        out = m(wav[:, :n].cuda().to(dtype), None, state, fin, True)
+        y = out["encoder_out"][0]
+        ref, pm = O.rain_forward(sd, cfg, wav[:, :n], None, finished=fin, is_infer=True)
+        assert tuple(y.shape) == tuple(ref.shape), n
+        assert tuple(out["encoder_padding_mask"][0].shape) == tuple(pm.shape)
+        if ref.numel():
+            assert valid_rel_err(y.cpu(), ref) < TOL[dtype], n
+
+
+def test_stream_unsupported_modes_fail_loudly():
+    cfg = cases.tiny(extractor_mode="default", pos_type="conv", encoder_layers=2)
+    from oracle import synth
+    m = build(cfg, synth.make_state_dict(cfg, 1), torch.float32)
+    with pytest.raises(W.cabi.W2vsError) as e:
+        m.open_stream(B=1, max_seconds=1.0)
+    assert e.value.status == W.cabi.UNSUPPORTED

@@ -16,7 +16,7 @@ F32, BF16 = 0, 1
 EXTRACTOR_DEFAULT, EXTRACTOR_LAYER_NORM = 0, 1
 POS_SIN, POS_CONV = 0, 1
 LAYOUT_BTD, LAYOUT_TBD = 0, 1
-GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
+GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, GEMM_TCGEN05_2CTA = 0, 1, 2, 3
 EPI_GELU = 1
 
 
@@ -72,6 +72,7 @@ PROTOTYPES = {
     "w2vs_stream_step": (C.c_int, [_P(Config), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                    C.c_int32, C.c_int32, C.c_void_p, C.c_int32, _P(C.c_int32), C.c_void_p,
                                    C.c_size_t, C.c_void_p]),
+    "w2vs_stream_info": (C.c_int, [C.c_void_p, _P(C.c_int64), _P(C.c_int32), _P(C.c_int32)]),
     "w2vs_op_gemm": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                C.c_void_p]),
@@ -88,7 +89,7 @@ PROTOTYPES = {
 }
 
 # kernel name -> class reported by bench.py
-KERNEL_CLASS = {"gemm_tc_kernel": "gemm", "gemm_simt_kernel": "gemm_simt", "attn_mma_kernel": "attention",
+KERNEL_CLASS = {"gemm_tc_kernel": "gemm", "gemm_tc2_kernel": "gemm", "gemm_simt_kernel": "gemm_simt", "attn_mma_kernel": "attention",
                 "attn_simt_kernel": "attention", "conv0_kernel": "conv0"}
 
 _lib = None

@@ -212,7 +212,7 @@ w2vs_status_t w2vs_encode(const w2vs_config* cfg, const void* d_packed, const w2
     c.C = cfg->conv_dim[0]; c.k = cfg->conv_kernel[0]; c.stride = cfg->conv_stride[0];
     c.norm = !conv_has_norm(cfg, 0) ? CONV0_NORM_NONE
              : (cfg->extractor_mode == W2VS_EXTRACTOR_LAYER_NORM ? CONV0_NORM_LAYER : CONV0_NORM_GROUP);
-    c.gn_stats = at<double>(d_ws, ws.gn_stats);
+    c.gn_stats = at<float>(d_ws, ws.gn_stats);
     W2VS_TRY(launch_conv0(c, st));
   }
   for (int i = 1; i < n; ++i) {
@@ -404,8 +404,13 @@ namespace w2vs {
 w2vs_status_t launch_gemm(int impl, const GemmArgs& g, cudaStream_t st) {
   W2VS_REQUIRE(g.dtype_ab == W2VS_F32 || g.dtype_ab == W2VS_BF16, "GEMM operand dtype");
   W2VS_REQUIRE(g.dtype_c == W2VS_F32 || g.dtype_c == W2VS_BF16, "GEMM output dtype");
-  if (impl == W2VS_GEMM_AUTO) impl = g.dtype_ab == W2VS_BF16 ? W2VS_GEMM_TCGEN05 : W2VS_GEMM_SIMT;
+  if (impl == W2VS_GEMM_AUTO) impl = g.dtype_ab == W2VS_BF16 ? W2VS_GEMM_TCGEN05_2CTA : W2VS_GEMM_SIMT;
   if (impl == W2VS_GEMM_TCGEN05) return launch_gemm_tc(g, st);
+  if (impl == W2VS_GEMM_TCGEN05_2CTA) {
+    // the pair kernel adds the residual in place; anything else goes through the 1-CTA kernel
+    if (g.residual != nullptr && (g.dtype_c != W2VS_F32 || g.residual != (const float*)g.C)) return launch_gemm_tc(g, st);
+    return launch_gemm_tc2(g, st);
+  }
   if (impl == W2VS_GEMM_SIMT) return launch_gemm_simt(g, st);
   set_error("invalid value: gemm impl %d", impl);
   return W2VS_INVALID_VALUE;

@@ -61,9 +61,11 @@ __device__ __forceinline__ void load_tile_async(bf16* tile, const bf16* src, int
   }
 }
 
+// step mode (kv_cache != nullptr): M = query tokens per stream, T2 = keys visible to all of them.
 __global__ void __launch_bounds__(128)
 attn_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ keypad, bf16* __restrict__ ctx,
-                int T2, int M, int main_ctx, int rc, int D, int n_main_tiles, int n_tiles, float scale_log2) {
+                int T2, int M, int main_ctx, int rc, int D, int n_main_tiles, int n_tiles, float scale_log2,
+                const bf16* __restrict__ kv_cache, int64_t kv_rows) {
   __shared__ __align__(128) bf16 Qs[TILE_ELEMS];
   __shared__ __align__(128) bf16 Ks[2][TILE_ELEMS];
   __shared__ __align__(128) bf16 Vs[2][TILE_ELEMS];
@@ -75,20 +77,23 @@ attn_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ keypad
   const int tile_id = n_tiles - 1 - (int)blockIdx.x;  // heaviest first
   const int nb = T2 / main_ctx;
   const int rcd = rc > 0 ? rc : 1;
+  const bool step = kv_cache != nullptr;
   const int64_t rs = 3 * (int64_t)D;
+  const int64_t krs = step ? 2 * (int64_t)D : rs;
   const bf16* qbase = qkv + (size_t)b * M * rs + (size_t)h * HD;
-  const bf16* kbase = qbase + D;
-  const bf16* vbase = qbase + 2 * D;
-  const uint8_t* kp = keypad + (size_t)b * M;
+  const bf16* kbase = step ? kv_cache + (size_t)b * kv_rows * krs + (size_t)h * HD : qbase + D;
+  const bf16* vbase = kbase + D;
+  const uint8_t* kp = step ? nullptr : keypad + (size_t)b * M;
 
   int q_first, q_count;
-  if (tile_id < n_main_tiles) { q_first = tile_id * QT; q_count = min(QT, T2 - q_first); }
+  if (step) { q_first = tile_id * QT; q_count = min(QT, M - q_first); }
+  else if (tile_id < n_main_tiles) { q_first = tile_id * QT; q_count = min(QT, T2 - q_first); }
   else { q_first = T2 + (tile_id - n_main_tiles) * QT; q_count = min(QT, M - q_first); }
-  auto qblock = [&](int m) { return m < T2 ? m / main_ctx : (m - T2) / rcd; };
+  auto qblock = [&](int m) { return step ? 0 : (m < T2 ? m / main_ctx : (m - T2) / rcd); };
   const int qb_lo = qblock(q_first), qb_hi = qblock(q_first + q_count - 1);
-  const int seg0_end = min(main_ctx * (qb_hi + 1), T2);
+  const int seg0_end = step ? T2 : min(main_ctx * (qb_hi + 1), T2);
   int seg1_begin = 0, seg1_end = 0;
-  if (rc > 0 && qb_lo <= nb - 1) { seg1_begin = T2 + rc * qb_lo; seg1_end = T2 + rc * (min(qb_hi, nb - 1) + 1); }
+  if (!step && rc > 0 && qb_lo <= nb - 1) { seg1_begin = T2 + rc * qb_lo; seg1_end = T2 + rc * (min(qb_hi, nb - 1) + 1); }
   const int n0 = (seg0_end + KT - 1) / KT;
   const int n1 = (seg1_end - seg1_begin + KT - 1) / KT;
   const int n_kt = n0 + n1;
@@ -97,11 +102,12 @@ attn_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ keypad
     const bool s1 = it >= n0;
     const int k0 = s1 ? seg1_begin + (it - n0) * KT : it * KT;
     const int cnt = min(KT, (s1 ? seg1_end : seg0_end) - k0);
-    load_tile_async(Ks[buf], kbase, rs, k0, cnt, tid);
-    load_tile_async(Vs[buf], vbase, rs, k0, cnt, tid);
+    load_tile_async(Ks[buf], kbase, krs, k0, cnt, tid);
+    load_tile_async(Vs[buf], vbase, krs, k0, cnt, tid);
     if (tid < KT) {
       int info;
-      if (tid < cnt && !kp[k0 + tid]) info = s1 ? (k0 + tid - T2) / rcd : (k0 + tid) / main_ctx;
+      if (step) info = tid < cnt ? 0 : INT_MAX;
+      else if (tid < cnt && !kp[k0 + tid]) info = s1 ? (k0 + tid - T2) / rcd : (k0 + tid) / main_ctx;
       else info = s1 ? -2 : INT_MAX;
       s_kinfo[buf][tid] = info;
     }
@@ -241,12 +247,20 @@ attn_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ keypad
 w2vs_status_t launch_attention_mma(const AttnArgs& a, cudaStream_t st) {
   W2VS_REQUIRE(a.D == a.heads * HD, "attention head_dim must be 64");
   W2VS_REQUIRE(a.D % 8 == 0, "attention D alignment");
+  const float scale_log2 = (1.0f / sqrtf((float)HD)) * 1.4426950408889634f;
+  if (a.n_step_q > 0) {
+    const int nt = (a.n_step_q + QT - 1) / QT;
+    dim3 grid((unsigned)nt, (unsigned)a.heads, (unsigned)a.B);
+    attn_mma_kernel<<<grid, 128, 0, st>>>((const bf16*)a.qkv, nullptr, (bf16*)a.ctx, a.n_step_keys, a.n_step_q, 1, 0,
+                                          a.D, nt, nt, scale_log2, (const bf16*)a.kv_cache, a.kv_rows);
+    W2VS_CHECK_LAUNCH("attn_mma_kernel");
+    return W2VS_OK;
+  }
   const int M = a.T2 + (a.rc > 0 ? (a.T2 / a.main_ctx) * a.rc : 0);
   const int n_main = (a.T2 + QT - 1) / QT, n_rc = (M - a.T2 + QT - 1) / QT;
   dim3 grid((unsigned)(n_main + n_rc), (unsigned)a.heads, (unsigned)a.B);
-  const float scale_log2 = (1.0f / sqrtf((float)HD)) * 1.4426950408889634f;
   attn_mma_kernel<<<grid, 128, 0, st>>>((const bf16*)a.qkv, a.keypad, (bf16*)a.ctx, a.T2, M, a.main_ctx, a.rc,
-                                        a.D, n_main, n_main + n_rc, scale_log2);
+                                        a.D, n_main, n_main + n_rc, scale_log2, nullptr, 0);
   W2VS_CHECK_LAUNCH("attn_mma_kernel");
   return W2VS_OK;
 }

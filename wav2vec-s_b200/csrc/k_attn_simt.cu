@@ -39,7 +39,8 @@ __device__ __forceinline__ void load_tile(float (*dst)[LDT], const T* __restrict
 template <typename T>
 __global__ void __launch_bounds__(256)
 attn_simt_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ keypad, T* __restrict__ ctx,
-                 int T2, int M, int main_ctx, int rc, int D, int n_main_tiles, float scale) {
+                 int T2, int M, int main_ctx, int rc, int D, int n_main_tiles, float scale,
+                 const T* __restrict__ kv_cache, int64_t kv_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float (*Qs)[LDT] = reinterpret_cast<float (*)[LDT]>(smem_raw);
   float (*Ks)[LDT] = Qs + QT;   // reused as Ps after the score tile is in registers
@@ -49,14 +50,20 @@ attn_simt_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ keypad, 
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int h = blockIdx.y, b = blockIdx.z;
   const int nb = T2 / main_ctx;
+  // step mode (kv_cache != nullptr): M = query tokens per stream, T2 = keys visible to all of them
+  const bool step = kv_cache != nullptr;
   const int64_t rs = 3 * (int64_t)D;  // token row stride in qkv
+  const int64_t krs = step ? 2 * (int64_t)D : rs;
   const T* qbase = qkv + (size_t)b * M * rs + (size_t)h * HD;
-  const T* kbase = qbase + D;
-  const T* vbase = qbase + 2 * D;
+  const T* kbase = step ? kv_cache + (size_t)b * kv_rows * krs + (size_t)h * HD : qbase + D;
+  const T* vbase = kbase + D;
 
   // ---- query tile
   int q_first, q_count;
-  if ((int)blockIdx.x < n_main_tiles) {
+  if (step) {
+    q_first = blockIdx.x * QT;
+    q_count = min(QT, M - q_first);
+  } else if ((int)blockIdx.x < n_main_tiles) {
     q_first = blockIdx.x * QT;
     q_count = min(QT, T2 - q_first);
   } else {
@@ -64,12 +71,12 @@ attn_simt_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ keypad, 
     q_count = min(QT, M - q_first);
   }
   const int rcd = rc > 0 ? rc : 1;
-  auto qblock = [&](int m) { return m < T2 ? m / main_ctx : (m - T2) / rcd; };
+  auto qblock = [&](int m) { return step ? 0 : (m < T2 ? m / main_ctx : (m - T2) / rcd); };
   const int qb_lo = qblock(q_first), qb_hi = qblock(q_first + q_count - 1);
   // visible key segments for the whole tile
-  const int seg0_end = min(main_ctx * (qb_hi + 1), T2);              // main keys [0, seg0_end)
+  const int seg0_end = step ? T2 : min(main_ctx * (qb_hi + 1), T2);  // main keys [0, seg0_end)
   int seg1_begin = 0, seg1_end = 0;                                   // look-ahead keys
-  if (rc > 0 && qb_lo <= nb - 1) {
+  if (!step && rc > 0 && qb_lo <= nb - 1) {
     seg1_begin = T2 + rc * qb_lo;
     seg1_end = T2 + rc * (min(qb_hi, nb - 1) + 1);
   }
@@ -97,9 +104,9 @@ attn_simt_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ keypad, 
     for (int k0 = s_begin; k0 < s_end; k0 += KT) {
       const int k_count = min(KT, s_end - k0);
       __syncthreads();  // previous tile's Ps / Vs fully consumed (also orders the Q load)
-      load_tile(Ks, kbase, rs, k0, k_count, 1.0f, tid);
-      load_tile(Vs, vbase, rs, k0, k_count, 1.0f, tid);
-      if (tid < KT) s_kpad[tid] = tid < k_count ? keypad[(size_t)b * M + k0 + tid] : 1;
+      load_tile(Ks, kbase, krs, k0, k_count, 1.0f, tid);
+      load_tile(Vs, vbase, krs, k0, k_count, 1.0f, tid);
+      if (tid < KT) s_kpad[tid] = tid < k_count ? (step ? 0 : keypad[(size_t)b * M + k0 + tid]) : 1;
       __syncthreads();
 
       // ---- S = Q K^T for queries ty+16i, keys tx+16j
@@ -131,7 +138,7 @@ attn_simt_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ keypad, 
         const int kk = tx + 16 * j;
         const int k = k0 + kk;
         const bool kpad = s_kpad[kk] != 0;
-        const int kb = seg == 0 ? k / main_ctx : (k - T2) / rcd;
+        const int kb = step ? 0 : (seg == 0 ? k / main_ctx : (k - T2) / rcd);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const bool vis = !kpad && my_qb[i] >= 0 && (seg == 0 ? kb <= my_qb[i] : kb == my_qb[i]);
@@ -209,8 +216,11 @@ attn_simt_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ keypad, 
 
 w2vs_status_t launch_attention_simt(const AttnArgs& a, cudaStream_t st) {
   W2VS_REQUIRE(a.D == a.heads * HD, "attention head_dim must be 64");
-  const int M = a.T2 + (a.rc > 0 ? (a.T2 / a.main_ctx) * a.rc : 0);
-  const int n_main = (a.T2 + QT - 1) / QT, n_rc = (M - a.T2 + QT - 1) / QT;
+  const bool step = a.n_step_q > 0;
+  const int M = step ? a.n_step_q : a.T2 + (a.rc > 0 ? (a.T2 / a.main_ctx) * a.rc : 0);
+  const int T2 = step ? a.n_step_keys : a.T2;
+  const int n_main = step ? (M + QT - 1) / QT : (a.T2 + QT - 1) / QT;
+  const int n_rc = step ? 0 : (M - a.T2 + QT - 1) / QT;
   dim3 grid((unsigned)(n_main + n_rc), (unsigned)a.heads, (unsigned)a.B);
   const size_t smem = (size_t)(QT + KT + KT) * LDT * sizeof(float);
   const float scale = 1.0f / sqrtf((float)HD);
@@ -218,13 +228,15 @@ w2vs_status_t launch_attention_simt(const AttnArgs& a, cudaStream_t st) {
   if (a.dtype == W2VS_F32) {
     e = cudaFuncSetAttribute(attn_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
-      attn_simt_kernel<float><<<grid, 256, smem, st>>>((const float*)a.qkv, a.keypad, (float*)a.ctx, a.T2, M,
-                                                       a.main_ctx, a.rc, a.D, n_main, scale);
+      attn_simt_kernel<float><<<grid, 256, smem, st>>>((const float*)a.qkv, a.keypad, (float*)a.ctx, T2, M,
+                                                       step ? 1 : a.main_ctx, step ? 0 : a.rc, a.D, n_main, scale,
+                                                       (const float*)a.kv_cache, a.kv_rows);
   } else {
     e = cudaFuncSetAttribute(attn_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
-      attn_simt_kernel<bf16><<<grid, 256, smem, st>>>((const bf16*)a.qkv, a.keypad, (bf16*)a.ctx, a.T2, M,
-                                                      a.main_ctx, a.rc, a.D, n_main, scale);
+      attn_simt_kernel<bf16><<<grid, 256, smem, st>>>((const bf16*)a.qkv, a.keypad, (bf16*)a.ctx, T2, M,
+                                                      step ? 1 : a.main_ctx, step ? 0 : a.rc, a.D, n_main, scale,
+                                                      (const bf16*)a.kv_cache, a.kv_rows);
   }
   if (e != cudaSuccess) { set_error("attn_simt attribute: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
   W2VS_CHECK_LAUNCH("attn_simt_kernel");

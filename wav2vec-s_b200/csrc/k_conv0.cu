@@ -10,7 +10,8 @@
 //
 // Modes:  PLAIN     y = gelu(conv + bias)
 //         LN        y = gelu(LayerNorm_C(conv + bias))            (extractor_mode = layer_norm)
-//         GN_STATS  accumulate per-(utterance, channel) sum / sum of squares over time (fp64 atomics)
+//         GN_STATS  per-CTA partial sum / sum of squares per (utterance, channel); a small finalize
+//                   kernel reduces them in a fixed order (fp64) -> bit-reproducible scale / shift
 //         GN_APPLY  y = gelu(GroupNorm(conv + bias)), groups == channels   (extractor_mode = default)
 #include "common.cuh"
 #include "kernels.h"
@@ -24,12 +25,12 @@ __global__ void __launch_bounds__(256, 1)
 conv0_kernel(const TIn* __restrict__ wav, int64_t wav_ld, const float* __restrict__ w,
              const float* __restrict__ bias, const float* __restrict__ gamma,
              const float* __restrict__ beta, TOut* __restrict__ out, int rows_per_utt, int T0,
-             int stride, double* __restrict__ gn_stats, int frames_per_cta) {
+             int stride, float* __restrict__ gn_stats, int frames_per_cta) {
   constexpr int C = NI * 64;
   __shared__ float s_bias[C];
   __shared__ float s_scale[C];   // LN: gamma; GN_APPLY: gamma * rstd
   __shared__ float s_shift[C];   // LN: beta;  GN_APPLY: beta - mean * gamma * rstd
-  __shared__ float s_red[2 * C]; // GN_STATS cross-warp reduction
+  __shared__ float s_red[MODE == C0_GN_STATS ? 8 * 2 * C : 1];  // GN_STATS: per-warp partials
 
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -39,17 +40,9 @@ conv0_kernel(const TIn* __restrict__ wav, int64_t wav_ld, const float* __restric
       s_scale[c] = gamma[c];
       s_shift[c] = beta[c];
     } else if (MODE == C0_GN_APPLY) {
-      const double sum = gn_stats[((size_t)b * C + c) * 2 + 0];
-      const double sq = gn_stats[((size_t)b * C + c) * 2 + 1];
-      const double mean = sum / T0;
-      double var = sq / T0 - mean * mean;
-      if (var < 0) var = 0;
-      const float rstd = (float)(1.0 / sqrt(var + 1e-5));
-      const float sc = gamma[c] * rstd;
-      s_scale[c] = sc;
-      s_shift[c] = beta[c] - (float)mean * sc;
+      s_scale[c] = gn_stats[((size_t)b * C + c) * 2 + 0];
+      s_shift[c] = gn_stats[((size_t)b * C + c) * 2 + 1];
     }
-    if (MODE == C0_GN_STATS) { s_red[c] = 0.f; s_red[C + c] = 0.f; }
   }
   // filter taps of this lane's channels -> registers
   float wr[NI][2][KW];
@@ -147,24 +140,51 @@ conv0_kernel(const TIn* __restrict__ wav, int64_t wav_ld, const float* __restric
   }
 
   if (MODE == C0_GN_STATS) {
+    // per-warp partials -> fixed-order sum over the 8 warps -> one partial row per CTA
 #pragma unroll
     for (int i = 0; i < NI; ++i)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        atomicAdd(&s_red[2 * lane + 64 * i + h], st_sum[i][h]);
-        atomicAdd(&s_red[C + 2 * lane + 64 * i + h], st_sq[i][h]);
+        s_red[(warp * 2 + 0) * C + 2 * lane + 64 * i + h] = st_sum[i][h];
+        s_red[(warp * 2 + 1) * C + 2 * lane + 64 * i + h] = st_sq[i][h];
       }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      atomicAdd(&gn_stats[((size_t)b * C + c) * 2 + 0], (double)s_red[c]);
-      atomicAdd(&gn_stats[((size_t)b * C + c) * 2 + 1], (double)s_red[C + c]);
+    float* part = gn_stats + (size_t)gridDim.y * C * 2 + ((size_t)b * gridDim.x + blockIdx.x) * 2 * C;
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+      float acc = 0.f;
+      for (int w = 0; w < 8; ++w) acc += s_red[(w * 2 + c / C) * C + (c % C)];
+      part[c] = acc;
     }
   }
 }
 
+// gn_stats layout (floats): [B][C][2] scale/shift, then [B][n_cta][2][C] partials.
+__global__ void __launch_bounds__(256)
+conv0_gn_finalize_kernel(float* __restrict__ gn_stats, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, int B, int C, int n_cta, int T0) {
+  const int b = blockIdx.x;
+  const float* part = gn_stats + (size_t)B * C * 2 + (size_t)b * n_cta * 2 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double sum = 0.0, sq = 0.0;
+    for (int i = 0; i < n_cta; ++i) {
+      sum += (double)part[(size_t)i * 2 * C + c];
+      sq += (double)part[(size_t)i * 2 * C + C + c];
+    }
+    const double mean = sum / T0;
+    double var = sq / T0 - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+    const float sc = gamma[c] * rstd;
+    gn_stats[((size_t)b * C + c) * 2 + 0] = sc;
+    gn_stats[((size_t)b * C + c) * 2 + 1] = beta[c] - (float)mean * sc;
+  }
+}
+
+constexpr int kFramesPerCta = 256;
+
 template <typename TIn, typename TOut, int NI, int MODE>
 static w2vs_status_t launch_one(const Conv0Args& a, cudaStream_t st) {
-  const int frames_per_cta = 256;
+  const int frames_per_cta = kFramesPerCta;
   dim3 grid((unsigned)ceil_div64(a.T0, frames_per_cta), (unsigned)a.B);
   conv0_kernel<TIn, TOut, NI, 10, MODE><<<grid, 256, 0, st>>>(
       (const TIn*)a.wav, a.wav_ld, a.w, a.bias, a.gamma, a.beta, (TOut*)a.out, a.rows_per_utt, a.T0,
@@ -179,9 +199,10 @@ static w2vs_status_t launch_mode(const Conv0Args& a, cudaStream_t st) {
     case CONV0_NORM_NONE: return launch_one<TIn, TOut, NI, C0_PLAIN>(a, st);
     case CONV0_NORM_LAYER: return launch_one<TIn, TOut, NI, C0_LN>(a, st);
     case CONV0_NORM_GROUP: {
-      cudaError_t e = cudaMemsetAsync(a.gn_stats, 0, (size_t)a.B * a.C * 2 * sizeof(double), st);
-      if (e != cudaSuccess) { set_error("memset gn_stats: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
       W2VS_TRY((launch_one<TIn, TOut, NI, C0_GN_STATS>(a, st)));
+      conv0_gn_finalize_kernel<<<a.B, 256, 0, st>>>(a.gn_stats, a.gamma, a.beta, a.B, a.C,
+                                                    (int)ceil_div64(a.T0, kFramesPerCta), a.T0);
+      W2VS_CHECK_LAUNCH("conv0_gn_finalize_kernel");
       return launch_one<TIn, TOut, NI, C0_GN_APPLY>(a, st);
     }
   }

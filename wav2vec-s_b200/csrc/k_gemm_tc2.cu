@@ -1,0 +1,493 @@
+// bf16 GEMM on tcgen05 tensor cores, CTA-pair (cta_group::2) version:
+//     C[M,N] = A[M,K] . W[N,K]^T + bias  (+GELU)  (+fp32 residual, in place)     fp32 accumulation in TMEM
+//
+// Every matrix product of the bf16 encoder runs here: the strided feature-extractor convs 1..6 (implicit
+// GEMM over the channels-last activation), post_extract_proj, QKV / out_proj, fc1(+GELU) / fc2(+residual)
+// (wav2vec2.py:725,568,950-973; modules/multihead_attention.py:162-194).
+//
+// One persistent cluster of two CTAs per SM pair; a cluster tile is 256 (M) x BN (N):
+//   * each CTA TMA-loads its own 128 rows of A and its own BN/2 rows of W per 64-wide K stage (128B-swizzled
+//     smem), signalling the leader CTA's "full" mbarrier (cp.async.bulk.tensor ... .cta_group::2);
+//   * the leader's MMA thread issues tcgen05.mma.cta_group::2 (M=256, N=BN, K=16): both tensor cores run, each
+//     reads its own A rows and both halves of W, accumulators land in each CTA's own TMEM (rows 0-127 /
+//     128-255); tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs;
+//   * 8 epilogue warps per CTA (2 per TMEM lane quarter, each half of the columns) drain the accumulator in
+//     32-column chunks: tcgen05.ld -> +bias (smem) -> [GELU] -> [+ residual chunk, TMA-loaded into the
+//     staging slot] -> swizzled staging slot -> TMA store.  Two accumulator stages (2 x BN TMEM columns)
+//     overlap the epilogue of tile i with the MMAs of tile i+1.
+//
+// Implicit-GEMM view of Conv1d(C_in -> C_out, k, stride s) on activations [rows, C_in]: output row r needs the
+// k*C_in contiguous inputs starting at row r*s.  The A tensor map describes the matrix [rows, a_row_len =
+// s*C_in]; K index kk >= a_row_len wraps to the next row: (x, y) = (kk % a_row_len, r + kk / a_row_len).
+#include <cuda.h>
+#include "common.cuh"
+#include "kernels.h"
+
+namespace w2vs {
+
+__device__ int g_tc2_fault = 0;  // set when a pipeline wait timed out (diagnostics)
+
+namespace {
+
+constexpr int BM = 128, BK = 64;           // per-CTA rows; K per stage
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int N_EPI_WARPS = 8;
+constexpr int N_THREADS = 64 + 32 * N_EPI_WARPS;
+constexpr int CHUNK = 32;                  // columns per epilogue chunk
+constexpr unsigned long long WAIT_TIMEOUT_NS = 4000000000ull;
+constexpr int SMEM_LIMIT = 232448;
+
+template <int BN, typename TC> struct Cfg2 {
+  static constexpr int kBStageBytes = (BN / 2) * BK * 2;
+  static constexpr int kStageBytes = A_STAGE_BYTES + kBStageBytes;
+  static constexpr int kSlotBytes = 32 * CHUNK * (int)sizeof(TC);          // 4 KB fp32 / 2 KB bf16
+  static constexpr int kStagingBytes = N_EPI_WARPS * 2 * kSlotBytes;
+  static constexpr int kMiscBytes = N_EPI_WARPS * (BN / 2) * 4 /*bias*/ + 512 /*barriers*/ + 1024 /*align*/;
+  static constexpr int kStagesFit = (SMEM_LIMIT - kStagingBytes - kMiscBytes) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kMiscBytes;
+  static constexpr int kChunksPerWarp = BN / 2 / CHUNK;
+  static_assert(BN == 64 || BN == 128 || BN == 256, "BN");
+  static_assert(kStages >= 3, "pipeline too shallow");
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// arrive on a barrier that may live in the peer CTA (address from mapa)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// false on timeout (a bug / bad descriptor): callers abandon their loops so the kernel ends instead of wedging
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const unsigned long long t0 = global_ns();
+  unsigned spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ff) == 0 && global_ns() - t0 > WAIT_TIMEOUT_NS) {
+      atomicExch(&g_tc2_fault, 1);
+      return false;
+    }
+  }
+  return true;
+}
+// 2-CTA TMA load: data lands in this CTA's smem, completion bytes are counted on `bar` (a shared::cluster
+// address, here always the leader CTA's barrier)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"((uint64_t)map), "r"(src), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// completion of all prior MMAs of this thread -> arrive on the barrier at this smem offset in both CTAs
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);   // start address        bits [0,14)
+  d |= (uint64_t)1 << 16;                                // leading byte offset  (unused for SW128 K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                      // stride byte offset   8 rows x 128 B
+  d |= (uint64_t)1 << 46;                                // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                                // layout type SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int BN, typename TC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int has_residual,
+                int M, int N, int K, int a_row_len, int gelu) {
+  using C2 = Cfg2<BN, TC>;
+  constexpr int S = C2::kStages;
+  constexpr bool kF32 = sizeof(TC) == 4;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = sA + S * A_STAGE_BYTES;
+  const uint32_t sStage = sB + S * C2::kBStageBytes;                 // epilogue staging slots (1024-aligned)
+  const uint32_t sBias = sStage + C2::kStagingBytes;                 // [8 warps][BN/2] floats
+  const uint32_t bars = sBias + N_EPI_WARPS * (BN / 2) * 4;
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * S, bar_tfull = bars + 16 * S, bar_tempty = bar_tfull + 16;
+  const uint32_t bar_res = bar_tempty + 16;                          // [8 warps][2 slots]
+  const uint32_t tmem_slot = bar_res + 8 * 2 * N_EPI_WARPS;
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));   // generic pointer to smem_base
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
+  float* bias_s = reinterpret_cast<float*>(gen_base + (sBias - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + 2 * BM - 1) / (2 * BM);
+  const int n_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 2 * N_EPI_WARPS); }
+    for (int i = 0; i < 2 * N_EPI_WARPS; ++i) mbar_init(bar_res + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)C2::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();          // the peer's barriers are initialised and its TMEM is allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+      const uint32_t full_leader = mapa(bar_full, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int tile = cluster_id; tile < n_tiles && ok; tile += n_clusters) {
+        const int m0 = (tile / tiles_n) * (2 * BM) + (int)rank * BM;
+        const int n0 = (tile % tiles_n) * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if (!(ok = mbar_wait(bar_empty + 8 * stage, phase ^ 1))) break;
+          if (leader) mbar_expect_tx(bar_full + 8 * stage, 2 * C2::kStageBytes);
+          const int kk = kb * BK;
+          tma_load_2d_2sm(sA + stage * A_STAGE_BYTES, &tmA, full_leader + 8 * stage, kk % a_row_len, m0 + kk / a_row_len);
+          tma_load_2d_2sm(sB + stage * C2::kBStageBytes, &tmB, full_leader + 8 * stage, kk, n0);
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=256 (cta_group::2)
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                 ((uint32_t)((2 * BM) >> 4) << 24);
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      bool ok = true;
+      for (int tile = cluster_id; tile < n_tiles && ok; tile += n_clusters) {
+        if (!(ok = mbar_wait(bar_tempty + 8 * as, aphase ^ 1))) break;
+        tc_fence_after();
+        const uint32_t tmem_c = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if (!(ok = mbar_wait(bar_full + 8 * stage, phase))) break;
+          tc_fence_after();
+          const uint32_t a_addr = sA + stage * A_STAGE_BYTES, b_addr = sB + stage * C2::kBStageBytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_2sm(tmem_c, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit_2sm(bar_empty + 8 * stage);   // both CTAs may refill this stage once the MMAs retire
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+        if (!ok) break;
+        tc_commit_2sm(bar_tfull + 8 * as);        // accumulator complete in both CTAs
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs) =====================
+    const int e = warp - 2;                  // 0..7
+    const int quarter = warp & 3;            // TMEM lanes this warp may touch: 32*quarter ..
+    const int half = e >> 2;                 // column half of the tile
+    const uint32_t slot0 = sStage + (uint32_t)e * 2 * C2::kSlotBytes;
+    const uint32_t my_res_bar = bar_res + 16 * e;
+    const uint32_t tempty_leader = mapa(bar_tempty, 0);
+    uint32_t res_phase = 0;                  // bit s = parity of residual slot s
+    int as = 0;
+    uint32_t aphase = 0;
+    bool ok = true;
+    for (int tile = cluster_id; tile < n_tiles && ok; tile += n_clusters) {
+      const int m0 = (tile / tiles_n) * (2 * BM) + (int)rank * BM;
+      const int n0 = (tile % tiles_n) * BN;
+      const int row0 = m0 + quarter * 32;
+      const int colw = n0 + half * (BN / 2);           // first column of this warp
+      // bias of this warp's columns -> its private smem strip
+      float* bs = bias_s + e * (BN / 2);
+      __syncwarp();
+#pragma unroll
+      for (int i = lane; i < BN / 2; i += 32) bs[i] = (bias != nullptr && colw + i < N) ? bias[colw + i] : 0.f;
+      // residual chunk 0 prefetch (overlaps the wait for the accumulator)
+      if (has_residual && lane == 0) {
+        bulk_wait_read<0>();                           // earlier stores from slot 0/1 have been read out
+        mbar_expect_tx(my_res_bar, C2::kSlotBytes);
+        tma_load_2d(slot0, &tmC, my_res_bar, colw, row0);
+      }
+      __syncwarp();                                    // bias strip visible to the whole warp
+      ok = mbar_wait(bar_tfull + 8 * as, aphase);
+      ok = __all_sync(0xffffffffu, ok);
+      if (!ok) break;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * (BN / 2));
+#pragma unroll 1
+      for (int c = 0; c < C2::kChunksPerWarp; ++c) {
+        const int sl = c & 1;
+        const uint32_t slot = slot0 + sl * C2::kSlotBytes;
+        if (has_residual) {
+          if (c + 1 < C2::kChunksPerWarp && lane == 0) {
+            bulk_wait_read<0>();                       // the store that used the other slot has drained it
+            mbar_expect_tx(my_res_bar + 8 * (sl ^ 1), C2::kSlotBytes);
+            tma_load_2d(slot0 + (sl ^ 1) * C2::kSlotBytes, &tmC, my_res_bar + 8 * (sl ^ 1), colw + (c + 1) * CHUNK, row0);
+          }
+        } else if (lane == 0) {
+          bulk_wait_read<1>();                         // the store issued two chunks ago (same slot) is done
+        }
+        uint32_t r[32];
+        tmem_ld32(taddr + c * CHUNK, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = __uint_as_float(r[j]) + bs[c * CHUNK + j];
+          if (gelu) v[j] = gelu_erf(v[j]);
+        }
+        if (has_residual) {
+          ok = mbar_wait(my_res_bar + 8 * sl, (res_phase >> sl) & 1u);
+          res_phase ^= 1u << sl;
+        }
+        __syncwarp();                                  // lane 0's wait_group / everyone's mbarrier wait done
+        if (kF32) {
+          // 128-byte rows, SWIZZLE_128B: 16-byte chunk j of row `lane` lives at chunk j ^ (lane & 7)
+          const uint32_t rowaddr = slot + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t a = rowaddr + ((uint32_t)(j ^ (lane & 7)) << 4);
+            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (has_residual) {
+              const uint4 rr = lds128(a);
+              o.x += __uint_as_float(rr.x); o.y += __uint_as_float(rr.y);
+              o.z += __uint_as_float(rr.z); o.w += __uint_as_float(rr.w);
+            }
+            sts128(a, make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
+          }
+        } else {
+          // 64-byte rows, SWIZZLE_64B: 16-byte chunk j of row `lane` lives at chunk j ^ ((lane >> 1) & 3)
+          const uint32_t rowaddr = slot + lane * 64;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t a = rowaddr + ((uint32_t)(j ^ ((lane >> 1) & 3)) << 4);
+            sts128(a, make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                 pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7])));
+          }
+        }
+        fence_async_smem();                            // generic-proxy writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmC, slot, colw + c * CHUNK, row0);
+          bulk_commit();
+        }
+      }
+      // this warp has read its part of the accumulator: release the TMEM stage to the leader's MMA thread
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * as);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (lane == 0) bulk_wait_read<0>();                // smem must stay valid until the last store has read it
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();          // both CTAs are done with both TMEMs
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)C2::kTmemCols) : "memory");
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;   // resolved once; benign race (same value)
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+w2vs_status_t make_map(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t inner,
+                       uint64_t rows, uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_rows,
+                       CUtensorMapSwizzle sw) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return W2VS_CUDA_ERROR; }
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {row_stride_elems * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: %d (inner=%llu rows=%llu stride=%llu box=%ux%u)", (int)r,
+              (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)row_stride_elems, box_inner,
+              box_rows);
+    return W2VS_CUDA_ERROR;
+  }
+  return W2VS_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, typename TC>
+w2vs_status_t launch_bn(const GemmArgs& g, cudaStream_t st) {
+  using C2 = Cfg2<BN, TC>;
+  alignas(64) CUtensorMap tmA, tmB, tmC;
+  const int64_t a_row_len = g.lda;
+  const uint64_t a_inner = (uint64_t)(g.K <= a_row_len ? g.K : a_row_len);
+  W2VS_TRY(make_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.A, a_inner, (uint64_t)g.a_rows, (uint64_t)a_row_len,
+                    BK, BM, CU_TENSOR_MAP_SWIZZLE_128B));
+  W2VS_TRY(make_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.W, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.K, BK,
+                    BN / 2, CU_TENSOR_MAP_SWIZZLE_128B));
+  if (sizeof(TC) == 4)
+    W2VS_TRY(make_map(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.C, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc,
+                      CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+  else
+    W2VS_TRY(make_map(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.C, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc,
+                      CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C2::kSmemBytes);
+    if (e != cudaSuccess) { set_error("gemm_tc2 smem attribute: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
+    attr_done = true;
+  }
+  const int tiles = (int)(ceil_div64(g.M, 2 * BM) * ceil_div64(g.N, BN));
+  const int max_clusters = num_sms() / 2;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  gemm_tc2_kernel<BN, TC><<<2 * clusters, N_THREADS, C2::kSmemBytes, st>>>(
+      tmA, tmB, tmC, g.bias, g.residual != nullptr ? 1 : 0, g.M, g.N, g.K, (int)a_row_len,
+      (g.flags & W2VS_EPI_GELU) ? 1 : 0);
+  W2VS_CHECK_LAUNCH("gemm_tc2_kernel");
+  return W2VS_OK;
+}
+
+template <typename TC>
+w2vs_status_t launch_typed(const GemmArgs& g, cudaStream_t st) {
+  if (g.N % 256 == 0) return launch_bn<256, TC>(g, st);
+  if (g.N % 128 == 0) return launch_bn<128, TC>(g, st);
+  if (g.N % 64 == 0 && g.N < 256) return launch_bn<64, TC>(g, st);
+  return launch_bn<256, TC>(g, st);
+}
+
+}  // namespace
+
+w2vs_status_t launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
+  W2VS_REQUIRE(g.dtype_ab == W2VS_BF16, "tcgen05 GEMM takes bf16 operands");
+  W2VS_REQUIRE(g.K % 8 == 0 && g.N % 8 == 0, "GEMM needs K % 8 == 0 and N % 8 == 0");
+  W2VS_REQUIRE(g.lda % 8 == 0 && g.ldc % 8 == 0, "GEMM leading dims must be multiples of 8");
+  W2VS_REQUIRE(g.K <= g.lda || g.lda % BK == 0, "wrapped (conv) A rows need lda % 64 == 0");
+  W2VS_REQUIRE(((uintptr_t)g.A & 15) == 0 && ((uintptr_t)g.W & 15) == 0 && ((uintptr_t)g.C & 15) == 0,
+               "GEMM operands must be 16-byte aligned");
+  W2VS_REQUIRE(g.residual == nullptr || (g.dtype_c == W2VS_F32 && g.residual == (const float*)g.C),
+               "tcgen05 GEMM adds the residual in place (residual == C, fp32)");
+  if (g.M <= 0) return W2VS_OK;
+  return g.dtype_c == W2VS_F32 ? launch_typed<float>(g, st) : launch_typed<bf16>(g, st);
+}
+
+w2vs_status_t debug_read_tc2_fault(int* out) {
+  int v = 0;
+  cudaError_t e = cudaMemcpyFromSymbol(&v, g_tc2_fault, sizeof(int));
+  if (e != cudaSuccess) { set_error("read g_tc2_fault: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
+  *out = v;
+  return W2VS_OK;
+}
+
+}  // namespace w2vs

@@ -13,7 +13,7 @@ struct Conv0Args {
   const float *w, *bias, *gamma, *beta;
   void* out; int out_dtype;
   int B, T0, rows_per_utt, C, k, stride, norm;
-  double* gn_stats;
+  float* gn_stats;   // [B][C][2] scale/shift + [B][ceil(T0/256)][2][C] partials (GroupNorm mode)
 };
 w2vs_status_t launch_conv0(const Conv0Args& a, cudaStream_t st);
 
@@ -64,18 +64,36 @@ struct GemmArgs {
   int M, N, K; int dtype_ab, dtype_c; int flags;
 };
 w2vs_status_t launch_gemm_simt(const GemmArgs& g, cudaStream_t st);
-w2vs_status_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
+w2vs_status_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st);    // 1-CTA tcgen05 (first version)
+w2vs_status_t launch_gemm_tc2(const GemmArgs& g, cudaStream_t st);   // CTA-pair tcgen05, TMA-store epilogue
 w2vs_status_t launch_gemm(int impl, const GemmArgs& g, cudaStream_t st);  // impl: w2vs_gemm_impl_t
 w2vs_status_t debug_read_tc_fault(int* out);
+w2vs_status_t debug_read_tc2_fault(int* out);
 
 // ---- attention ------------------------------------------------------------------------------------
+// Two modes share the kernels:
+//   block mode (n_step_q == 0): queries = keys = the M = T2 + nb*rc tokens of `qkv` [B, M, 3D]; visibility
+//       from (T2, main_ctx, rc) + key padding bytes.
+//   step mode  (n_step_q  > 0): incremental inference -- n_step_q query tokens per stream (rows of `qkv`,
+//       [B, n_step_q, 3D]) attend to the first n_step_keys rows of a K/V cache [B, kv_rows, 2D] (K | V per
+//       row); everything is visible, no padding.
 struct AttnArgs {
   const void* qkv; const uint8_t* keypad; void* ctx; int dtype;
   int B, T2, main_ctx, rc, heads, D;
+  int n_step_q, n_step_keys; const void* kv_cache; int64_t kv_rows;
 };
 w2vs_status_t launch_attention_simt(const AttnArgs& a, cudaStream_t st);
 w2vs_status_t launch_attention_mma(const AttnArgs& a, cudaStream_t st);
 w2vs_status_t launch_attention(int impl, const AttnArgs& a, cudaStream_t st);
+
+// ---- incremental mode data movement (k_stream.cu) ------------------------------------------------------
+w2vs_status_t launch_concat_rows(void* dst, int64_t dst_bs_bytes, const void* srcA, int64_t a_bs_bytes, int offA,
+                                 int cA, const void* srcB, int64_t b_bs_bytes, int nB, int row_bytes, int B,
+                                 cudaStream_t st);
+w2vs_status_t launch_concat_wav(float* dst, int64_t dst_bs, const float* srcA, int64_t a_bs, int offA, int cA,
+                                const void* src_new, int new_dtype, int64_t new_bs, int n, int B, cudaStream_t st);
+w2vs_status_t launch_kv_append(const void* qkv, void* cache, int64_t cache_rows, int row0, int n_tok, int D,
+                               int elem_bytes, int B, cudaStream_t st);
 
 // ---- positional conv + weight packing -----------------------------------------------------------------
 struct PosConvArgs {

@@ -239,7 +239,9 @@ void make_workspace(const w2vs_config* cfg, const Geometry& g, int B, Workspace*
       if (ln && bytes > tmp) tmp = bytes;
     }
   ws->conv_tmp = tmp ? b.take(tmp) : kNone;
-  ws->gn_stats = b.take((size_t)B * cfg->conv_dim[0] * 2 * sizeof(double));
+  ws->gn_stats = cfg->extractor_mode == W2VS_EXTRACTOR_DEFAULT
+                     ? b.take((size_t)B * cfg->conv_dim[0] * 2 * 4 * (1 + (size_t)(g.conv_len[0] + 255) / 256))
+                     : kNone;
   const int D = cfg->embed_dim, F = cfg->ffn_dim;
   ws->feats = b.take((size_t)B * g.conv_rows[n - 1] * D * 4);
   ws->frame_pad = b.take((size_t)B * g.T);

@@ -434,6 +434,79 @@ class Wav2VecSModel(nn.Module):
         return out, (out_mask if has_mask else None)
 
 
+class EncoderStream:
+    """Incremental encoder state of B lock-step streams (w2vs_stream_*): conv carry buffers, the
+    projected-frame buffer and the per-layer K/V cache of finalised main frames live on the device.
+
+    ``step(new_samples, flush)`` feeds [B, n] new samples and returns the frames that became final,
+    time-major [n_out, B, D].  flush: 0 none, 1 final (end of stream), 2 peek (also return the
+    not-yet-final tail as the offline encoder would compute it on the current prefix)."""
+
+    NONE, FINAL, PEEK = 0, 1, 2
+
+    def __init__(self, model, B, max_frames, max_new_samples, main_context=None, right_context=None):
+        device, dtype = model._device_dtype()
+        self.model, self.B, self.device, self.dtype = model, B, device, dtype
+        self.main = model.encoder.main_context if main_context is None else main_context
+        self.rc = model.encoder.right_context if right_context is None else right_context
+        self.max_frames, self.max_new = int(max_frames), int(max_new_samples)
+        self.ccfg, self.packed = model._ensure_packed(self.max_frames + 2)
+        lib = cabi.lib()
+        hb, db, wb = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        cabi.check(lib.w2vs_stream_state_size(C.byref(self.ccfg), B, self.max_frames, self.max_new, self.main,
+                                              self.rc, C.byref(hb), C.byref(db), C.byref(wb)),
+                   "w2vs_stream_state_size")
+        self.host_state = C.create_string_buffer(hb.value)
+        self.d_state = torch.empty(db.value, dtype=torch.uint8, device=device)
+        self.ws = torch.empty(wb.value, dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream().cuda_stream
+            cabi.check(lib.w2vs_stream_init(C.byref(self.ccfg), B, self.max_frames, self.max_new, self.main,
+                                            self.rc, self.host_state, hb.value, self.d_state.data_ptr(), db.value,
+                                            C.c_void_p(stream)), "w2vs_stream_init")
+        self.D = model.args.encoder_embed_dim
+        self.samples = 0
+        self.out_cap = 0
+        self._out = None
+
+    def step(self, new_samples=None, flush=0):
+        n_new = 0 if new_samples is None else int(new_samples.size(1))
+        src_ptr, wdt = None, cabi.F32
+        if n_new:
+            if new_samples.size(0) != self.B:
+                raise ValueError("new_samples must be [B, n]")
+            if new_samples.device != self.device:
+                raise RuntimeError("new_samples must be on the model's CUDA device")
+            if new_samples.dtype not in (torch.float32, torch.bfloat16):
+                new_samples = new_samples.float()
+            new_samples = new_samples.contiguous()
+            src_ptr = new_samples.data_ptr()
+            wdt = cabi.BF16 if new_samples.dtype == torch.bfloat16 else cabi.F32
+        # every call can emit at most the frames the new samples complete plus the pending tail
+        cap = n_new // 320 + 2 * (self.main + self.rc) + 2
+        out = torch.empty((cap, self.B, self.D), dtype=self.dtype, device=self.device)
+        n_out = C.c_int32(0)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            cabi.check(cabi.lib().w2vs_stream_step(C.byref(self.ccfg), self.packed.data_ptr(), self.host_state,
+                                                   self.d_state.data_ptr(), src_ptr, wdt, n_new, int(flush),
+                                                   out.data_ptr(), cap, C.byref(n_out), self.ws.data_ptr(),
+                                                   self.ws.numel(), C.c_void_p(stream)), "w2vs_stream_step")
+        self.samples += n_new
+        return out[: n_out.value]
+
+    def final_frames(self) -> int:
+        """Frames of committed blocks (their outputs never change again)."""
+        v = C.c_int32(0)
+        cabi.check(cabi.lib().w2vs_stream_info(self.host_state, None, None, C.byref(v)), "w2vs_stream_info")
+        return v.value
+
+    def frames(self) -> int:
+        v = C.c_int32(0)
+        cabi.check(cabi.lib().w2vs_stream_info(self.host_state, None, C.byref(v), None), "w2vs_stream_info")
+        return v.value
+
+
 class BlockWiseWav2Vec2Model(Wav2VecSModel):
     """rain API (rain/layers/unidirect_w2v2_encoder.py:443-531): time-major output dict."""
 
@@ -443,8 +516,14 @@ class BlockWiseWav2Vec2Model(Wav2VecSModel):
 
     def forward(self, source, padding_mask=None, incremental_state=None, finished=False, is_infer=False,
                 src_lengths=None, mask_len=None):
-        # `incremental_state` is accepted and ignored exactly as in the reference (the code path
-        # that would use it is dead, unidirect_w2v2_encoder.py:262-264).
+        # The reference threads `incremental_state` through but never uses it (the code path is dead,
+        # unidirect_w2v2_encoder.py:262-264) and re-encodes the whole prefix on every call.  Here a
+        # dict passed as `incremental_state` together with is_infer=True switches to the cached
+        # incremental path: `source` is still the whole prefix (as the reference driver passes it),
+        # only the samples not seen before are encoded, and the return value is the same full-prefix
+        # tensor the reference would have produced.
+        if incremental_state is not None and is_infer:
+            return self._forward_incremental(source, incremental_state, finished)
         drop = bool(is_infer and not finished and self.encoder.right_context > 0)
         ctx = (self.encoder.main_context, self.encoder.right_context)
         if src_lengths is not None:
@@ -469,6 +548,41 @@ class BlockWiseWav2Vec2Model(Wav2VecSModel):
     def extract_features(self, source, padding_mask, mask=False):
         return self._encode(source, padding_mask=padding_mask, layout=cabi.LAYOUT_BTD,
                             context=(self.encoder.main_context, self.encoder.right_context))
+
+    def open_stream(self, B=1, max_seconds=60.0, max_new_samples=4 * 5120 + 8000):
+        """Incremental encoder state for B lock-step live streams (see EncoderStream)."""
+        max_frames = int(max_seconds * 16000) // 320 + 1
+        return EncoderStream(self, B, max_frames, max_new_samples)
+
+    def _forward_incremental(self, source, incremental_state, finished):
+        st = incremental_state.get("w2vs_stream")
+        B, L = source.shape
+        if st is None:
+            st = dict(stream=self.open_stream(B), frames=[])
+            incremental_state["w2vs_stream"] = st
+        stream, hist = st["stream"], st["frames"]
+        if L < stream.samples or B != stream.B:
+            raise ValueError("incremental forward needs a growing prefix of the same streams")
+        pos = stream.samples
+        while True:                       # feed at most max_new samples per call
+            n = min(L - pos, stream.max_new)
+            last = pos + n >= L
+            flush = (EncoderStream.FINAL if finished else EncoderStream.PEEK) if last else EncoderStream.NONE
+            before = stream.final_frames()
+            out = stream.step(source[:, pos:pos + n] if n else None, flush)
+            n_final = stream.final_frames() - before
+            if n_final:
+                hist.append(out[:n_final])   # frames of whole blocks never change again
+            pos += n
+            if last:
+                break
+        x = torch.cat(hist + [out[n_final:]], 0)   # + the tail as the reference computes it on this prefix
+        rc = self.encoder.right_context
+        if not finished and rc > 0:
+            x = x[: max(x.size(0) - rc, 0)]
+        pm = torch.zeros((B, x.size(0)), dtype=torch.bool, device=x.device)
+        return {"encoder_out": [x], "encoder_padding_mask": [pm], "encoder_embedding": [], "encoder_states": [],
+                "src_tokens": [], "src_lengths": [], "dec1_state": [], "dec1_padding_mask": []}
 
 
 class OnlineW2V2TransformerEncoder(nn.Module):

@@ -36,7 +36,13 @@ def gemm(A, W, bias=None, residual=None, out_dtype=None, gelu=False, impl=cabi.G
     M = A.size(0) if M is None else M
     lda = A.stride(0) if lda is None else lda
     out_dtype = out_dtype or A.dtype
-    Cm = torch.empty((M, N), dtype=out_dtype, device=A.device)
+    if residual is not None:
+        # the library adds the residual in place (C aliases the residual, as the encoder's residual stream does)
+        assert out_dtype == torch.float32 and tuple(residual.shape) == (M, N)
+        Cm = residual.to(torch.float32).clone()
+        residual = Cm
+    else:
+        Cm = torch.empty((M, N), dtype=out_dtype, device=A.device)
     flags = cabi.EPI_GELU if gelu else 0
     cabi.check(cabi.lib().w2vs_op_gemm(impl, _dt(A), _dt(Cm), _ptr(A), lda, _ptr(W), _ptr(bias), _ptr(residual),
                                        _ptr(Cm), N, M, N, K, flags, _stream(A)), "w2vs_op_gemm")
