@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--workload", default="large_64x20s", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-detail", action="store_true", help="per-kernel (name, shape) device ms in the JSON line")
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
@@ -297,7 +298,7 @@ def main():
     # ---- per-kernel-class device time of one step (CUDA events on the launching stream) -----
     prof = None
     if hasattr(cabi.lib(), "w2vs_prof_enable"):
-        prof = cabi.profile_step(step_device, reps=2)
+        prof = cabi.profile_step(step_device, reps=2, detail=a.kernel_detail)
     barrier()
 
     if rank == 0:
@@ -320,12 +321,15 @@ def main():
         if prof is not None and prof.get("gemm", {}).get("count"):
             gm = prof["gemm"]
             ach = fl["gemm"] * B / (gm["ms"] / 1e3) / 1e12
-            line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (all launches of one step)",
+            line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc2_kernel (all launches of one step)",
                                 "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                                 "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
                                 "peak_source": pk_kind + " (sustained: timed inside a long step)",
                                 "launches_per_step": gm["count"], "ms_per_step": gm["ms"]}
-            line["kernel_ms_per_step"] = {k: round(v["ms"], 3) for k, v in prof.items()}
+            line["kernel_ms_per_step"] = {k: round(v["ms"], 3) for k, v in prof.items() if "[" not in k and "_kernel" not in k}
+            if a.kernel_detail:
+                line["kernel_detail"] = {k: [round(v["ms"], 3), v["count"]] for k, v in sorted(prof.items())
+                                         if "[" in k or "_kernel" in k}
         else:
             line["roofline"] = None
         if not a.no_cpu_baseline:

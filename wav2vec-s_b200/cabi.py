@@ -120,7 +120,7 @@ def launch_count(reset=False):
     return int(lib().w2vs_launch_count(1 if reset else 0))
 
 
-def profile_step(fn, reps=1):
+def profile_step(fn, reps=1, detail=False):
     """Run ``fn`` (one step on the current stream) ``reps`` times with per-launch event timing;
     returns {class: {"ms": per-step device ms, "count": launches per step}}."""
     import torch
@@ -136,8 +136,9 @@ def profile_step(fn, reps=1):
     out = {}
     for line in buf.value.decode().splitlines():
         name, ms, cnt = line.rsplit(" ", 2)
-        cls = KERNEL_CLASS.get(name, "rows")
-        d = out.setdefault(cls, {"ms": 0.0, "count": 0})
-        d["ms"] += float(ms) / reps
-        d["count"] += int(cnt) // reps
+        cls = KERNEL_CLASS.get(name.split("[")[0], "rows")
+        for key in (cls,) + ((name,) if detail else ()):
+            d = out.setdefault(key, {"ms": 0.0, "count": 0})
+            d["ms"] += float(ms) / reps
+            d["count"] += int(cnt) // reps
     return out

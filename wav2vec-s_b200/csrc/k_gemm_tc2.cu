@@ -455,7 +455,14 @@ w2vs_status_t launch_bn(const GemmArgs& g, cudaStream_t st) {
   gemm_tc2_kernel<BN, TC><<<2 * clusters, N_THREADS, C2::kSmemBytes, st>>>(
       tmA, tmB, tmC, g.bias, g.residual != nullptr ? 1 : 0, g.M, g.N, g.K, (int)a_row_len,
       (g.flags & W2VS_EPI_GELU) ? 1 : 0);
-  W2VS_CHECK_LAUNCH("gemm_tc2_kernel");
+  if (g_prof_on) {
+    char name[96];
+    snprintf(name, sizeof(name), "gemm_tc2_kernel[M=%d,N=%d,K=%d,lda=%lld,%s%s%s]", g.M, g.N, g.K, (long long)g.lda,
+             sizeof(TC) == 4 ? "f32" : "bf16", g.residual ? ",res" : "", (g.flags & W2VS_EPI_GELU) ? ",gelu" : "");
+    W2VS_CHECK_LAUNCH(name);
+  } else {
+    W2VS_CHECK_LAUNCH("gemm_tc2_kernel");
+  }
   return W2VS_OK;
 }
 
