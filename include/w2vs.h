@@ -189,7 +189,8 @@ w2vs_status_t w2vs_op_layernorm(int32_t dtype_in, const void* d_x, int64_t ldx, 
                                 void* d_out_act, int64_t ldo, int32_t rows, int32_t N,
                                 int32_t gelu, void* stream);
 /* Block-masked attention over a token buffer qkv [B, M, 3D] (q|k|v), M = T' + (T'/main)*rc,
- * key padding [B, M] (1 = masked with -inf).  ctx [B, M, D]. impl: 0 auto, 1 SIMT, 2 tensor-core. */
+ * key padding [B, M] (1 = masked with -inf).  ctx [B, M, D].
+ * impl: 0 auto, 1 SIMT fp32-accumulate, 2 mma.sync flash kernel, 3 tcgen05/TMEM kernel (bf16). */
 w2vs_status_t w2vs_op_attention(int32_t impl, int32_t dtype, const void* d_qkv,
                                 const uint8_t* d_keypad, void* d_ctx, int32_t B, int32_t T_pad,
                                 int32_t main_ctx, int32_t right_ctx, int32_t heads, int32_t D,

@@ -226,12 +226,13 @@ w2vs_status_t w2vs_encode(const w2vs_config* cfg, const void* d_packed, const w2
     ga.W = at<void>(W, wl.conv[i].w); ga.bias = at<float>(W, wl.conv[i].bias); ga.residual = nullptr;
     ga.M = B * g.conv_rows[i]; ga.N = cout; ga.K = k * cin; ga.dtype_ab = adt;
     if (ln) {
-      // pre-norm activations in fp32 (Fp32LayerNorm computes its statistics in fp32)
-      void* tmp = adt == W2VS_F32 ? dst : at<void>(d_ws, ws.conv_tmp);
-      ga.C = tmp; ga.ldc = cout; ga.dtype_c = W2VS_F32; ga.flags = 0;
+      // The pre-norm activation is stored in the model dtype, exactly like the reference module chain
+      // (Conv1d output dtype -> Fp32LayerNorm upcasts it, layer_norm.py:39-50); LayerNorm + GELU run in place
+      // with fp32 statistics.
+      ga.C = dst; ga.ldc = cout; ga.dtype_c = adt; ga.flags = 0;
       W2VS_TRY(launch_gemm(gemm_impl, ga, st));
       LayerNormArgs la{};
-      la.x = tmp; la.in_dtype = W2VS_F32; la.ldx = cout;
+      la.x = dst; la.in_dtype = adt; la.ldx = cout;
       la.gamma = at<float>(W, wl.conv[i].norm_w); la.beta = at<float>(W, wl.conv[i].norm_b);
       la.out_f32 = nullptr; la.out_act = dst; la.act_dtype = adt; la.ldo = cout;
       la.rows = ga.M; la.N = cout; la.gelu = 1;
@@ -418,7 +419,8 @@ w2vs_status_t launch_gemm(int impl, const GemmArgs& g, cudaStream_t st) {
 
 w2vs_status_t launch_attention(int impl, const AttnArgs& a, cudaStream_t st) {
   W2VS_REQUIRE(a.dtype == W2VS_F32 || a.dtype == W2VS_BF16, "attention dtype");
-  if (impl == 0) impl = a.dtype == W2VS_BF16 ? 2 : 1;
+  if (impl == 0) impl = a.dtype == W2VS_BF16 ? (a.n_step_q > 0 ? 2 : 3) : 1;
+  if (impl == 3) return launch_attention_tc(a, st);
   if (impl == 2) {
     W2VS_REQUIRE(a.dtype == W2VS_BF16, "tensor-core attention takes bf16");
     return launch_attention_mma(a, st);

@@ -86,21 +86,32 @@ __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
 }
 
 // ---- math --------------------------------------------------------------------------------------
-// erf GELU, x * Phi(x) (torch nn.GELU / fairseq modules/gelu.py:24-25).  erf by Abramowitz-Stegun
-// 7.1.26 (|abs err| <= 1.5e-7) with one MUFU.RCP + one MUFU.EX2: about half the instructions of
-// erff(), which matters because GELU runs in GEMM epilogues that must keep pace with tcgen05.
+// erf GELU, x * Phi(x) (torch nn.GELU / fairseq modules/gelu.py:24-25).  erf by Abramowitz-Stegun 7.1.26
+// (|abs err| <= 1.5e-7) with one MUFU.RCP + one MUFU.EX2 issued as the raw approx instructions: 14
+// instructions, no branches.  (__frcp_rn / exp2f() expand to ~28 instructions with a slow-path call, which
+// made the fc1 epilogue 2.5x slower than the MMAs it has to keep pace with.)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
   p *= t;
-  const float e = exp2f(-z * z * 1.4426950408889634f);
+  const float e = ex2_approx(-z * z * 1.4426950408889634f);
   const float erf_abs = fmaf(-p, e, 1.0f);          // erf(|x|/sqrt2)
-  const float phi2 = 1.0f + copysignf(erf_abs, x);  // 1 + erf(x/sqrt2)
-  return 0.5f * x * phi2;
+  const float hx = 0.5f * x;
+  return fmaf(copysignf(erf_abs, x), hx, hx);       // 0.5 x (1 + erf(x/sqrt2))
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -83,7 +83,8 @@ struct AttnArgs {
   int n_step_q, n_step_keys; const void* kv_cache; int64_t kv_rows;
 };
 w2vs_status_t launch_attention_simt(const AttnArgs& a, cudaStream_t st);
-w2vs_status_t launch_attention_mma(const AttnArgs& a, cudaStream_t st);
+w2vs_status_t launch_attention_mma(const AttnArgs& a, cudaStream_t st);   // mma.sync flash kernel (also step mode)
+w2vs_status_t launch_attention_tc(const AttnArgs& a, cudaStream_t st);    // tcgen05 / TMEM kernel (block mode)
 w2vs_status_t launch_attention(int impl, const AttnArgs& a, cudaStream_t st);
 
 // ---- incremental mode data movement (k_stream.cu) ------------------------------------------------------

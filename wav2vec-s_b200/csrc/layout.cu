@@ -231,14 +231,6 @@ void make_workspace(const w2vs_config* cfg, const Geometry& g, int B, Workspace*
   }
   ws->conv_a = b.take(ping);
   ws->conv_b = b.take(pong ? pong : 256);
-  size_t tmp = 0;
-  if (cfg->dtype != W2VS_F32)
-    for (int i = 1; i < n; ++i) {
-      const bool ln = cfg->extractor_mode == W2VS_EXTRACTOR_LAYER_NORM && i < cfg->layer_norm_num;
-      const size_t bytes = ((size_t)B * g.conv_rows[i] + 64) * cfg->conv_dim[i] * 4;
-      if (ln && bytes > tmp) tmp = bytes;
-    }
-  ws->conv_tmp = tmp ? b.take(tmp) : kNone;
   ws->gn_stats = cfg->extractor_mode == W2VS_EXTRACTOR_DEFAULT
                      ? b.take((size_t)B * cfg->conv_dim[0] * 2 * 4 * (1 + (size_t)(g.conv_len[0] + 255) / 256))
                      : kNone;

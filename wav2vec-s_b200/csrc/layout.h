@@ -63,7 +63,6 @@ inline LayerW layer_at(const WeightLayout& wl, int n) {
 // ---- workspace (full-utterance forward) --------------------------------------------------------
 struct Workspace {
   size_t conv_a, conv_b;       // act ping/pong [B*rows_i + slack][C_i]
-  size_t conv_tmp;             // fp32 [B*rows_1][C] pre-LayerNorm conv output (bf16 models only)
   size_t gn_stats;             // fp32 [B][C0][2] + per-CTA partials (GroupNorm mode only)
   size_t feats;                // fp32 [B*rows_last][D]  (post_extract_proj output)
   size_t frame_pad;            // u8 [B][T]

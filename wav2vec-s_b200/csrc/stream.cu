@@ -46,7 +46,7 @@ struct StreamLayout {
   // device state
   size_t in[W2VS_MAX_CONV][2], fbuf, kv, kv_layer_bytes, dev_total;
   // workspace
-  size_t out[2], conv_tmp, normed, feats_tmp, x, xa, qkv, ctx, h, ws_total;
+  size_t out[2], normed, feats_tmp, x, xa, qkv, ctx, h, ws_total;
 };
 
 inline bool conv_has_ln(const w2vs_config* cfg, int i) {
@@ -107,16 +107,13 @@ w2vs_status_t make_stream_layout(const w2vs_config* cfg, int B, int max_frames, 
   L->dev_total = d.off;
 
   Bump w;
-  size_t o[2] = {0, 0}, tmp = 0;
+  size_t o[2] = {0, 0};
   for (int i = 0; i < n; ++i) {
     const size_t bytes = ((size_t)B * L->out_cap[i] + 128) * cfg->conv_dim[i] * as;
     if (bytes > o[i & 1]) o[i & 1] = bytes;
-    const size_t t = ((size_t)B * L->out_cap[i] + 128) * cfg->conv_dim[i] * 4;
-    if (i > 0 && conv_has_ln(cfg, i) && cfg->dtype != W2VS_F32 && t > tmp) tmp = t;
   }
   L->out[0] = w.take(o[0]);
   L->out[1] = w.take(o[1] ? o[1] : 256);
-  L->conv_tmp = w.take(tmp ? tmp : 256);
   const size_t last_rows = (size_t)B * L->out_cap[n - 1] + 128;
   L->normed = w.take(last_rows * cfg->conv_dim[n - 1] * as);
   L->feats_tmp = w.take(last_rows * D * 4);
@@ -328,11 +325,10 @@ w2vs_status_t w2vs_stream_step(const w2vs_config* cfg, const void* d_packed, voi
         ga.W = at<void>(W, wl.conv[i].w); ga.bias = at<float>(W, wl.conv[i].bias); ga.residual = nullptr;
         ga.M = (B - 1) * L.out_cap[i] + n_o[i]; ga.N = cout; ga.K = k * cin; ga.dtype_ab = adt; ga.ldc = cout;
         if (ln) {
-          void* tmp = adt == W2VS_F32 ? out : at<void>(d_ws, L.conv_tmp);
-          ga.C = tmp; ga.dtype_c = W2VS_F32; ga.flags = 0;
+          ga.C = out; ga.dtype_c = adt; ga.flags = 0;
           W2VS_TRY(launch_gemm(W2VS_GEMM_AUTO, ga, st));
           LayerNormArgs la{};
-          la.x = tmp; la.in_dtype = W2VS_F32; la.ldx = cout;
+          la.x = out; la.in_dtype = adt; la.ldx = cout;
           la.gamma = at<float>(W, wl.conv[i].norm_w); la.beta = at<float>(W, wl.conv[i].norm_b);
           la.out_f32 = nullptr; la.out_act = out; la.act_dtype = adt; la.ldo = cout;
           la.rows = ga.M; la.N = cout; la.gelu = 1;
