@@ -86,11 +86,6 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 // named barrier over the 128 softmax threads with an OR reduction of a predicate
 __device__ __forceinline__ bool softmax_bar_or(bool pred) {
   uint32_t out;
@@ -230,33 +225,57 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const uint8_t* __restr
     }
   } else {
     // ===================== softmax warps: one query row per thread =====================
+    // Visibility of the 128 key columns of a tile for one query row is a contiguous column range [lo, hi):
+    //   main keys: columns whose block <= qblock(row)  ->  [0, (qb+1)*main - k0)
+    //   look-ahead keys: the rc copies owned by qblock(row)  ->  [T2 + qb*rc - k0, +rc)
+    // so 32-column chunks are classified per warp as all-visible (no masking), none-visible (no loads, no
+    // exponentials: P = 0) or partial (one range compare per element).  Tiles that contain padded keys take
+    // the general per-key path (s_info), which also covers arbitrary (non-prefix) padding masks.
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;                 // row inside the query tile == TMEM lane
     const int st = (warp - 2) * 32 + lane;               // 0..127: key column this thread describes
     const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const int my_qb = row < q_count ? qblock(q_first + row) : -1;
+    // rows past the end of the tile behave like the last valid row (their output is never stored); this keeps
+    // the chunk classification uniform across the warp
+    const int my_qb = row < q_count ? qblock(q_first + row) : qb_hi;
     const uint8_t* kp = keypad + (size_t)b * M;
     float m_ref = -INFINITY, l = 0.f;
     bool ok = true;
 
     int k0, cnt; bool s1;
     uint8_t kp_next = 1;
-    if (n_kt > 0) { ts.get(0, k0, cnt, s1); kp_next = st < cnt ? kp[k0 + st] : 1; }
+    if (n_kt > 0) { ts.get(0, k0, cnt, s1); kp_next = st < cnt ? kp[k0 + st] : 0; }
 
     for (int it = 0; it < n_kt && ok; ++it) {
       ts.get(it, k0, cnt, s1);
-      // ---- describe key column `st` of this tile; the barrier publishes it and ORs the "needs mask" flag
+      // ---- per-key description for the general path; the barrier publishes it and ORs "tile has padding"
+      const bool padded = st < cnt && kp_next != 0;
       int info;
-      const bool valid = st < cnt && kp_next == 0;
-      if (valid) info = s1 ? (k0 + st - T2) / rcd : (k0 + st) / main_ctx;
+      if (st < cnt && !padded) info = s1 ? (k0 + st - T2) / rcd : (k0 + st) / main_ctx;
       else info = s1 ? -2 : INT_MAX;
       int* info_t = s_info + (it & 1) * KT;
       info_t[st] = info;
-      const bool need_mask = softmax_bar_or(s1 || !valid || info > qb_lo);
+      const bool has_pad = softmax_bar_or(padded);
       if (it + 1 < n_kt) {   // prefetch the padding byte of the next tile's column
         int k0n, cntn; bool s1n;
         ts.get(it + 1, k0n, cntn, s1n);
-        kp_next = st < cntn ? kp[k0n + st] : 1;
+        kp_next = st < cntn ? kp[k0n + st] : 0;
+      }
+      // ---- visible column range of this row
+      int lo = 0, hi = 0;
+      if (my_qb >= 0) {
+        if (!s1) { hi = min(max((my_qb + 1) * main_ctx - k0, 0), cnt); }
+        else if (my_qb <= nb - 1) { lo = min(max(T2 + my_qb * rc - k0, 0), cnt); hi = min(max(T2 + (my_qb + 1) * rc - k0, 0), cnt); }
+      }
+      const uint32_t span = (uint32_t)(hi - lo);
+      // chunk classes, warp-uniform: bit c of all_vis / none_vis
+      uint32_t all_vis = 0, none_vis = 0;
+#pragma unroll
+      for (int c = 0; c < KT / 32; ++c) {
+        const bool a = !has_pad && lo <= c * 32 && c * 32 + 32 <= hi;
+        const bool n = (!has_pad && (hi <= c * 32 || lo >= c * 32 + 32 || span == 0)) || c * 32 >= cnt;
+        all_vis |= (uint32_t)__all_sync(0xffffffffu, a) << c;
+        none_vis |= (uint32_t)__all_sync(0xffffffffu, n) << c;
       }
       ok = mbar_wait(bar_sfull, it & 1);
       tc_fence_after();
@@ -265,26 +284,31 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const uint8_t* __restr
       float mx = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < KT / 32; ++c) {
+        if ((none_vis >> c) & 1u) continue;
         uint32_t r[32];
         tmem_ld32(tlane + S_COL + c * 32, r);
         tmem_ld_wait();
-        if (need_mask) {
+        if ((all_vis >> c) & 1u) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+        } else if (!has_pad) {
+          const int off = c * 32 - lo;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (uint32_t)(off + j) < span ? __uint_as_float(r[j]) : -INFINITY);
+        } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int ki = info_t[c * 32 + j];
             const bool vis = s1 ? (ki == my_qb) : (ki <= my_qb);
             mx = fmaxf(mx, vis ? __uint_as_float(r[j]) : -INFINITY);
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
         }
       }
       // ---- running maximum with lazy rescale (exact: the final normalisation uses the same reference)
       const float m_tile = mx * scale_log2;               // -inf stays -inf
       const bool grow = m_tile > m_ref + RESCALE_THRESHOLD;
       float alpha = 1.0f;
-      if (grow) { alpha = ex2(m_ref - m_tile); m_ref = m_tile; l *= alpha; }
+      if (grow) { alpha = ex2_approx(m_ref - m_tile); m_ref = m_tile; l *= alpha; }
       if (it > 0) {
         ok = mbar_wait(bar_pvdone, (it - 1) & 1) && ok;   // PV(it-1) retired: P is free, O is stable
         tc_fence_after();
@@ -303,31 +327,59 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const uint8_t* __restr
       const float m_use = m_ref == -INFINITY ? 0.f : m_ref;
 
       // ---- sweep 2: P = exp2(s * scale - m), row sum, bf16 P -> TMEM
+      const int last_read = 31 - __clz((int)(~none_vis & 0xfu));   // last chunk whose scores are read (-1: none)
+      if (last_read < 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_local(bar_sfree);
+      }
 #pragma unroll 1
       for (int c = 0; c < KT / 32; ++c) {
+        uint32_t pk[16];
+        if ((none_vis >> c) & 1u) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = 0u;
+          tmem_st16(tlane + P_COL + c * 16, pk);
+          continue;
+        }
         uint32_t r[32];
         tmem_ld32(tlane + S_COL + c * 32, r);
         tmem_ld_wait();
-        if (c == KT / 32 - 1) {       // every score of this tile has been read: S may be overwritten
+        if (c == last_read) {         // every score of this tile has been read: S may be overwritten
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_local(bar_sfree);
         }
-        uint32_t pk[16];
+        if ((all_vis >> c) & 1u) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float s0 = __uint_as_float(r[j]), s1v = __uint_as_float(r[j + 1]);
-          if (need_mask) {
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(r[j]), scale_log2, -m_use));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), scale_log2, -m_use));
+            l += p0 + p1;
+            pk[j >> 1] = pack_bf16x2(p0, p1);
+          }
+        } else if (!has_pad) {
+          const int off = c * 32 - lo;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float s0 = (uint32_t)(off + j) < span ? __uint_as_float(r[j]) : -INFINITY;
+            const float s1v = (uint32_t)(off + j + 1) < span ? __uint_as_float(r[j + 1]) : -INFINITY;
+            const float p0 = ex2_approx(fmaf(s0, scale_log2, -m_use));
+            const float p1 = ex2_approx(fmaf(s1v, scale_log2, -m_use));
+            l += p0 + p1;
+            pk[j >> 1] = pack_bf16x2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
             const int k0i = info_t[c * 32 + j], k1i = info_t[c * 32 + j + 1];
             const bool v0 = s1 ? (k0i == my_qb) : (k0i <= my_qb);
             const bool v1 = s1 ? (k1i == my_qb) : (k1i <= my_qb);
-            s0 = v0 ? s0 : -INFINITY;
-            s1v = v1 ? s1v : -INFINITY;
+            const float p0 = ex2_approx(fmaf(v0 ? __uint_as_float(r[j]) : -INFINITY, scale_log2, -m_use));
+            const float p1 = ex2_approx(fmaf(v1 ? __uint_as_float(r[j + 1]) : -INFINITY, scale_log2, -m_use));
+            l += p0 + p1;
+            pk[j >> 1] = pack_bf16x2(p0, p1);
           }
-          const float p0 = ex2(fmaf(s0, scale_log2, -m_use));
-          const float p1 = ex2(fmaf(s1v, scale_log2, -m_use));
-          l += p0 + p1;
-          pk[j >> 1] = pack_bf16x2(p0, p1);
         }
         tmem_st16(tlane + P_COL + c * 16, pk);
       }

@@ -1,12 +1,13 @@
 // Layer-0 feature-extractor convolution: Conv1d(1 -> C, k, stride s), no padding, with its
 // normalisation + GELU fused (ConvFeatureExtractionModel block 0, wav2vec2.py:715-752,773-781).
 //
-// HBM-streaming kernel: reads the waveform once, writes the channels-last activation [B, rows, C]
-// once.  One warp produces whole frames: lane l owns channel pairs {2l + 64 i, 2l + 64 i + 1}, so a
-// warp-wide store of one `i` is one contiguous 128 B (bf16) / 256 B (fp32) segment, and the
-// per-frame LayerNorm over C is a warp-shuffle reduction.  The C*k filter taps of a lane's channels
-// live in registers for the whole CTA lifetime (160 registers for C=512,k=10), so the inner loop is
-// pure FFMA on broadcast waveform samples.
+// Streaming kernel: reads the waveform once, writes the channels-last activation [B, rows, C] once.
+// One warp produces whole frames: lane l owns channel pairs {2l + 64 i, 2l + 64 i + 1}, so a warp-wide
+// store of one `i` is one contiguous 128 B (bf16) / 256 B (fp32) segment and the per-frame LayerNorm
+// over C is a warp-shuffle reduction.  The filter taps (tap-major) and the CTA's waveform slice sit
+// in shared memory; a warp iteration computes 4 frames so that each 8-byte weight read feeds 8 FFMAs.
+// Registers stay under 128 (two CTAs = 16 warps per SM): the kernel is bound by the ~30 ALU
+// instructions per output element of LayerNorm + erf-GELU, not by HBM (65.5 MB per 20 s utterance).
 //
 // Modes:  PLAIN     y = gelu(conv + bias)
 //         LN        y = gelu(LayerNorm_C(conv + bias))            (extractor_mode = layer_norm)
@@ -20,20 +21,36 @@ namespace w2vs {
 
 enum { C0_PLAIN = 0, C0_LN = 1, C0_GN_STATS = 2, C0_GN_APPLY = 3 };
 
+constexpr int kFramesPerCta = 256;
+constexpr int FPI = 4;   // frames per warp iteration
+
 template <typename TIn, typename TOut, int NI, int KW, int MODE>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 2)
 conv0_kernel(const TIn* __restrict__ wav, int64_t wav_ld, const float* __restrict__ w,
              const float* __restrict__ bias, const float* __restrict__ gamma,
              const float* __restrict__ beta, TOut* __restrict__ out, int rows_per_utt, int T0,
              int stride, float* __restrict__ gn_stats, int frames_per_cta) {
   constexpr int C = NI * 64;
-  __shared__ float s_bias[C];
-  __shared__ float s_scale[C];   // LN: gamma; GN_APPLY: gamma * rstd
-  __shared__ float s_shift[C];   // LN: beta;  GN_APPLY: beta - mean * gamma * rstd
-  __shared__ float s_red[MODE == C0_GN_STATS ? 8 * 2 * C : 1];  // GN_STATS: per-warp partials
+  extern __shared__ __align__(16) float smem[];
+  float* s_w = smem;                       // [KW][C]  tap-major: a lane's channel pairs are 8-byte contiguous
+  float* s_bias = s_w + KW * C;            // [C]
+  float* s_scale = s_bias + C;             // LN: gamma; GN_APPLY: gamma * rstd
+  float* s_shift = s_scale + C;            // LN: beta;  GN_APPLY: beta - mean * gamma * rstd
+  float* s_x = s_shift + C;                // waveform samples of this CTA: (frames_per_cta - 1) * stride + KW
+  float* s_red = s_x + ((kFramesPerCta - 1) * 8 + KW + 3) / 4 * 4;   // GN_STATS: [8 warps][2][C]
 
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int t_begin = blockIdx.x * frames_per_cta;
+  const int t_end = min(t_begin + frames_per_cta, T0);
+  const int n_frames = t_end - t_begin;
+  const TIn* x = wav + (size_t)b * wav_ld + (size_t)t_begin * stride;
+  const int n_samples = (n_frames - 1) * stride + KW;
+  for (int i = threadIdx.x; i < n_samples; i += blockDim.x) s_x[i] = to_f32(x[i]);
+  for (int i = threadIdx.x; i < KW * C; i += blockDim.x) {
+    const int j = i / C, c = i % C;
+    s_w[i] = w[(size_t)c * KW + j];
+  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     s_bias[c] = bias ? bias[c] : 0.f;
     if (MODE == C0_LN) {
@@ -44,14 +61,6 @@ conv0_kernel(const TIn* __restrict__ wav, int64_t wav_ld, const float* __restric
       s_shift[c] = gn_stats[((size_t)b * C + c) * 2 + 1];
     }
   }
-  // filter taps of this lane's channels -> registers
-  float wr[NI][2][KW];
-#pragma unroll
-  for (int i = 0; i < NI; ++i)
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-      for (int j = 0; j < KW; ++j) wr[i][h][j] = w[(size_t)(2 * lane + 64 * i + h) * KW + j];
   __syncthreads();
 
   float st_sum[NI][2], st_sq[NI][2];
@@ -59,38 +68,34 @@ conv0_kernel(const TIn* __restrict__ wav, int64_t wav_ld, const float* __restric
 #pragma unroll
     for (int i = 0; i < NI; ++i) { st_sum[i][0] = st_sum[i][1] = 0.f; st_sq[i][0] = st_sq[i][1] = 0.f; }
   }
-
-  const int t_begin = blockIdx.x * frames_per_cta;
-  const int t_end = min(t_begin + frames_per_cta, T0);
-  const TIn* x = wav + (size_t)b * wav_ld;
   const int nwarps = blockDim.x >> 5;
 
-  for (int t0 = t_begin + 2 * warp; t0 < t_end; t0 += 2 * nwarps) {
-    const bool has2 = (t0 + 1) < t_end;
-    float acc[2][NI][2];
+  for (int f0 = FPI * warp; f0 < n_frames; f0 += FPI * nwarps) {
+    float acc[FPI][NI][2];
 #pragma unroll
-    for (int f = 0; f < 2; ++f)
+    for (int i = 0; i < NI; ++i) {
+      const float2 bb = *reinterpret_cast<const float2*>(s_bias + 64 * i + 2 * lane);
 #pragma unroll
-      for (int i = 0; i < NI; ++i) {
-        acc[f][i][0] = s_bias[2 * lane + 64 * i];
-        acc[f][i][1] = s_bias[2 * lane + 64 * i + 1];
-      }
-    const int64_t base = (int64_t)t0 * stride;
+      for (int f = 0; f < FPI; ++f) { acc[f][i][0] = bb.x; acc[f][i][1] = bb.y; }
+    }
 #pragma unroll
     for (int j = 0; j < KW; ++j) {
-      const float x0 = to_f32(x[base + j]);
-      const float x1 = has2 ? to_f32(x[base + stride + j]) : 0.f;
+      float xv[FPI];
+#pragma unroll
+      for (int f = 0; f < FPI; ++f) xv[f] = (f0 + f) < n_frames ? s_x[(f0 + f) * stride + j] : 0.f;   // broadcast
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
-        acc[0][i][0] = fmaf(wr[i][0][j], x0, acc[0][i][0]);
-        acc[0][i][1] = fmaf(wr[i][1][j], x0, acc[0][i][1]);
-        acc[1][i][0] = fmaf(wr[i][0][j], x1, acc[1][i][0]);
-        acc[1][i][1] = fmaf(wr[i][1][j], x1, acc[1][i][1]);
+        const float2 ww = *reinterpret_cast<const float2*>(s_w + j * C + 64 * i + 2 * lane);
+#pragma unroll
+        for (int f = 0; f < FPI; ++f) {
+          acc[f][i][0] = fmaf(ww.x, xv[f], acc[f][i][0]);
+          acc[f][i][1] = fmaf(ww.y, xv[f], acc[f][i][1]);
+        }
       }
     }
 #pragma unroll
-    for (int f = 0; f < 2; ++f) {
-      if (f == 1 && !has2) break;
+    for (int f = 0; f < FPI; ++f) {
+      if (f0 + f >= n_frames) break;
       if (MODE == C0_GN_STATS) {
 #pragma unroll
         for (int i = 0; i < NI; ++i)
@@ -103,10 +108,10 @@ conv0_kernel(const TIn* __restrict__ wav, int64_t wav_ld, const float* __restric
       }
       float mean = 0.f, rstd = 1.f;
       if (MODE == C0_LN) {
-        float s = 0.f;
+        float sm = 0.f;
 #pragma unroll
-        for (int i = 0; i < NI; ++i) s += acc[f][i][0] + acc[f][i][1];
-        mean = warp_sum(s) * (1.0f / C);
+        for (int i = 0; i < NI; ++i) sm += acc[f][i][0] + acc[f][i][1];
+        mean = warp_sum(sm) * (1.0f / C);
         float q = 0.f;
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
@@ -116,17 +121,21 @@ conv0_kernel(const TIn* __restrict__ wav, int64_t wav_ld, const float* __restric
         }
         rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / C) + 1e-5f);
       }
-      TOut* o = out + ((size_t)b * rows_per_utt + (t0 + f)) * C;
+      TOut* o = out + ((size_t)b * rows_per_utt + (t_begin + f0 + f)) * C;
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
         const int c = 2 * lane + 64 * i;
         float v0 = acc[f][i][0], v1 = acc[f][i][1];
-        if (MODE == C0_LN) {
-          v0 = (v0 - mean) * rstd * s_scale[c] + s_shift[c];
-          v1 = (v1 - mean) * rstd * s_scale[c + 1] + s_shift[c + 1];
-        } else if (MODE == C0_GN_APPLY) {
-          v0 = fmaf(v0, s_scale[c], s_shift[c]);
-          v1 = fmaf(v1, s_scale[c + 1], s_shift[c + 1]);
+        if (MODE == C0_LN || MODE == C0_GN_APPLY) {
+          const float2 sc = *reinterpret_cast<const float2*>(s_scale + c);
+          const float2 sh = *reinterpret_cast<const float2*>(s_shift + c);
+          if (MODE == C0_LN) {
+            v0 = (v0 - mean) * rstd * sc.x + sh.x;
+            v1 = (v1 - mean) * rstd * sc.y + sh.y;
+          } else {
+            v0 = fmaf(v0, sc.x, sh.x);
+            v1 = fmaf(v1, sc.y, sh.y);
+          }
         }
         v0 = gelu_erf(v0);
         v1 = gelu_erf(v1);
@@ -152,7 +161,7 @@ conv0_kernel(const TIn* __restrict__ wav, int64_t wav_ld, const float* __restric
     float* part = gn_stats + (size_t)gridDim.y * C * 2 + ((size_t)b * gridDim.x + blockIdx.x) * 2 * C;
     for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
       float acc = 0.f;
-      for (int w = 0; w < 8; ++w) acc += s_red[(w * 2 + c / C) * C + (c % C)];
+      for (int w8 = 0; w8 < 8; ++w8) acc += s_red[(w8 * 2 + c / C) * C + (c % C)];
       part[c] = acc;
     }
   }
@@ -180,13 +189,22 @@ conv0_gn_finalize_kernel(float* __restrict__ gn_stats, const float* __restrict__
   }
 }
 
-constexpr int kFramesPerCta = 256;
-
 template <typename TIn, typename TOut, int NI, int MODE>
 static w2vs_status_t launch_one(const Conv0Args& a, cudaStream_t st) {
+  constexpr int C = NI * 64, KW = 10;
   const int frames_per_cta = kFramesPerCta;
+  W2VS_REQUIRE(a.stride >= 1 && a.stride <= 8, "first conv stride must be <= 8");
+  size_t smem = (size_t)(KW * C + 3 * C + ((kFramesPerCta - 1) * 8 + KW + 3) / 4 * 4) * sizeof(float);
+  if (MODE == C0_GN_STATS) smem += (size_t)8 * 2 * C * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv0_kernel<TIn, TOut, NI, KW, MODE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("conv0 smem attribute: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
+    attr_done = true;
+  }
   dim3 grid((unsigned)ceil_div64(a.T0, frames_per_cta), (unsigned)a.B);
-  conv0_kernel<TIn, TOut, NI, 10, MODE><<<grid, 256, 0, st>>>(
+  conv0_kernel<TIn, TOut, NI, KW, MODE><<<grid, 256, smem, st>>>(
       (const TIn*)a.wav, a.wav_ld, a.w, a.bias, a.gamma, a.beta, (TOut*)a.out, a.rows_per_utt, a.T0,
       a.stride, a.gn_stats, frames_per_cta);
   W2VS_CHECK_LAUNCH("conv0_kernel");

@@ -137,7 +137,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t phase = 0, aphase = 0;
       bool ok = true;
       for (int tile = cluster_id; tile < n_tiles && ok; tile += n_clusters) {
-        if (!(ok = mbar_wait(bar_tempty + 8 * as, aphase ^ 1))) break;
+        if (!(ok = mbar_wait_cluster(bar_tempty + 8 * as, aphase ^ 1))) break;   // peer CTA's epilogue arrives here
         tc_fence_after();
         const uint32_t tmem_c = tmem_base + (uint32_t)(as * BN);
         for (int kb = 0; kb < num_kb; ++kb) {

@@ -34,7 +34,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// CTA-scope wait (the default).  NB: an .acquire.cluster wait makes ptxas emit CCTL.IVALL (L1 invalidate)
+// after every probe, so the cluster-scope variant below is reserved for barriers that peer CTAs arrive on.
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -54,7 +65,19 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   const unsigned long long t0 = global_ns();
   unsigned spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ff) == 0 && global_ns() - t0 > WAIT_TIMEOUT_NS) {
+    if ((++spins & 0xfff) == 0 && global_ns() - t0 > WAIT_TIMEOUT_NS) {
+      atomicExch(W2VS_TC_FAULT_FLAG, 1);
+      return false;
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return true;
+  const unsigned long long t0 = global_ns();
+  unsigned spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 0xfff) == 0 && global_ns() - t0 > WAIT_TIMEOUT_NS) {
       atomicExch(W2VS_TC_FAULT_FLAG, 1);
       return false;
     }
