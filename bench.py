@@ -36,6 +36,10 @@ WORKLOADS = {
     "large_64x30s": ("large", 64, 30),
     "large_8x20s": ("large", 8, 20),
     "tiny_4x2s": ("tiny", 4, 2),
+    # incremental (SimulEval-style) inference: configs[3]; B streams in lock-step, 30 s each
+    "stream_large_b1": ("large", 1, 30),
+    "stream_large_b16": ("large", 16, 30),
+    "stream_tiny_b2": ("tiny", 2, 6),
 }
 SR = 16000
 
@@ -165,6 +169,106 @@ def cpu_reference_run(cfg_kind, B, seconds, steps, warmup):
                 ms_per_step=t * 1e3)
 
 
+def stream_bench(a, kind, B, seconds):
+    """configs[3]: chunk-by-chunk incremental inference with cached left context.  First chunk = 24 frames
+    (7760 samples), then `--step-blocks` x 16 frames per decision step (5120 samples per block), as the
+    SimulEval agent feeds the encoder (rain/simul/transducer_searcher.py:712-721).  Reports p50 per-chunk
+    device latency; the reference arm re-encodes the whole prefix per step (what the reference does)."""
+    import torch
+    cfg = model_cfg(kind)
+    L = seconds * SR
+    step = 5120 * a.step_blocks
+    bounds = [7760]
+    while bounds[-1] + step < L:
+        bounds.append(bounds[-1] + step)
+    bounds.append(L)
+    metric = f"p50 per-chunk latency (wav2vec-S {kind} incremental, batch {B}, {16 * a.step_blocks} frames/step)"
+    config = {"workload": f"wav2vec-S {kind} incremental encoder, {B} stream(s) x {seconds} s, first chunk 24 frames, "
+                          f"then {16 * a.step_blocks} frames per step, {a.dtype}", "name": a.workload,
+              "chunks": len(bounds), "l2_policy": "weights (613 MB bf16) exceed the 126 MB L2"}
+    if a.impl == "reference":
+        from oracle import synth
+        from oracle import w2vs_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        ocfg = O.default_cfg(**cfg)
+        sd = synth.make_state_dict(ocfg, 0)
+        wav = synth.make_waveform(1, L, 1234)
+        sel = bounds[:: max(1, len(bounds) // 8)][:8]     # bounded sample of the decision steps
+        times = []
+        for n in sel:
+            t0 = time.perf_counter()
+            O.rain_forward(sd, ocfg, wav[:, :n], None, finished=(n >= L), is_infer=True)
+            times.append((time.perf_counter() - t0) * 1e3)
+        v = statistics.median(times)
+        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": "ms", "n_gpus": a.gpus,
+                          "steps": len(sel), "warmup": 0, "ms_per_step": v, "higher_is_better": False,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": v, "unit": "ms", "cores": os.cpu_count(), "kind": "port",
+                                           "sample": f"prefix re-encoding of 1 stream at {len(sel)} of {len(bounds)} decision steps"},
+                          "e2e": {"value": v, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
+    import wav2vec_s_b200 as W
+    from wav2vec_s_b200 import cabi
+    from wav2vec_s_b200.model import EncoderStream
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    dtype = torch.bfloat16 if a.dtype == "bf16" else torch.float32
+    torch.manual_seed(0)
+    model = W.BlockWiseWav2Vec2Model(cfg).to(dev, dtype).eval()
+    g = torch.Generator().manual_seed(1234)
+    wav_host = torch.randn(B, L, generator=g).pin_memory()
+    wav = wav_host.to(dev)
+
+    def run(e2e):
+        st = model.open_stream(B=B, max_seconds=seconds + 1, max_new_samples=max(7760, step) + 400)
+        lat, pos, outs = [], 0, 0
+        for n in bounds:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            ev0.record()
+            chunk = wav_host[:, pos:n].to(dev, non_blocking=True) if e2e else wav[:, pos:n]
+            y = st.step(chunk, EncoderStream.FINAL if n >= L else EncoderStream.NONE)
+            if e2e:
+                y = y.to("cpu", non_blocking=True)
+            ev1.record()
+            torch.cuda.synchronize()
+            lat.append(ev0.elapsed_time(ev1))
+            outs += y.size(0)
+            pos = n
+        return lat, outs
+
+    for _ in range(max(1, a.warmup // 3)):
+        run(False)
+    cabi.launch_count(reset=True)
+    sampler = ClockSampler(0)
+    sampler.start()
+    lats = []
+    for _ in range(max(1, a.steps // 5)):
+        lat, frames = run(False)
+        lats += lat[1:-1]
+    launches = cabi.launch_count(reset=True)
+    clocks = sampler.stop()
+    lat_e2e, _ = run(True)
+    p50 = statistics.median(lats)
+    fl = flops_per_utt(cfg, L)
+    wbytes = 613e6 if kind == "large" else 179e6
+    pk, pk_kind = peaks()
+    line = {"metric": metric, "value": p50, "unit": "ms", "n_gpus": 1, "steps": len(lats), "warmup": a.warmup,
+            "ms_per_step": p50, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": a.dtype,
+            "data": "synthetic", "config": config, "clocks": clocks,
+            "p90_ms": sorted(lats)[int(0.9 * len(lats))], "frames_emitted": frames,
+            "realtime_factor": (16 * a.step_blocks * 0.02) / (p50 / 1e3),
+            "e2e": {"value": statistics.median(lat_e2e[1:-1]), "unit": "ms", "h2d_bytes_per_step": B * step * 4,
+                    "d2h_bytes_per_step": 16 * a.step_blocks * B * cfg["encoder_embed_dim"] * 2},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "one decision step = weights streamed once per block",
+                         "achieved": wbytes * a.step_blocks / (p50 / 1e3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": wbytes * a.step_blocks / (p50 / 1e3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                         "peak_source": pk_kind}}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -176,7 +280,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-detail", action="store_true", help="per-kernel (name, shape) device ms in the JSON line")
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
+    ap.add_argument("--step-blocks", type=int, default=1, help="streaming workloads: blocks of 16 frames per decision step")
     a = ap.parse_args()
+    if a.workload.startswith("stream_"):
+        kind, B, seconds = WORKLOADS[a.workload]
+        if int(os.environ.get("RANK", "0")) == 0:
+            stream_bench(a, kind, B, seconds)
+        return
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
 
     rank = int(os.environ.get("RANK", "0"))

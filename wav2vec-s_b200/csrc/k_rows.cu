@@ -94,12 +94,87 @@ static w2vs_status_t ln_dispatch(const LayerNormArgs& a, cudaStream_t st) {
   return W2VS_OK;
 }
 
+// fp32-input fast path (the 2 LayerNorms of every transformer layer): lane owns float4 slices at
+// 4*lane + 128*j, so every warp load is one fully coalesced 512-byte request (the generic kernel's
+// 8-element chunks cost two half-used requests per fp32 chunk).
+template <typename TAct, int NV>
+__global__ void __launch_bounds__(256)
+layernorm_f32_kernel(const float* x, int64_t ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     float* out_f32, TAct* out_act, int64_t ldo, int rows, int gelu) {
+  constexpr int N = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + (size_t)row * ldx + 4 * lane;
+  float4 v[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) v[j] = *reinterpret_cast<const float4*>(xr + 128 * j);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  const float mean = warp_sum(s) * (1.0f / N);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+    q = fmaf(a, a, q); q = fmaf(b, b, q); q = fmaf(c, c, q); q = fmaf(d, d, q);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / N) + 1e-5f);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * lane + 128 * j);
+    const float4 bt = *reinterpret_cast<const float4*>(beta + 4 * lane + 128 * j);
+    float4 y;
+    y.x = (v[j].x - mean) * rstd * g.x + bt.x;
+    y.y = (v[j].y - mean) * rstd * g.y + bt.y;
+    y.z = (v[j].z - mean) * rstd * g.z + bt.z;
+    y.w = (v[j].w - mean) * rstd * g.w + bt.w;
+    if (gelu) { y.x = gelu_erf(y.x); y.y = gelu_erf(y.y); y.z = gelu_erf(y.z); y.w = gelu_erf(y.w); }
+    const size_t o = (size_t)row * ldo + 4 * lane + 128 * j;
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = y;
+    if (out_act) {
+      if (sizeof(TAct) == 4) {
+        *reinterpret_cast<float4*>(out_act + o) = y;
+      } else {
+        uint2 u;
+        u.x = pack_bf16x2(y.x, y.y);
+        u.y = pack_bf16x2(y.z, y.w);
+        *reinterpret_cast<uint2*>(out_act + o) = u;
+      }
+    }
+  }
+}
+
+template <typename TAct>
+static w2vs_status_t ln_f32_dispatch(const LayerNormArgs& a, cudaStream_t st) {
+  const int wpb = 8;
+  dim3 grid((unsigned)ceil_div64(a.rows, wpb));
+#define W2VS_LNF_CASE(NV)                                                                          \
+  layernorm_f32_kernel<TAct, NV><<<grid, wpb * 32, 0, st>>>((const float*)a.x, a.ldx, a.gamma, a.beta, a.out_f32, \
+                                                            (TAct*)a.out_act, a.ldo, a.rows, a.gelu)
+  switch (a.N / 128) {
+    case 1: W2VS_LNF_CASE(1); break;
+    case 2: W2VS_LNF_CASE(2); break;
+    case 4: W2VS_LNF_CASE(4); break;
+    case 6: W2VS_LNF_CASE(6); break;
+    case 8: W2VS_LNF_CASE(8); break;
+    default: return W2VS_UNSUPPORTED;
+  }
+#undef W2VS_LNF_CASE
+  W2VS_CHECK_LAUNCH("layernorm_rows_kernel");
+  return W2VS_OK;
+}
+
 w2vs_status_t launch_layernorm(const LayerNormArgs& a, cudaStream_t st) {
   W2VS_REQUIRE(a.N % 8 == 0 && a.N >= 8 && a.N <= 2048, "LayerNorm width must be a multiple of 8, <= 2048");
   W2VS_REQUIRE(a.ldx % 8 == 0 && a.ldo % 8 == 0, "LayerNorm leading dims must be multiples of 8");
   if (a.rows <= 0) return W2VS_OK;
-  if (a.in_dtype == W2VS_F32)
+  if (a.in_dtype == W2VS_F32) {
+    const int nv = a.N / 128;
+    if (a.N % 128 == 0 && (nv == 1 || nv == 2 || nv == 4 || nv == 6 || nv == 8))
+      return a.act_dtype == W2VS_F32 ? ln_f32_dispatch<float>(a, st) : ln_f32_dispatch<bf16>(a, st);
     return a.act_dtype == W2VS_F32 ? ln_dispatch<float, float>(a, st) : ln_dispatch<float, bf16>(a, st);
+  }
   return a.act_dtype == W2VS_F32 ? ln_dispatch<bf16, float>(a, st) : ln_dispatch<bf16, bf16>(a, st);
 }
 
