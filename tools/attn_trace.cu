@@ -22,6 +22,10 @@ int main() {
   AttnArgs a{};
   a.qkv = qkv; a.keypad = kp; a.ctx = ctx; a.dtype = W2VS_BF16; a.B = B; a.T2 = T2; a.main_ctx = main_ctx; a.rc = rc;
   a.heads = heads; a.D = D;
+  { int nb = 0; cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, attn_tc_kernel, N_THREADS, SMEM_BYTES);
+    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, attn_tc_kernel);
+    printf("occupancy: %d CTAs/SM (regs %d, static smem %zu, dyn smem %d)\n", nb, fa.numRegs, fa.sharedSizeBytes, SMEM_BYTES); }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int i = 0; i < 3; ++i) launch_attention_tc(a, 0);
   cudaEventRecord(e0);
@@ -30,19 +34,19 @@ int main() {
   cudaDeviceSynchronize();
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   printf("attn_tc: %.1f us per launch (B=%d)  err=%s\n", ms * 100, B, cudaGetErrorString(cudaGetLastError()));
-  static long long tr[2][64][8];
+  static long long tr[2][64][12];
   cudaMemcpyFromSymbol(tr, g_attn_trace, sizeof(tr));
   long long t0 = tr[0][0][0];
-  printf("softmax warp0: tile | bar_in bar_out sfull sweep1+xch pvdone/rescale sweep2 pfull   (cycles since first event)\n");
+  printf("softmax warp0: tile | bar_in Sloaded sfull max+xch rescaled exp_done pfull pvdone_seen after_any before_sfull_wait (cycles since first event)\n");
   for (int it = 0; it < 12; ++it) {
     printf("%2d |", it);
-    for (int e = 0; e < 7; ++e) printf(" %7lld", tr[0][it][e] ? tr[0][it][e] - t0 : -1);
+    for (int e = 0; e < 11; ++e) printf(" %7lld", tr[0][it][e] ? tr[0][it][e] - t0 : -1);
     printf("\n");
   }
-  printf("MMA thread: tile | loop_top sfree_done S_issued vfull pfull_done PV_issued\n");
+  printf("MMA thread: tile | loop_top sfree_done S_issued vfull pfull_done PV_issued [S_done PV_done]\n");
   for (int it = 0; it < 12; ++it) {
     printf("%2d |", it);
-    for (int e = 0; e < 6; ++e) printf(" %7lld", tr[1][it][e] ? tr[1][it][e] - t0 : -1);
+    for (int e = 0; e < 8; ++e) printf(" %7lld", tr[1][it][e] ? tr[1][it][e] - t0 : -1);
     printf("\n");
   }
   return 0;

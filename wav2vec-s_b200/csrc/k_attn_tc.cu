@@ -5,21 +5,26 @@
 // visibility derived from (T', main, rc) and the key-padding bytes; key tiles invisible to a whole query tile
 // are never loaded, tiles entirely below the block diagonal skip the per-element mask.
 //
-// One CTA = 128 query tokens of one (utterance, head); two CTAs are resident per SM so that one CTA's
-// softmax overlaps the other's MMAs.  Roles (320 threads):
-//   (warp ids: softmax 0-7, loader 8, MMA 9 -- the SMSP arbiter favours high warp ids and the two
-//    single-thread roles are on the critical path of every tile)
-//   warp 8   TMA loader   Q once; K and V tiles of 128 keys through two 2-stage rings (128B-swizzled smem)
-//   warp 9   MMA issuer   S = Q K^T  (tcgen05.mma M=128,N=128,K=64: A,B K-major from smem -> TMEM cols 0..127)
-//                         O += P V   (M=128,N=64,K=128: A = P bf16 from TMEM cols 128..191, B = V MN-major from
-//                         smem -> TMEM cols 192..255); also owns the TMEM allocation (256 columns)
-//   warps 0-7 softmax     two threads per query row (warp w and w+4 share TMEM lane quarter w&3, each owns 64 of
-//                         the 128 key columns): tcgen05.ld S, mask, running max (halves exchanged through smem;
-//                         lazy rescale of O: only when the max grows by more than 2^8), exp2 (ex2.approx), row
-//                         sum, P -> TMEM (tcgen05.st); final O / l -> bf16 -> global.  16 softmax warps per SM
-//                         keep the MUFU / FMA pipes busy (4 warps per SMSP issued only ~0.25 IPC each).
-// S(i+1) is issued as soon as the softmax threads have read S(i), i.e. it overlaps softmax(i)'s exponentials
-// and PV(i).  TMEM budget: S 128 + P 64 + O 64 = 256 columns per CTA.
+// One persistent CTA per SM runs two independent pipelines ("groups", each with its own work-item stream, smem
+// rings, barriers and half of TMEM); one work item = 128 query tokens of one (utterance, head).  Two groups
+// per SM let one group's load/max/store phases hide under the other's exponentials.  The register file is
+// repartitioned with setmaxnreg (softmax warpgroups 216 registers, MMA warpgroup 40): register allocation is
+// per 4 warps, so two 5-warp CTAs per SM would not fit.
+// Roles per group (warps 0-3 / 4-7 softmax of group 0 / 1, warp 8 / 9 MMA of group 0 / 1, warps 10-11 idle):
+//   4 warps    softmax     one query row per thread (TMEM lane = row): the 128 scores of a key tile are read from
+//                          TMEM exactly once into registers (tcgen05.ld) and S is handed back to the MMA thread at
+//                          once, so S(g+1) is computed while this tile's exponentials run; range mask, row max
+//                          (thread-local, no cross-thread traffic), lazy rescale of O (only when the max grows by
+//                          more than 2^8), exp2 (ex2.approx, packed f32x2 FMAs/adds around it), row sum, bf16 P ->
+//                          TMEM (tcgen05.st); per item: O / l -> bf16 -> global.
+//   1 warp     MMA issuer  (one thread; it also issues the TMA loads, at the points where it has just observed that a
+//                          ring slot is free: S(g) retired -> K(g+2); PV(g) retired -> V(g+2); last S of an item
+//                          -> next Q -- no loader warp, no "empty" barriers)
+//                          S = Q K^T  (tcgen05.mma M=128,N=128,K=64: A,B K-major from smem -> TMEM cols 0..127)
+//                          O += P V   (M=128,N=64,K=128: A = P bf16 from TMEM cols 128..191, B = V MN-major from
+//                          smem -> TMEM cols 192..255); owns the TMEM allocation (256 columns).
+// The kernel is bound by the MUFU pipe (16 exp2 / clk / SM: 1024 cycles per 128x128 tile) once everything else
+// overlaps.  TMEM budget: S 128 + P 64 + O 64 = 256 columns per group, 512 per CTA.
 #include <math.h>
 #include <limits.h>
 #include <cuda.h>
@@ -29,7 +34,7 @@
 namespace w2vs {
 __device__ int g_attn_tc_fault = 0;
 #ifdef W2VS_ATTN_TRACE
-__device__ long long g_attn_trace[2][64][8];   // [role: 0 softmax warp 0, 1 MMA thread][tile][event] (clock64)
+__device__ long long g_attn_trace[2][64][12];   // [role: 0 softmax warp 0, 1 MMA thread][tile][event] (clock64)
 #define TRACE(role, it, ev) do { if (trace_on && (it) < 64) g_attn_trace[role][it][ev] = clock64(); } while (0)
 #else
 #define TRACE(role, it, ev) do { } while (0)
@@ -45,9 +50,12 @@ using namespace tc;
 constexpr int QT = 128, KT = 128, HD = 64;
 constexpr int TILE_BYTES = 128 * HD * 2;     // 16 KB: Q, K or V tile
 constexpr int NS = 2;                        // K ring and V ring depth
-constexpr int N_SOFTMAX_WARPS = 8, LOADER_WARP = 8, MMA_WARP = 9, N_THREADS = 320;
-constexpr int SMEM_BYTES = TILE_BYTES * (1 + 2 * NS) + 2 * KT * 4 /*info*/ + 2 * 2 * QT * 4 /*exchange*/ + 256 + 1024;
-constexpr uint32_t TMEM_COLS = 256, S_COL = 0, P_COL = 128, O_COL = 192;
+constexpr int N_SOFTMAX_WARPS = 4;            // per group
+constexpr int N_GROUPS = 2, N_THREADS = 384;  // warps 0-7 softmax (two groups), 8-9 MMA, 10-11 idle
+constexpr int REGS_SOFTMAX = 232, REGS_OTHER = 40;
+constexpr int GROUP_SMEM = TILE_BYTES * (1 + 2 * NS);
+constexpr int SMEM_BYTES = N_GROUPS * GROUP_SMEM + 256 /*barriers*/ + 1024 /*align*/;
+constexpr uint32_t TMEM_COLS = 512, GROUP_COLS = 256, S_COL = 0, P_COL = 128, O_COL = 192;
 constexpr float RESCALE_THRESHOLD = 8.0f;    // log2 units
 
 __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
@@ -97,21 +105,6 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// named barrier over the 256 softmax threads with an OR reduction of a predicate
-__device__ __forceinline__ bool softmax_bar_or(bool pred) {
-  uint32_t out;
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\t"
-      "barrier.cta.red.or.pred.aligned p, 1, 256, q;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(out) : "r"((uint32_t)pred) : "memory");
-  return out != 0;
-}
-
-// barrier between the two warps that share a TMEM lane quarter (ids 2..5, 64 threads)
-__device__ __forceinline__ void pair_bar(int quarter) {
-  asm volatile("barrier.cta.sync.aligned %0, 64;" ::"r"(2 + quarter) : "memory");
-}
 // packed fp32 pairs (sm_100): one instruction for two lanes of the softmax arithmetic
 __device__ __forceinline__ uint64_t pack2(float a, float b) {
   uint64_t r;
@@ -141,349 +134,431 @@ struct TileSeq {   // key tiles visible to one query tile
   }
 };
 
-__global__ void __launch_bounds__(N_THREADS, 2)
+// Runtime divisors get host-computed magic multipliers (floor(x/d) == umulhi(x, ceil(2^32/d)) for x < 2^32/d;
+// the launcher checks the ranges): a single thread walks the work list, and a hardware-less 32-bit division
+// costs ~50 dependent instructions -- with half a dozen of them per work item the item switch used to take
+// longer than two key tiles.
+struct Shape {
+  int T2, M, main_ctx, rc, rcd, nb, D, H, B, n_main_tiles, n_tiles;
+  int HB, n_vcta, g_div, g_mod;         // H*B; pipelines in the grid (work-list stride), stride / HB, stride % HB
+  uint32_t magic_main, magic_rcd, magic_H;
+};
+__device__ __forceinline__ int fdiv(int x, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)x, magic) : x; }  // magic 0: d == 1
+
+// One work item = one query tile of one (utterance, head).  Items are ordered heaviest first (late query
+// tiles see the most keys) and dealt round-robin to the G = 2 * gridDim.x pipelines: pipeline c takes w = c, c+G, ...
+// Walker keeps (tile rank, hb) = (w / HB, w % HB) incrementally.
+struct Walker {
+  int w, rank, hb;
+  __device__ __forceinline__ void init(const Shape& sh, int vcta) {
+    w = vcta;
+    rank = 0; hb = w;
+    while (hb >= sh.HB) { hb -= sh.HB; ++rank; }
+  }
+  __device__ __forceinline__ void next(const Shape& sh) {
+    w += sh.n_vcta;
+    rank += sh.g_div; hb += sh.g_mod;
+    if (hb >= sh.HB) { hb -= sh.HB; ++rank; }
+  }
+};
+struct Item {
+  int q_first, q_count, qb_lo, qb_hi, h, row_base;
+  TileSeq ts;
+};
+__device__ __forceinline__ int qblock_of(const Shape& sh, int m) {
+  return m < sh.T2 ? fdiv(m, sh.magic_main) : fdiv(m - sh.T2, sh.magic_rcd);
+}
+__device__ __forceinline__ Item item_of(const Shape& sh, const Walker& wk) {
+  Item it;
+  const int tile_id = sh.n_tiles - 1 - wk.rank;
+  const int b = fdiv(wk.hb, sh.magic_H);
+  it.h = wk.hb - b * sh.H;
+  it.row_base = b * sh.M;
+  if (tile_id < sh.n_main_tiles) { it.q_first = tile_id * QT; it.q_count = min(QT, sh.T2 - it.q_first); }
+  else { it.q_first = sh.T2 + (tile_id - sh.n_main_tiles) * QT; it.q_count = min(QT, sh.M - it.q_first); }
+  it.qb_lo = qblock_of(sh, it.q_first);
+  it.qb_hi = qblock_of(sh, it.q_first + it.q_count - 1);
+  it.ts.seg0_end = min(sh.main_ctx * (it.qb_hi + 1), sh.T2);
+  it.ts.seg1_begin = it.ts.seg1_end = 0;
+  if (sh.rc > 0 && it.qb_lo <= sh.nb - 1) {
+    it.ts.seg1_begin = sh.T2 + sh.rc * it.qb_lo;
+    it.ts.seg1_end = sh.T2 + sh.rc * (min(it.qb_hi, sh.nb - 1) + 1);
+  }
+  it.ts.n0 = (it.ts.seg0_end + KT - 1) / KT;
+  it.ts.n_kt = it.ts.n0 + (it.ts.seg1_end - it.ts.seg1_begin + KT - 1) / KT;
+  return it;
+}
+
+__global__ void __launch_bounds__(N_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const uint8_t* __restrict__ keypad,
-               bf16* __restrict__ ctx, int T2, int M, int main_ctx, int rc, int D, int n_main_tiles, int n_tiles,
-               float scale_log2) {
+               bf16* __restrict__ ctx, Shape sh, int n_items, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = smem_base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = warp < 2 * N_SOFTMAX_WARPS ? warp / N_SOFTMAX_WARPS : (warp - 2 * N_SOFTMAX_WARPS) & 1;
+  const bool is_softmax = warp < 2 * N_SOFTMAX_WARPS, is_mma = warp == 2 * N_SOFTMAX_WARPS || warp == 2 * N_SOFTMAX_WARPS + 1;
+  const uint32_t sQ = smem_base + grp * GROUP_SMEM;
   const uint32_t sK = sQ + TILE_BYTES;
   const uint32_t sV = sK + NS * TILE_BYTES;
-  const uint32_t sInfo = sV + NS * TILE_BYTES;              // int [2][KT]
-  const uint32_t sXch = sInfo + 2 * KT * 4;                 // float [2 tile parities][2 halves][QT]
-  const uint32_t bars = sXch + 2 * 2 * QT * 4;
-  const uint32_t bar_q = bars, bar_kfull = bars + 8, bar_kempty = bar_kfull + 8 * NS, bar_vfull = bar_kempty + 8 * NS,
-                 bar_vempty = bar_vfull + 8 * NS, bar_sfull = bar_vempty + 8 * NS, bar_sfree = bar_sfull + 8,
-                 bar_pfull = bar_sfree + 8, bar_pvdone = bar_pfull + 8;
-  const uint32_t tmem_slot = bar_pvdone + 8;
+  const uint32_t bars0 = smem_base + N_GROUPS * GROUP_SMEM;
+  const uint32_t bars = bars0 + grp * 96;
+  const uint32_t bar_qfull = bars, bar_kfull = bars + 8, bar_vfull = bar_kfull + 8 * NS, bar_sfull = bar_vfull + 8 * NS,
+                 bar_sfree = bar_sfull + 8, bar_pfull = bar_sfree + 8, bar_pvdone = bar_pfull + 8;
+  const uint32_t tmem_slot = bars0 + 2 * 96;
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
-  int* s_info = reinterpret_cast<int*>(gen_base + (sInfo - smem_base));
-  float* s_xch = reinterpret_cast<float*>(gen_base + (sXch - smem_base));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int tile_id = n_tiles - 1 - (int)blockIdx.x;        // heaviest query tiles first
+  const int D = sh.D;
+  const int vcta = 2 * blockIdx.x + grp;
 #ifdef W2VS_ATTN_TRACE
-  const bool trace_on = blockIdx.x == 0 && blockIdx.y == 3 && blockIdx.z == 1 && lane == 0 && (warp == 0 || warp == MMA_WARP);
+  const bool trace_on = blockIdx.x == 0 && lane == 0 && (warp == 1 || warp == 2 * N_SOFTMAX_WARPS);
 #endif
-  const int nb = T2 / main_ctx;
-  const int rcd = rc > 0 ? rc : 1;
 
-  int q_first, q_count;
-  if (tile_id < n_main_tiles) { q_first = tile_id * QT; q_count = min(QT, T2 - q_first); }
-  else { q_first = T2 + (tile_id - n_main_tiles) * QT; q_count = min(QT, M - q_first); }
-  auto qblock = [&](int m) { return m < T2 ? m / main_ctx : (m - T2) / rcd; };
-  const int qb_lo = qblock(q_first), qb_hi = qblock(q_first + q_count - 1);
-  TileSeq ts;
-  ts.seg0_end = min(main_ctx * (qb_hi + 1), T2);
-  ts.seg1_begin = ts.seg1_end = 0;
-  if (rc > 0 && qb_lo <= nb - 1) { ts.seg1_begin = T2 + rc * qb_lo; ts.seg1_end = T2 + rc * (min(qb_hi, nb - 1) + 1); }
-  ts.n0 = (ts.seg0_end + KT - 1) / KT;
-  ts.n_kt = ts.n0 + (ts.seg1_end - ts.seg1_begin + KT - 1) / KT;
-  const int n_kt = ts.n_kt;
-  const int row_base = b * M;                                // first token row of this utterance in qkv
-
-  if (threadIdx.x == 0) {
-    mbar_init(bar_q, 1);
-    for (int s = 0; s < NS; ++s) {
-      mbar_init(bar_kfull + 8 * s, 1); mbar_init(bar_kempty + 8 * s, 1);
-      mbar_init(bar_vfull + 8 * s, 1); mbar_init(bar_vempty + 8 * s, 1);
-    }
+  if (lane == 0 && is_mma) {            // each MMA warp initialises its group's barriers
+    mbar_init(bar_qfull, 1);
+    for (int s = 0; s < NS; ++s) { mbar_init(bar_kfull + 8 * s, 1); mbar_init(bar_vfull + 8 * s, 1); }
     mbar_init(bar_sfull, 1); mbar_init(bar_sfree, N_SOFTMAX_WARPS); mbar_init(bar_pfull, N_SOFTMAX_WARPS); mbar_init(bar_pvdone, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
-  if (warp == MMA_WARP) {
+  if (warp == 2 * N_SOFTMAX_WARPS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_all = *tmem_slot_ptr;
+  const uint32_t tmem_base = tmem_all + grp * GROUP_COLS;
 
-  if (warp == LOADER_WARP) {
-    // ===================== TMA loader =====================
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmQKV) : "memory");
-      mbar_expect_tx(bar_q, TILE_BYTES);
-      tma_load_2d(sQ, &tmQKV, bar_q, h * HD, row_base + q_first);
-      bool ok = true;
-      for (int it = 0; it < n_kt && ok; ++it) {
-        const int s = it % NS;
-        const uint32_t par = ((it / NS) & 1) ^ 1;
-        int k0, cnt; bool s1;
-        ts.get(it, k0, cnt, s1);
-        if (!(ok = mbar_wait(bar_kempty + 8 * s, par))) break;
-        mbar_expect_tx(bar_kfull + 8 * s, TILE_BYTES);
-        tma_load_2d(sK + s * TILE_BYTES, &tmQKV, bar_kfull + 8 * s, D + h * HD, row_base + k0);
-        if (!(ok = mbar_wait(bar_vempty + 8 * s, par))) break;
-        mbar_expect_tx(bar_vfull + 8 * s, TILE_BYTES);
-        tma_load_2d(sV + s * TILE_BYTES, &tmQKV, bar_vfull + 8 * s, 2 * D + h * HD, row_base + k0);
-      }
-    }
-  } else if (warp == MMA_WARP) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+  if (!is_softmax) {
+    // warpgroup 2 (warps 8-11) gives registers back: the softmax warpgroups hold 128 scores per thread
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_OTHER));
+    // ===================== MMA issuer + TMA loader (one thread) =====================
+    // The thread that issues the MMAs also knows when each ring slot becomes free (it commits the MMAs that
+    // read them), so it issues the TMA loads in its idle time: after S(g+1) is issued it waits for that MMA
+    // (about 260 cycles, it would be waiting for P(g) anyway) and loads K(g+1+NS); after PV(g) it loads
+    // V(g+NS).  The softmax warps stay perfectly balanced (no warp doubles as loader).
+    if (is_mma && lane == 0) {
       // D=f32, A=B=bf16; QK: both K-major, N=128; PV: B MN-major (bit 16), N=64; M=128
       constexpr uint32_t idesc_qk = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KT >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
       constexpr uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) |
                                     ((uint32_t)(QT >> 4) << 24);
-      bool ok = mbar_wait(bar_q, 0);
-      auto issue_s = [&](int it) {
-        const int s = it % NS;
-        if (!mbar_wait(bar_kfull + 8 * s, (it / NS) & 1)) return false;
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmQKV) : "memory");
+      const uint64_t dQ = umma_desc_sw128(sQ), dK = umma_desc_sw128(sK), dV = umma_desc_mn_sw128(sV);
+      bool ok = true;
+      // ---- load cursor: (work item, tile in item, global tile index) of the next K tile and of the next V tile
+      struct Cur { Walker wk; int it, g, n_kt, n0, seg1, hcol, row; };
+      auto cur_item = [&](Cur& c) {
+        if (c.wk.w < n_items) {
+          const Item ci = item_of(sh, c.wk);
+          c.n_kt = ci.ts.n_kt; c.n0 = ci.ts.n0; c.seg1 = ci.ts.seg1_begin; c.hcol = ci.h * HD; c.row = ci.row_base;
+        }
+      };
+      auto load_kv = [&](Cur& c, uint32_t bar0, uint32_t smem0, int col0) {   // tile c.g -> ring slot c.g % NS
+        if (c.wk.w >= n_items) return;
+        const int k0 = c.it < c.n0 ? c.it * KT : c.seg1 + (c.it - c.n0) * KT;
+        const int sl = c.g % NS;
+        mbar_expect_tx(bar0 + 8 * sl, TILE_BYTES);
+        tma_load_2d(smem0 + sl * TILE_BYTES, &tmQKV, bar0 + 8 * sl, col0 + c.hcol, c.row + k0);
+        ++c.g;
+        if (++c.it == c.n_kt) { c.it = 0; c.wk.next(sh); cur_item(c); }
+      };
+      auto load_q = [&](const Walker& wq) {
+        if (wq.w >= n_items) return;
+        const Item q = item_of(sh, wq);
+        mbar_expect_tx(bar_qfull, TILE_BYTES);
+        tma_load_2d(sQ, &tmQKV, bar_qfull, q.h * HD, q.row_base + q.q_first);
+      };
+      Cur ck, cv;
+      ck.wk.init(sh, vcta); ck.it = 0; ck.g = 0; cur_item(ck);
+      cv = ck;
+      Walker wk, wnext;                  // this item / the next one (whose Q is loaded ahead)
+      wk.init(sh, vcta);
+      wnext = wk;
+      load_q(wnext);
+      wnext.next(sh);
+      for (int i = 0; i < NS; ++i) { load_kv(ck, bar_kfull, sK, D); load_kv(cv, bar_vfull, sV, 2 * D); }
+
+      auto issue_s = [&](int g) {     // S(g) = Q K(g)^T
+        const int sl = g % NS;
+        if (!mbar_wait(bar_kfull + 8 * sl, (g / NS) & 1)) return false;
         tc_fence_after();
+        const uint64_t dk = dK + (uint64_t)((sl * TILE_BYTES) >> 4);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          umma_ss(tmem_base + S_COL, umma_desc_sw128(sQ + k * 32), umma_desc_sw128(sK + s * TILE_BYTES + k * 32),
-                  idesc_qk, k > 0 ? 1u : 0u);
+          umma_ss(tmem_base + S_COL, dQ + 2 * k, dk + 2 * k, idesc_qk, k > 0 ? 1u : 0u);
         tc_commit_1sm(bar_sfull);
-        tc_commit_1sm(bar_kempty + 8 * s);
         return true;
       };
-      if (ok && n_kt > 0) ok = issue_s(0);
-      for (int it = 0; it < n_kt && ok; ++it) {
-        TRACE(1, it, 0);
-        if (it + 1 < n_kt) {
-          if (!(ok = mbar_wait(bar_sfree, it & 1))) break;      // softmax has read S(it)
-          tc_fence_after();
-          TRACE(1, it, 1);
-          if (!(ok = issue_s(it + 1))) break;
-          TRACE(1, it, 2);
-        }
-        const int s = it % NS;
-        if (!(ok = mbar_wait(bar_vfull + 8 * s, (it / NS) & 1))) break;
-        TRACE(1, it, 3);
-        if (!(ok = mbar_wait(bar_pfull, it & 1))) break;         // P(it) is in TMEM, O has been rescaled
+      int gt = 0, wi = 0;
+      for (; wk.w < n_items && ok; wk.next(sh), wnext.next(sh), ++wi) {
+        const Item im = item_of(sh, wk);
+        const int n = im.ts.n_kt;
+        if (!(ok = mbar_wait(bar_qfull, wi & 1))) break;
+        if (gt > 0 && !(ok = mbar_wait(bar_sfree, (gt - 1) & 1))) break;   // softmax has read the previous item's last S
         tc_fence_after();
-        TRACE(1, it, 4);
+        if (!(ok = issue_s(gt))) break;
+        if (n == 1) {     // the item's only S: once it has retired, K's slot and Q are free
+          if (!(ok = mbar_wait(bar_sfull, gt & 1))) break;
+          load_kv(ck, bar_kfull, sK, D);
+          load_q(wnext);
+        }
+        for (int it = 0; it < n && ok; ++it) {
+          const int g = gt + it;
+          TRACE(1, g, 0);
+          if (it == 0 && n > 1) {   // S(g) of the item's first tile was issued above: free its K slot when it retires
+            if (!(ok = mbar_wait(bar_sfull, g & 1))) break;
+            load_kv(ck, bar_kfull, sK, D);
+          }
+          if (it + 1 < n) {
+            if (!(ok = mbar_wait(bar_sfree, g & 1))) break;          // softmax holds S(g) in registers
+            tc_fence_after();
+            TRACE(1, g, 1);
+            if (!(ok = issue_s(g + 1))) break;
+            TRACE(1, g, 2);
+            if (!(ok = mbar_wait(bar_sfull, (g + 1) & 1))) break;    // S(g+1) retired (idle time: P(g) is not ready yet)
+            load_kv(ck, bar_kfull, sK, D);                             // K(g+1+NS)
+            if (it + 2 == n) load_q(wnext);                            // it was the item's last S: Q is free
+            TRACE(1, g, 6);
+          }
+          const int sl = g % NS;
+          if (!(ok = mbar_wait(bar_vfull + 8 * sl, (g / NS) & 1))) break;
+          TRACE(1, g, 3);
+          if (!(ok = mbar_wait(bar_pfull, g & 1))) break;            // P(g) is in TMEM, O has been rescaled
+          tc_fence_after();
+          TRACE(1, g, 4);
+          const uint64_t dv = dV + (uint64_t)((sl * TILE_BYTES) >> 4);
 #pragma unroll
-        for (int k = 0; k < KT / 16; ++k)
-          umma_ts(tmem_base + O_COL, tmem_base + P_COL + k * 8, umma_desc_mn_sw128(sV + s * TILE_BYTES + k * 2048),
-                  idesc_pv, (it > 0 || k > 0) ? 1u : 0u);
-        tc_commit_1sm(bar_pvdone);
-        tc_commit_1sm(bar_vempty + 8 * s);
-        TRACE(1, it, 5);
+          for (int k = 0; k < KT / 16; ++k)
+            umma_ts(tmem_base + O_COL, tmem_base + P_COL + k * 8, dv + (2048 >> 4) * k, idesc_pv, (it > 0 || k > 0) ? 1u : 0u);
+          tc_commit_1sm(bar_pvdone);
+          TRACE(1, g, 5);
+          if (!(ok = mbar_wait(bar_pvdone, g & 1))) break;           // PV(g) retired: V's slot is free
+          load_kv(cv, bar_vfull, sV, 2 * D);                           // V(g+NS)
+          TRACE(1, g, 7);
+        }
+        gt += n;
       }
     }
   } else {
-    // ===================== softmax warps: two threads per query row =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_SOFTMAX));
+    // ===================== softmax warps: one query row per thread =====================
     // Visibility of the 128 key columns of a tile for one query row is a contiguous column range [lo, hi):
     //   main keys: columns whose block <= qblock(row)  ->  [0, (qb+1)*main - k0)
     //   look-ahead keys: the rc copies owned by qblock(row)  ->  [T2 + qb*rc - k0, +rc)
-    // so 32-column chunks are classified per warp as all-visible (no masking), none-visible (no loads, no
-    // exponentials: P = 0) or partial (one range compare per element).  Tiles that contain padded keys take
-    // the general per-key path (s_info), which also covers arbitrary (non-prefix) padding masks.
-    const int quarter = warp & 3, half = warp >> 2;
+    // so 32-column chunks are classified per warp as all-visible (no masking), none-visible (not loaded, no
+    // exponentials: P = 0) or partial (one range compare per element).  Key padding (any mask, not only a
+    // ragged tail) is detected per warp from the tile's 128 padding bytes and handled per element.
+    const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;                 // row inside the query tile == TMEM lane
-    const int st = warp * 32 + lane;                     // 0..255: threads 0..127 describe the key columns
     const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    // rows past the end of the tile behave like the last valid row (their output is never stored); this keeps
-    // the chunk classification uniform across the warp
-    const int my_qb = row < q_count ? qblock(q_first + row) : qb_hi;
-    const uint8_t* kp = keypad + (size_t)b * M;
-    float m_ref = -INFINITY;
-    uint64_t l2 = pack2(0.f, 0.f);                       // partial row sums (two accumulators)
+    const int T2 = sh.T2, main_ctx = sh.main_ctx, rc = sh.rc, rcd = sh.rcd, nb = sh.nb;
     bool ok = true;
+    int gt = 0;
+    // padding bytes of the key columns 4*lane .. 4*lane+3 of the NEXT tile in this CTA's sequence (it may belong to
+    // the next work item): fetched with volatile loads one tile ahead, looked at only when that tile starts, so
+    // the global-load latency never sits on the critical path
+    uint32_t kb0 = 0, kb1 = 0, kb2 = 0, kb3 = 0;
+    auto ldu8 = [](const uint8_t* p_) {
+      uint32_t v;
+      asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p_));
+      return v;
+    };
+    auto prefetch_kp = [&](const Item& pi, int it_) {
+      int k0_, cnt_; bool s1_;
+      pi.ts.get(it_, k0_, cnt_, s1_);
+      // unconditional loads (columns past the tile's end are clamped to its last byte and discarded when the
+      // bytes are looked at): nothing may consume a loaded value here, or the load latency is exposed
+      const uint8_t* p_ = keypad + pi.row_base + k0_;
+      const int last = cnt_ - 1;
+      kb0 = ldu8(p_ + min(4 * lane + 0, last));
+      kb1 = ldu8(p_ + min(4 * lane + 1, last));
+      kb2 = ldu8(p_ + min(4 * lane + 2, last));
+      kb3 = ldu8(p_ + min(4 * lane + 3, last));
+    };
+    Walker wk, wnext;
+    wk.init(sh, vcta);
+    wnext = wk;
+    wnext.next(sh);
+    Item im;
+    if (wk.w < n_items) { im = item_of(sh, wk); prefetch_kp(im, 0); }
+    for (; wk.w < n_items && ok; wk.next(sh), wnext.next(sh)) {
+      const int n_kt = im.ts.n_kt;
+      const bool have_next = wnext.w < n_items;
+      // rows past the end of the tile behave like the last valid row (their output is never stored); this keeps
+      // the chunk classification uniform across the warp
+      const int my_qb = row < im.q_count ? qblock_of(sh, im.q_first + row) : im.qb_hi;
+      float m_ref = -INFINITY;
+      uint64_t l2 = pack2(0.f, 0.f);                     // row sum (two accumulators)
+      int k0, cnt; bool s1;
 
-    int k0, cnt; bool s1;
-    uint8_t kp_next = 0;
-    if (n_kt > 0 && st < KT) { ts.get(0, k0, cnt, s1); kp_next = st < cnt ? kp[k0 + st] : 0; }
-
-    for (int it = 0; it < n_kt && ok; ++it) {
-      ts.get(it, k0, cnt, s1);
-      // ---- per-key description for the general path; the barrier publishes it and ORs "tile has padding"
-      const bool padded = st < cnt && kp_next != 0;
-      int* info_t = s_info + (it & 1) * KT;
-      if (st < KT) {
-        int info;
-        if (st < cnt && !padded) info = s1 ? (k0 + st - T2) / rcd : (k0 + st) / main_ctx;
-        else info = s1 ? -2 : INT_MAX;
-        info_t[st] = info;
-      }
-      TRACE(0, it, 0);
-      const bool has_pad = softmax_bar_or(padded);
-      TRACE(0, it, 1);
-      if (it + 1 < n_kt && st < KT) {   // prefetch the padding byte of the next tile's column
-        int k0n, cntn; bool s1n;
-        ts.get(it + 1, k0n, cntn, s1n);
-        kp_next = st < cntn ? kp[k0n + st] : 0;
-      }
-      // ---- visible column range of this row
-      int lo = 0, hi = 0;
-      if (!s1) { hi = min(max((my_qb + 1) * main_ctx - k0, 0), cnt); }
-      else if (my_qb <= nb - 1) { lo = min(max(T2 + my_qb * rc - k0, 0), cnt); hi = min(max(T2 + (my_qb + 1) * rc - k0, 0), cnt); }
-      const uint32_t span = (uint32_t)(hi - lo);
-      // classes of this thread's two 32-column chunks, warp-uniform
-      bool all_vis[2], none_vis[2];
+      for (int it = 0; it < n_kt && ok; ++it) {
+        const int g = gt + it;
+        im.ts.get(it, k0, cnt, s1);
+        TRACE(0, g, 0);
+        const int kr = cnt - 4 * lane;     // columns 4*lane+k of this tile exist for k < kr
+        const uint32_t kp_cur = (uint32_t)(kr > 0 && kb0 != 0) | ((uint32_t)(kr > 1 && kb1 != 0) << 8) |
+                                ((uint32_t)(kr > 2 && kb2 != 0) << 16) | ((uint32_t)(kr > 3 && kb3 != 0) << 24);
+        const bool has_pad = __any_sync(0xffffffffu, kp_cur != 0);
+        TRACE(0, g, 8);
+#ifndef W2VS_EXP_NO_KP
+        if (it + 1 < n_kt) prefetch_kp(im, it + 1);
+        else if (have_next) { const Item nx = item_of(sh, wnext); prefetch_kp(nx, 0); }
+#endif
+        TRACE(0, g, 10);
+        // ---- visible column range of this row
+        int lo = 0, hi = 0;
+        if (!s1) { hi = min(max((my_qb + 1) * main_ctx - k0, 0), cnt); }
+        else if (my_qb <= nb - 1) { lo = min(max(T2 + my_qb * rc - k0, 0), cnt); hi = min(max(T2 + (my_qb + 1) * rc - k0, 0), cnt); }
+        const uint32_t span = (uint32_t)(hi - lo);
+        // classes of the four 32-column chunks, warp-uniform
+        bool all_vis[4], none_vis[4];
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c0 = (2 * half + cc) * 32;
-        const bool a = !has_pad && lo <= c0 && c0 + 32 <= hi;
-        const bool n = (!has_pad && (hi <= c0 || lo >= c0 + 32 || span == 0)) || c0 >= cnt;
-        all_vis[cc] = __all_sync(0xffffffffu, a);
-        none_vis[cc] = __all_sync(0xffffffffu, n);
-      }
-      ok = mbar_wait(bar_sfull, it & 1);
-      tc_fence_after();
-      TRACE(0, it, 2);
-
-      // ---- sweep 1: maximum of the visible scores of this half row
-      float mxa = -INFINITY, mxb = -INFINITY;
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        if (none_vis[cc]) continue;
-        const int c0 = (2 * half + cc) * 32;
-        uint32_t r[32];
-        tmem_ld32(tlane + S_COL + c0, r);
-        tmem_ld_wait();
-        if (all_vis[cc]) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            mxa = fmaxf(mxa, fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
-            mxb = fmaxf(mxb, fmaxf(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
-          }
-        } else if (!has_pad) {
-          const int off = c0 - lo;
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            mxa = fmaxf(mxa, (uint32_t)(off + j) < span ? __uint_as_float(r[j]) : -INFINITY);
-            mxb = fmaxf(mxb, (uint32_t)(off + j + 1) < span ? __uint_as_float(r[j + 1]) : -INFINITY);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int ki = info_t[c0 + j];
-            const bool vis = s1 ? (ki == my_qb) : (ki <= my_qb);
-            mxa = fmaxf(mxa, vis ? __uint_as_float(r[j]) : -INFINITY);
-          }
+        for (int c = 0; c < 4; ++c) {
+          const int c0 = c * 32;
+          const bool a = !has_pad && lo <= c0 && c0 + 32 <= hi;
+          const bool nv = hi <= c0 || lo >= c0 + 32 || span == 0;
+          all_vis[c] = __all_sync(0xffffffffu, a);
+          none_vis[c] = __all_sync(0xffffffffu, nv);
         }
-      }
-      // ---- combine the two half-row maxima through shared memory
-      float* xch = s_xch + (it & 1) * 2 * QT;
-      xch[half * QT + row] = fmaxf(mxa, mxb);
-      pair_bar(quarter);
-      const float mx = fmaxf(fmaxf(mxa, mxb), xch[(half ^ 1) * QT + row]);
-      TRACE(0, it, 3);
-      // ---- running maximum with lazy rescale (exact: the final normalisation uses the same reference)
-      const float m_tile = mx * scale_log2;               // -inf stays -inf
-      const bool grow = m_tile > m_ref + RESCALE_THRESHOLD;
-      float alpha = 1.0f;
-      if (grow) {
-        alpha = ex2_approx(m_ref - m_tile);
-        m_ref = m_tile;
-        l2 = ffma2(l2, pack2(alpha, alpha), pack2(0.f, 0.f));
-      }
-      if (it > 0) {
-        ok = mbar_wait(bar_pvdone, (it - 1) & 1) && ok;   // PV(it-1) retired: P is free, O is stable
+        TRACE(0, g, 9);
+        ok = mbar_wait(bar_sfull, g & 1);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, grow)) {               // this thread rescales its 32 columns of O
-          uint32_t r[32];
-          tmem_ld32(tlane + O_COL + half * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * alpha);
-          tmem_st32(tlane + O_COL + half * 32, r);
-        }
-      }
-      TRACE(0, it, 4);
-      const float m_use = m_ref == -INFINITY ? 0.f : m_ref;
-      const uint64_t sc2 = pack2(scale_log2, scale_log2), nm2 = pack2(-m_use, -m_use);
+        TRACE(0, g, 2);
 
-      // ---- sweep 2: P = exp2(s * scale - m), row sum, bf16 P -> TMEM
-      const int last_read = none_vis[1] ? (none_vis[0] ? -1 : 0) : 1;
-      if (last_read < 0) {
+        // ---- this row's scores -> registers (one TMEM read per score); S goes back to the MMA thread at once
+        uint32_t r[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (!none_vis[c]) tmem_ld32(tlane + S_COL + c * 32, r[c]);
+        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_local(bar_sfree);
-      }
+        TRACE(0, g, 1);
+
+        // ---- mask (partial chunks) and row maximum
+        uint32_t pb[4] = {0u, 0u, 0u, 0u};          // pb[k] bit L = padding of column 4L + k
+        if (has_pad) {
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = 2 * half + cc, c0 = c * 32;
-        uint32_t pk[16];
-        if (none_vis[cc]) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = 0u;
-          tmem_st16(tlane + P_COL + c * 16, pk);
-          continue;
+          for (int k = 0; k < 4; ++k) pb[k] = __ballot_sync(0xffffffffu, (kp_cur >> (8 * k)) & 0xffu);
         }
-        uint32_t r[32];
-        tmem_ld32(tlane + S_COL + c0, r);
-        tmem_ld_wait();
-        if (cc == last_read) {        // every score of this tile has been read by this warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_local(bar_sfree);
+        float mxa = -INFINITY, mxb = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (none_vis[c]) continue;
+          if (!all_vis[c]) {
+            const int off = c * 32 - lo;
+            if (!has_pad) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[c][j] = (uint32_t)(off + j) < span ? r[c][j] : 0xff800000u;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const bool padj = (pb[j & 3] >> (c * 8 + (j >> 2))) & 1u;
+                r[c][j] = ((uint32_t)(off + j) < span && !padj) ? r[c][j] : 0xff800000u;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            mxa = fmaxf(mxa, fmaxf(__uint_as_float(r[c][j]), __uint_as_float(r[c][j + 1])));
+            mxb = fmaxf(mxb, fmaxf(__uint_as_float(r[c][j + 2]), __uint_as_float(r[c][j + 3])));
+          }
         }
-        if (!all_vis[cc]) {           // partial chunk: replace invisible scores by -inf
-          if (!has_pad) {
-            const int off = c0 - lo;
+        const float mx = fmaxf(mxa, mxb);
+        TRACE(0, g, 3);
+        // ---- running maximum with lazy rescale (exact: the final normalisation uses the same reference)
+        const float m_tile = mx * scale_log2;               // -inf stays -inf
+        const bool grow = m_tile > m_ref + RESCALE_THRESHOLD;
+        float alpha = 1.0f;
+        if (grow) {
+          alpha = ex2_approx(m_ref - m_tile);
+          m_ref = m_tile;
+          l2 = ffma2(l2, pack2(alpha, alpha), pack2(0.f, 0.f));
+        }
+        if (it > 0) {
+          ok = mbar_wait(bar_pvdone, (g - 1) & 1) && ok;    // PV(g-1) retired: P is free, O is stable
+          tc_fence_after();
+          TRACE(0, g, 7);
+          if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              r[j] = (uint32_t)(off + j) < span ? r[j] : 0xff800000u;
-          } else {
+            for (int c = 0; c < HD / 32; ++c) {
+              uint32_t o[32];
+              tmem_ld32(tlane + O_COL + c * 32, o);
+              tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int ki = info_t[c0 + j];
-              const bool vis = s1 ? (ki == my_qb) : (ki <= my_qb);
-              r[j] = vis ? r[j] : 0xff800000u;
+              for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+              tmem_st32(tlane + O_COL + c * 32, o);
             }
           }
         }
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float a0, a1;
-          unpack2(ffma2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), sc2, nm2), a0, a1);
-          const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
-          l2 = fadd2(l2, pack2(p0, p1));
-          pk[j >> 1] = pack_bf16x2(p0, p1);
-        }
-        tmem_st16(tlane + P_COL + c * 16, pk);
-      }
-      TRACE(0, it, 5);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_local(bar_pfull);
-      TRACE(0, it, 6);
-    }
+        TRACE(0, g, 4);
+        const float m_use = m_ref == -INFINITY ? 0.f : m_ref;
+        const uint64_t sc2 = pack2(scale_log2, scale_log2), nm2 = pack2(-m_use, -m_use);
 
-    // ---- epilogue: O / l -> bf16 -> ctx (each thread: 32 of the 64 output columns of its row)
-    float la, lb;
-    unpack2(l2, la, lb);
-    float* xch = s_xch + (n_kt & 1) * 2 * QT;
-    xch[half * QT + row] = la + lb;
-    pair_bar(quarter);
-    const float l = (la + lb) + xch[(half ^ 1) * QT + row];
-    if (n_kt > 0) ok = mbar_wait(bar_pvdone, (n_kt - 1) & 1) && ok;
-    tc_fence_after();
-    const float inv = l > 0.f ? 1.0f / l : 0.f;
-    bf16* dst = ctx + ((size_t)row_base + q_first + row) * D + (size_t)h * HD + half * 32;
-    {
-      uint32_t r[32];
-      tmem_ld32(tlane + O_COL + half * 32, r);
-      tmem_ld_wait();
-      if (row < q_count && n_kt > 0) {
+        // ---- P = exp2(s * scale - m), row sum, bf16 P -> TMEM
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(r[8 * g + 0]) * inv, __uint_as_float(r[8 * g + 1]) * inv);
-          o.y = pack_bf16x2(__uint_as_float(r[8 * g + 2]) * inv, __uint_as_float(r[8 * g + 3]) * inv);
-          o.z = pack_bf16x2(__uint_as_float(r[8 * g + 4]) * inv, __uint_as_float(r[8 * g + 5]) * inv);
-          o.w = pack_bf16x2(__uint_as_float(r[8 * g + 6]) * inv, __uint_as_float(r[8 * g + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + g * 8) = o;
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+          if (none_vis[c]) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = 0u;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float a0, a1;
+              unpack2(ffma2(pack2(__uint_as_float(r[c][j]), __uint_as_float(r[c][j + 1])), sc2, nm2), a0, a1);
+              const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+              l2 = fadd2(l2, pack2(p0, p1));
+              pk[j >> 1] = pack_bf16x2(p0, p1);
+            }
+          }
+          tmem_st16(tlane + P_COL + c * 16, pk);
+        }
+        TRACE(0, g, 5);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_local(bar_pfull);
+        TRACE(0, g, 6);
+      }
+      gt += n_kt;
+
+      // ---- epilogue: O / l -> bf16 -> ctx
+      float la, lb;
+      unpack2(l2, la, lb);
+      const float l = la + lb;
+      ok = mbar_wait(bar_pvdone, (gt - 1) & 1) && ok;
+      tc_fence_after();
+      const float inv = l > 0.f ? 1.0f / l : 0.f;
+      bf16* dst = ctx + ((size_t)im.row_base + im.q_first + row) * D + (size_t)im.h * HD;
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tlane + O_COL + c * 32, o);
+        tmem_ld_wait();
+        if (row < im.q_count) {
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(o[8 * gq + 0]) * inv, __uint_as_float(o[8 * gq + 1]) * inv);
+            v.y = pack_bf16x2(__uint_as_float(o[8 * gq + 2]) * inv, __uint_as_float(o[8 * gq + 3]) * inv);
+            v.z = pack_bf16x2(__uint_as_float(o[8 * gq + 4]) * inv, __uint_as_float(o[8 * gq + 5]) * inv);
+            v.w = pack_bf16x2(__uint_as_float(o[8 * gq + 6]) * inv, __uint_as_float(o[8 * gq + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + c * 32 + gq * 8) = v;
+          }
         }
       }
+      tc_fence_before();   // orders these TMEM reads before this warp's next p_full arrive (next item overwrites O)
+      if (have_next) im = item_of(sh, wnext);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == MMA_WARP) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  if (warp == 2 * N_SOFTMAX_WARPS) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_all), "r"(TMEM_COLS) : "memory");
   }
 }
 }  // namespace
@@ -493,10 +568,14 @@ w2vs_status_t launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
   W2VS_REQUIRE(a.D == a.heads * HD, "attention head_dim must be 64");
   W2VS_REQUIRE(a.n_step_q == 0, "tcgen05 attention implements the full-utterance (block mask) mode");
   W2VS_REQUIRE(((uintptr_t)a.qkv & 15) == 0 && ((uintptr_t)a.ctx & 15) == 0, "attention buffers must be 16-byte aligned");
-  const int M = a.T2 + (a.rc > 0 ? (a.T2 / a.main_ctx) * a.rc : 0);
-  const int n_main = (a.T2 + QT - 1) / QT, n_rc = (M - a.T2 + QT - 1) / QT;
+  Shape sh;
+  sh.T2 = a.T2; sh.main_ctx = a.main_ctx; sh.rc = a.rc; sh.rcd = a.rc > 0 ? a.rc : 1; sh.nb = a.T2 / a.main_ctx;
+  sh.M = a.T2 + (a.rc > 0 ? sh.nb * a.rc : 0);
+  sh.D = a.D; sh.H = a.heads; sh.B = a.B;
+  sh.n_main_tiles = (a.T2 + QT - 1) / QT;
+  sh.n_tiles = sh.n_main_tiles + (sh.M - a.T2 + QT - 1) / QT;
   alignas(64) CUtensorMap tm;
-  W2VS_TRY(tc::make_map(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.qkv, (uint64_t)3 * a.D, (uint64_t)a.B * M,
+  W2VS_TRY(tc::make_map(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.qkv, (uint64_t)3 * a.D, (uint64_t)a.B * sh.M,
                         (uint64_t)3 * a.D, HD, 128, CU_TENSOR_MAP_SWIZZLE_128B));
   static bool attr_done = false;
   if (!attr_done) {
@@ -504,10 +583,23 @@ w2vs_status_t launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
     if (e != cudaSuccess) { set_error("attn_tc smem attribute: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
     attr_done = true;
   }
-  dim3 grid((unsigned)(n_main + n_rc), (unsigned)a.heads, (unsigned)a.B);
+  const int64_t n_items = (int64_t)sh.n_tiles * a.heads * a.B;
+  W2VS_REQUIRE(n_items < (1ll << 31), "attention problem too large");
+  const int max_ctas = tc::num_sms();         // persistent: one CTA (two pipelines) per SM
+  const int grid = (int)((n_items + 1) / 2 < max_ctas ? (n_items + 1) / 2 : max_ctas);
+  sh.HB = a.heads * a.B;
+  sh.n_vcta = 2 * grid;
+  sh.g_div = sh.n_vcta / sh.HB;
+  sh.g_mod = sh.n_vcta % sh.HB;
+  // magic multipliers: floor(x / d) == umulhi(x, ceil(2^32 / d)) holds for x < 2^32 / d
+  auto magic = [](int d) { return (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d); };
+  W2VS_REQUIRE((int64_t)sh.M * a.main_ctx < (1ll << 32) && (int64_t)sh.M * sh.rcd < (1ll << 32) &&
+               (int64_t)sh.HB * a.heads < (1ll << 32), "attention shape out of range for the fast index arithmetic");
+  sh.magic_main = a.main_ctx >= 2 ? magic(a.main_ctx) : 0u;
+  sh.magic_rcd = sh.rcd >= 2 ? magic(sh.rcd) : 0u;   // d == 1 handled below
+  sh.magic_H = a.heads >= 2 ? magic(a.heads) : 0u;
   const float scale_log2 = (1.0f / sqrtf((float)HD)) * 1.4426950408889634f;
-  attn_tc_kernel<<<grid, N_THREADS, SMEM_BYTES, st>>>(tm, a.keypad, (bf16*)a.ctx, a.T2, M, a.main_ctx, a.rc, a.D, n_main,
-                                                n_main + n_rc, scale_log2);
+  attn_tc_kernel<<<grid, N_THREADS, SMEM_BYTES, st>>>(tm, a.keypad, (bf16*)a.ctx, sh, (int)n_items, scale_log2);
   W2VS_CHECK_LAUNCH("attn_tc_kernel");
   return W2VS_OK;
 }
