@@ -114,6 +114,54 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(copysignf(erf_abs, x), hx, hx);       // 0.5 x (1 + erf(x/sqrt2))
 }
 
+// ---- packed fp32 pairs (sm_100 f32x2 pipe): one instruction for two lanes of elementwise arithmetic -------
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// two erf-GELUs at once: same formula as gelu_erf, 20 instructions per pair instead of 28
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const uint64_t x = pack2(x0, x1);
+  const uint64_t z = pack2(fabsf(x0) * 0.70710678118654752f, fabsf(x1) * 0.70710678118654752f);
+  float d0, d1;
+  unpack2(ffma2(pack2(0.3275911f, 0.3275911f), z, pack2(1.0f, 1.0f)), d0, d1);
+  const uint64_t t = pack2(rcp_approx(d0), rcp_approx(d1));
+  uint64_t p = ffma2(pack2(1.061405429f, 1.061405429f), t, pack2(-1.453152027f, -1.453152027f));
+  p = ffma2(p, t, pack2(1.421413741f, 1.421413741f));
+  p = ffma2(p, t, pack2(-0.284496736f, -0.284496736f));
+  p = ffma2(p, t, pack2(0.254829592f, 0.254829592f));
+  p = fmul2(p, t);
+  float e0, e1;
+  unpack2(fmul2(fmul2(z, z), pack2(-1.4426950408889634f, -1.4426950408889634f)), e0, e1);
+  const uint64_t e = pack2(ex2_approx(e0), ex2_approx(e1));
+  float q0, q1;
+  unpack2(ffma2(p, e, pack2(-1.0f, -1.0f)), q0, q1);     // q = -erf(|x|/sqrt2)
+  // copysign(erf_abs, x): magnitude bits of q, sign bit of x
+  const float s0 = __uint_as_float((__float_as_uint(q0) & 0x7fffffffu) | (__float_as_uint(x0) & 0x80000000u));
+  const float s1 = __uint_as_float((__float_as_uint(q1) & 0x7fffffffu) | (__float_as_uint(x1) & 0x80000000u));
+  const uint64_t hx = fmul2(x, pack2(0.5f, 0.5f));
+  unpack2(ffma2(pack2(s0, s1), hx, hx), x0, x1);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

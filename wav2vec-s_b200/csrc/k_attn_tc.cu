@@ -105,26 +105,6 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// packed fp32 pairs (sm_100): one instruction for two lanes of the softmax arithmetic
-__device__ __forceinline__ uint64_t pack2(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
 struct TileSeq {   // key tiles visible to one query tile
   int seg0_end, seg1_begin, seg1_end, n0, n_kt;
   __device__ __forceinline__ void get(int it, int& k0, int& cnt, bool& s1) const {
@@ -406,20 +386,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const uint8_t* __restr
         else if (have_next) { const Item nx = item_of(sh, wnext); prefetch_kp(nx, 0); }
 #endif
         TRACE(0, g, 10);
-        // ---- visible column range of this row
+        // ---- visible column range of this row.  Rows of a warp are consecutive tokens, so lo and hi are
+        //      non-decreasing in the lane index: the warp-wide classification needs lanes 0 and 31 only.
         int lo = 0, hi = 0;
         if (!s1) { hi = min(max((my_qb + 1) * main_ctx - k0, 0), cnt); }
         else if (my_qb <= nb - 1) { lo = min(max(T2 + my_qb * rc - k0, 0), cnt); hi = min(max(T2 + (my_qb + 1) * rc - k0, 0), cnt); }
+        else { lo = hi = cnt; }             // past the last owner block: sees no look-ahead copy
         const uint32_t span = (uint32_t)(hi - lo);
-        // classes of the four 32-column chunks, warp-uniform
+        const int lo_min = __shfl_sync(0xffffffffu, lo, 0), lo_max = __shfl_sync(0xffffffffu, lo, 31);
+        const int hi_min = __shfl_sync(0xffffffffu, hi, 0), hi_max = __shfl_sync(0xffffffffu, hi, 31);
         bool all_vis[4], none_vis[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int c0 = c * 32;
-          const bool a = !has_pad && lo <= c0 && c0 + 32 <= hi;
-          const bool nv = hi <= c0 || lo >= c0 + 32 || span == 0;
-          all_vis[c] = __all_sync(0xffffffffu, a);
-          none_vis[c] = __all_sync(0xffffffffu, nv);
+          all_vis[c] = !has_pad && lo_max <= c0 && c0 + 32 <= hi_min;
+          none_vis[c] = hi_max <= c0 || lo_min >= c0 + 32;
         }
         TRACE(0, g, 9);
         ok = mbar_wait(bar_sfull, g & 1);
@@ -443,7 +424,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const uint8_t* __restr
 #pragma unroll
           for (int k = 0; k < 4; ++k) pb[k] = __ballot_sync(0xffffffffu, (kp_cur >> (8 * k)) & 0xffu);
         }
-        float mxa = -INFINITY, mxb = -INFINITY;
+        float mxa = -INFINITY, mxb = -INFINITY, mxc = -INFINITY, mxd = -INFINITY;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (none_vis[c]) continue;
@@ -461,12 +442,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const uint8_t* __restr
             }
           }
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
+          for (int j = 0; j < 32; j += 8) {   // four independent 3-input max chains
             mxa = fmaxf(mxa, fmaxf(__uint_as_float(r[c][j]), __uint_as_float(r[c][j + 1])));
             mxb = fmaxf(mxb, fmaxf(__uint_as_float(r[c][j + 2]), __uint_as_float(r[c][j + 3])));
+            mxc = fmaxf(mxc, fmaxf(__uint_as_float(r[c][j + 4]), __uint_as_float(r[c][j + 5])));
+            mxd = fmaxf(mxd, fmaxf(__uint_as_float(r[c][j + 6]), __uint_as_float(r[c][j + 7])));
           }
         }
-        const float mx = fmaxf(mxa, mxb);
+        mxa = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
+        const float mx = mxa;
         TRACE(0, g, 3);
         // ---- running maximum with lazy rescale (exact: the final normalisation uses the same reference)
         const float m_tile = mx * scale_log2;               // -inf stays -inf

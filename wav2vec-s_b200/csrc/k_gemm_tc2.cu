@@ -211,9 +211,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tmem_ld_wait();
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = __uint_as_float(r[j]) + bs[c * CHUNK + j];
-          if (gelu) v[j] = gelu_erf(v[j]);
+        for (int j = 0; j < 32; j += 2) {
+          const float2 bb = *reinterpret_cast<const float2*>(bs + c * CHUNK + j);   // smem broadcast
+          unpack2(fadd2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), pack2(bb.x, bb.y)), v[j], v[j + 1]);
+          if (gelu) gelu_erf2(v[j], v[j + 1]);
         }
         if (has_residual) {
           ok = mbar_wait(my_res_bar + 8 * sl, (res_phase >> sl) & 1u);
