@@ -19,7 +19,9 @@ int main() {
   unsigned s = 1;
   for (auto& v : h) { s = s * 1664525u + 1013904223u; v = (uint16_t)(0x3c00u + ((s >> 20) & 0x1ff)) ^ ((s >> 3) & 0x8000u); }
   cudaMemcpy(qkv, h.data(), h.size() * 2, cudaMemcpyHostToDevice);
+  uint8_t* pblk; cudaMalloc(&pblk, 4096); cudaMemset(pblk, 0, 4096);
   AttnArgs a{};
+  a.pad_blk = pblk;
   a.qkv = qkv; a.keypad = kp; a.ctx = ctx; a.dtype = W2VS_BF16; a.B = B; a.T2 = T2; a.main_ctx = main_ctx; a.rc = rc;
   a.heads = heads; a.D = D;
   { int nb = 0; cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -34,13 +36,13 @@ int main() {
   cudaDeviceSynchronize();
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   printf("attn_tc: %.1f us per launch (B=%d)  err=%s\n", ms * 100, B, cudaGetErrorString(cudaGetLastError()));
-  static long long tr[2][64][12];
+  static long long tr[2][64][16];
   cudaMemcpyFromSymbol(tr, g_attn_trace, sizeof(tr));
   long long t0 = tr[0][0][0];
-  printf("softmax warp0: tile | bar_in Sloaded sfull max+xch rescaled exp_done pfull pvdone_seen after_any before_sfull_wait (cycles since first event)\n");
+  printf("softmax warp0: tile | bar_in Sloaded sfull max+xch rescaled exp_done pfull pvdone_seen after_any before_sfull_wait ev10 epi_in pvdone stored item_of (cycles since first event)\n");
   for (int it = 0; it < 12; ++it) {
     printf("%2d |", it);
-    for (int e = 0; e < 11; ++e) printf(" %7lld", tr[0][it][e] ? tr[0][it][e] - t0 : -1);
+    for (int e = 0; e < 15; ++e) printf(" %7lld", tr[0][it][e] ? tr[0][it][e] - t0 : -1);
     printf("\n");
   }
   printf("MMA thread: tile | loop_top sfree_done S_issued vfull pfull_done PV_issued [S_done PV_done]\n");

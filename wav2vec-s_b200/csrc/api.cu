@@ -278,7 +278,7 @@ w2vs_status_t w2vs_encode(const w2vs_config* cfg, const void* d_packed, const w2
   {
     PrepArgs p{};
     p.lengths = a->d_lengths; p.sample_mask = a->d_sample_pad_mask; p.mask_len = has_mask ? a->mask_len : 0;
-    p.frame_pad = frame_pad; p.pos = pos; p.keypad = keypad;
+    p.frame_pad = frame_pad; p.pos = pos; p.keypad = keypad; p.pad_blk = at<uint8_t>(d_ws, ws.pad_blk);
     p.B = B; p.T = g.T; p.T2 = g.T2; p.M = g.M; p.main_ctx = g.main_ctx; p.rc = g.rc > 0 ? g.rc : 1;
     W2VS_TRY(launch_prep_masks(p, st));
   }
@@ -333,7 +333,7 @@ w2vs_status_t w2vs_encode(const w2vs_config* cfg, const void* d_packed, const w2
     W2VS_TRY(gemm(Xa, D, lw.wqkv, lw.bqkv, nullptr, qkv, 3 * D, adt, 0));
     {
       AttnArgs aa{};
-      aa.qkv = qkv; aa.keypad = keypad; aa.ctx = ctx; aa.dtype = adt;
+      aa.qkv = qkv; aa.keypad = keypad; aa.ctx = ctx; aa.dtype = adt; aa.pad_blk = at<uint8_t>(d_ws, ws.pad_blk);
       aa.B = B; aa.T2 = g.T2; aa.main_ctx = g.main_ctx; aa.rc = g.rc; aa.heads = cfg->heads; aa.D = D;
       W2VS_TRY(launch_attention(0, aa, st));
     }

@@ -34,7 +34,7 @@
 namespace w2vs {
 __device__ int g_attn_tc_fault = 0;
 #ifdef W2VS_ATTN_TRACE
-__device__ long long g_attn_trace[2][64][12];   // [role: 0 softmax warp 0, 1 MMA thread][tile][event] (clock64)
+__device__ long long g_attn_trace[2][64][16];   // [role: 0 softmax warp 0, 1 MMA thread][tile][event] (clock64)
 #define TRACE(role, it, ev) do { if (trace_on && (it) < 64) g_attn_trace[role][it][ev] = clock64(); } while (0)
 #else
 #define TRACE(role, it, ev) do { } while (0)
@@ -53,7 +53,8 @@ constexpr int NS = 2;                        // K ring and V ring depth
 constexpr int N_SOFTMAX_WARPS = 4;            // per group
 constexpr int N_GROUPS = 2, N_THREADS = 384;  // warps 0-7 softmax (two groups), 8-9 MMA, 10-11 idle
 constexpr int REGS_SOFTMAX = 232, REGS_OTHER = 40;
-constexpr int GROUP_SMEM = TILE_BYTES * (1 + 2 * NS);
+constexpr int O_STAGE_BYTES = 32 * HD * 2;         // one warp's 32 output rows (bf16), 128B-swizzled for the TMA store
+constexpr int GROUP_SMEM = TILE_BYTES * (1 + 2 * NS) + N_SOFTMAX_WARPS * O_STAGE_BYTES;
 constexpr int SMEM_BYTES = N_GROUPS * GROUP_SMEM + 256 /*barriers*/ + 1024 /*align*/;
 constexpr uint32_t TMEM_COLS = 512, GROUP_COLS = 256, S_COL = 0, P_COL = 128, O_COL = 192;
 constexpr float RESCALE_THRESHOLD = 8.0f;    // log2 units
@@ -105,6 +106,29 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// exp2 on the FMA pipe for a fraction of the scores (the MUFU pipe, 16 ex2/clk/SM, is the kernel's bound):
+// round-to-nearest split x = n + f, |f| <= 0.5, 2^f by a degree-3 minimax polynomial (relative error 7.5e-5,
+// far below the bf16 rounding of P), 2^n applied through the exponent bits.  Inputs are clamped at -125.
+__device__ __forceinline__ void ex2_emul2(float x0, float x1, float& p0, float& p1) {
+  const uint64_t x = pack2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+  const uint64_t magic = pack2(12582912.f, 12582912.f);            // 1.5 * 2^23: low mantissa bits = round(x)
+  const uint64_t t = fadd2(x, magic);
+  const uint64_t n = fadd2(t, pack2(-12582912.f, -12582912.f));
+  const uint64_t f = fadd2(x, fmul2(n, pack2(-1.f, -1.f)));
+  uint64_t p = ffma2(pack2(0.055171407759189606f, 0.055171407759189606f), f, pack2(0.24261075258255005f, 0.24261075258255005f));
+  p = ffma2(p, f, pack2(0.6932609677314758f, 0.6932609677314758f));
+  p = ffma2(p, f, pack2(0.9999281167984009f, 0.9999281167984009f));
+  float t0, t1, q0, q1;
+  unpack2(t, t0, t1);
+  unpack2(p, q0, q1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
+__device__ __forceinline__ void tma_store_2d_(const CUtensorMap* map, uint32_t src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"((uint64_t)map), "r"(src), "r"(x), "r"(y) : "memory");
+}
+
 struct TileSeq {   // key tiles visible to one query tile
   int seg0_end, seg1_begin, seg1_end, n0, n_kt;
   __device__ __forceinline__ void get(int it, int& k0, int& cnt, bool& s1) const {
@@ -142,7 +166,7 @@ struct Walker {
   }
 };
 struct Item {
-  int q_first, q_count, qb_lo, qb_hi, h, row_base;
+  int q_first, q_count, qb_lo, qb_hi, h, row_base, b;
   TileSeq ts;
 };
 __device__ __forceinline__ int qblock_of(const Shape& sh, int m) {
@@ -153,6 +177,7 @@ __device__ __forceinline__ Item item_of(const Shape& sh, const Walker& wk) {
   const int tile_id = sh.n_tiles - 1 - wk.rank;
   const int b = fdiv(wk.hb, sh.magic_H);
   it.h = wk.hb - b * sh.H;
+  it.b = b;
   it.row_base = b * sh.M;
   if (tile_id < sh.n_main_tiles) { it.q_first = tile_id * QT; it.q_count = min(QT, sh.T2 - it.q_first); }
   else { it.q_first = sh.T2 + (tile_id - sh.n_main_tiles) * QT; it.q_count = min(QT, sh.M - it.q_first); }
@@ -170,8 +195,9 @@ __device__ __forceinline__ Item item_of(const Shape& sh, const Walker& wk) {
 }
 
 __global__ void __launch_bounds__(N_THREADS, 1)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const uint8_t* __restrict__ keypad,
-               bf16* __restrict__ ctx, Shape sh, int n_items, float scale_log2) {
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmCtx,
+               const uint8_t* __restrict__ keypad, const uint8_t* __restrict__ pad_blk, bf16* __restrict__ ctx, Shape sh,
+               int n_items, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -180,6 +206,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const uint8_t* __restr
   const uint32_t sQ = smem_base + grp * GROUP_SMEM;
   const uint32_t sK = sQ + TILE_BYTES;
   const uint32_t sV = sK + NS * TILE_BYTES;
+  const uint32_t sO = sV + NS * TILE_BYTES;                 // [4 warps][32 rows][128 B]
   const uint32_t bars0 = smem_base + N_GROUPS * GROUP_SMEM;
   const uint32_t bars = bars0 + grp * 96;
   const uint32_t bar_qfull = bars, bar_kfull = bars + 8, bar_vfull = bar_kfull + 8 * NS, bar_sfull = bar_vfull + 8 * NS,
@@ -335,33 +362,31 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const uint8_t* __restr
     const int T2 = sh.T2, main_ctx = sh.main_ctx, rc = sh.rc, rcd = sh.rcd, nb = sh.nb;
     bool ok = true;
     int gt = 0;
-    // padding bytes of the key columns 4*lane .. 4*lane+3 of the NEXT tile in this CTA's sequence (it may belong to
-    // the next work item): fetched with volatile loads one tile ahead, looked at only when that tile starts, so
-    // the global-load latency never sits on the critical path
-    uint32_t kb0 = 0, kb1 = 0, kb2 = 0, kb3 = 0;
+    // Key padding.  prep_masks leaves one "any padded key" flag per 128 tokens (pad_blk); the two flags a key
+    // tile can touch are fetched one tile ahead with volatile loads and only looked at when that tile starts,
+    // so the common case (no padding in the tile) costs two uniform byte loads off the critical path.  Only
+    // flagged tiles (or callers without pad_blk) read their 128 padding bytes (4 per lane).
+    const int pad_stride = (sh.M + 127) >> 7;
+    uint32_t pf0 = 0, pf1 = 0;
     auto ldu8 = [](const uint8_t* p_) {
       uint32_t v;
       asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p_));
       return v;
     };
-    auto prefetch_kp = [&](const Item& pi, int it_) {
+    auto prefetch_flags = [&](const Item& pi, int it_) {
+      if (pad_blk == nullptr) return;
       int k0_, cnt_; bool s1_;
       pi.ts.get(it_, k0_, cnt_, s1_);
-      // unconditional loads (columns past the tile's end are clamped to its last byte and discarded when the
-      // bytes are looked at): nothing may consume a loaded value here, or the load latency is exposed
-      const uint8_t* p_ = keypad + pi.row_base + k0_;
-      const int last = cnt_ - 1;
-      kb0 = ldu8(p_ + min(4 * lane + 0, last));
-      kb1 = ldu8(p_ + min(4 * lane + 1, last));
-      kb2 = ldu8(p_ + min(4 * lane + 2, last));
-      kb3 = ldu8(p_ + min(4 * lane + 3, last));
+      const uint8_t* p_ = pad_blk + (size_t)pi.b * pad_stride;
+      pf0 = ldu8(p_ + (k0_ >> 7));
+      pf1 = ldu8(p_ + ((k0_ + cnt_ - 1) >> 7));
     };
     Walker wk, wnext;
     wk.init(sh, vcta);
     wnext = wk;
     wnext.next(sh);
     Item im;
-    if (wk.w < n_items) { im = item_of(sh, wk); prefetch_kp(im, 0); }
+    if (wk.w < n_items) { im = item_of(sh, wk); prefetch_flags(im, 0); }
     for (; wk.w < n_items && ok; wk.next(sh), wnext.next(sh)) {
       const int n_kt = im.ts.n_kt;
       const bool have_next = wnext.w < n_items;
@@ -376,15 +401,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const uint8_t* __restr
         const int g = gt + it;
         im.ts.get(it, k0, cnt, s1);
         TRACE(0, g, 0);
-        const int kr = cnt - 4 * lane;     // columns 4*lane+k of this tile exist for k < kr
-        const uint32_t kp_cur = (uint32_t)(kr > 0 && kb0 != 0) | ((uint32_t)(kr > 1 && kb1 != 0) << 8) |
-                                ((uint32_t)(kr > 2 && kb2 != 0) << 16) | ((uint32_t)(kr > 3 && kb3 != 0) << 24);
+        uint32_t kp_cur = 0;               // byte k: column 4*lane+k of this tile is padded
+        if (pad_blk == nullptr || (pf0 | pf1) != 0) {
+          const uint8_t* p_ = keypad + im.row_base + k0;
+          const int last = cnt - 1, kr = cnt - 4 * lane;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            kp_cur |= (uint32_t)(kr > k && p_[min(4 * lane + k, last)] != 0) << (8 * k);
+        }
         const bool has_pad = __any_sync(0xffffffffu, kp_cur != 0);
         TRACE(0, g, 8);
-#ifndef W2VS_EXP_NO_KP
-        if (it + 1 < n_kt) prefetch_kp(im, it + 1);
-        else if (have_next) { const Item nx = item_of(sh, wnext); prefetch_kp(nx, 0); }
-#endif
+        if (it + 1 < n_kt) prefetch_flags(im, it + 1);
+        else if (have_next) { const Item nx = item_of(sh, wnext); prefetch_flags(nx, 0); }
         TRACE(0, g, 10);
         // ---- visible column range of this row.  Rows of a warp are consecutive tokens, so lo and hi are
         //      non-decreasing in the lane index: the warp-wide classification needs lanes 0 and 31 only.
@@ -491,9 +519,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const uint8_t* __restr
           } else {
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
-              float a0, a1;
+              float a0, a1, p0, p1;
               unpack2(ffma2(pack2(__uint_as_float(r[c][j]), __uint_as_float(r[c][j + 1])), sc2, nm2), a0, a1);
-              const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+              if ((j >> 1) % 3 == 2) {          // 5 of 16 pairs on the FMA pipe, 11 on the MUFU pipe
+                ex2_emul2(a0, a1, p0, p1);
+              } else {
+                p0 = ex2_approx(a0);
+                p1 = ex2_approx(a1);
+              }
               l2 = fadd2(l2, pack2(p0, p1));
               pk[j >> 1] = pack_bf16x2(p0, p1);
             }
@@ -509,34 +542,70 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const uint8_t* __restr
       }
       gt += n_kt;
 
-      // ---- epilogue: O / l -> bf16 -> ctx
+      // ---- epilogue: O / l -> bf16 -> ctx.  The next item is worked out while PV(last) is still in flight.
       float la, lb;
       unpack2(l2, la, lb);
       const float l = la + lb;
+      const float inv = l > 0.f ? 1.0f / l : 0.f;
+      const int out_row0 = im.row_base + im.q_first + quarter * 32;      // first token row this warp writes
+      const int out_col = im.h * HD;
+      const int n_valid = min(max(im.q_count - quarter * 32, 0), 32);    // valid rows of this warp
+      TRACE(0, gt - 1, 11);
+      if (have_next) im = item_of(sh, wnext);
+      TRACE(0, gt - 1, 14);
       ok = mbar_wait(bar_pvdone, (gt - 1) & 1) && ok;
       tc_fence_after();
-      const float inv = l > 0.f ? 1.0f / l : 0.f;
-      bf16* dst = ctx + ((size_t)im.row_base + im.q_first + row) * D + (size_t)im.h * HD;
+      TRACE(0, gt - 1, 12);
+      const uint32_t stage = sO + quarter * O_STAGE_BYTES;
+      if (n_valid == 32) {
+        // full warp tile: rows -> 128B-swizzled staging -> one TMA store
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store has drained the slot
+        __syncwarp();
 #pragma unroll
-      for (int c = 0; c < HD / 32; ++c) {
-        uint32_t o[32];
-        tmem_ld32(tlane + O_COL + c * 32, o);
-        tmem_ld_wait();
-        if (row < im.q_count) {
+        for (int c = 0; c < HD / 32; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tlane + O_COL + c * 32, o);
+          tmem_ld_wait();
 #pragma unroll
           for (int gq = 0; gq < 4; ++gq) {
-            uint4 v;
-            v.x = pack_bf16x2(__uint_as_float(o[8 * gq + 0]) * inv, __uint_as_float(o[8 * gq + 1]) * inv);
-            v.y = pack_bf16x2(__uint_as_float(o[8 * gq + 2]) * inv, __uint_as_float(o[8 * gq + 3]) * inv);
-            v.z = pack_bf16x2(__uint_as_float(o[8 * gq + 4]) * inv, __uint_as_float(o[8 * gq + 5]) * inv);
-            v.w = pack_bf16x2(__uint_as_float(o[8 * gq + 6]) * inv, __uint_as_float(o[8 * gq + 7]) * inv);
-            *reinterpret_cast<uint4*>(dst + c * 32 + gq * 8) = v;
+            const uint32_t a = stage + lane * 128 + ((uint32_t)((c * 4 + gq) ^ (lane & 7)) << 4);
+            sts128(a, make_uint4(pack_bf16x2(__uint_as_float(o[8 * gq + 0]) * inv, __uint_as_float(o[8 * gq + 1]) * inv),
+                                 pack_bf16x2(__uint_as_float(o[8 * gq + 2]) * inv, __uint_as_float(o[8 * gq + 3]) * inv),
+                                 pack_bf16x2(__uint_as_float(o[8 * gq + 4]) * inv, __uint_as_float(o[8 * gq + 5]) * inv),
+                                 pack_bf16x2(__uint_as_float(o[8 * gq + 6]) * inv, __uint_as_float(o[8 * gq + 7]) * inv)));
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d_(&tmCtx, stage, out_col, out_row0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      } else {
+        // ragged warp tile (end of the main or of the look-ahead segment): guarded per-row stores
+        bf16* dst = ctx + (size_t)(out_row0 + lane) * D + out_col;
+#pragma unroll
+        for (int c = 0; c < HD / 32; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tlane + O_COL + c * 32, o);
+          tmem_ld_wait();
+          if (lane < n_valid) {
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) {
+              uint4 v;
+              v.x = pack_bf16x2(__uint_as_float(o[8 * gq + 0]) * inv, __uint_as_float(o[8 * gq + 1]) * inv);
+              v.y = pack_bf16x2(__uint_as_float(o[8 * gq + 2]) * inv, __uint_as_float(o[8 * gq + 3]) * inv);
+              v.z = pack_bf16x2(__uint_as_float(o[8 * gq + 4]) * inv, __uint_as_float(o[8 * gq + 5]) * inv);
+              v.w = pack_bf16x2(__uint_as_float(o[8 * gq + 6]) * inv, __uint_as_float(o[8 * gq + 7]) * inv);
+              *reinterpret_cast<uint4*>(dst + c * 32 + gq * 8) = v;
+            }
           }
         }
       }
       tc_fence_before();   // orders these TMEM reads before this warp's next p_full arrive (next item overwrites O)
-      if (have_next) im = item_of(sh, wnext);
+      TRACE(0, gt - 1, 13);
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging must outlive its last store
   }
 
   tc_fence_before();
@@ -583,7 +652,11 @@ w2vs_status_t launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
   sh.magic_rcd = sh.rcd >= 2 ? magic(sh.rcd) : 0u;   // d == 1 handled below
   sh.magic_H = a.heads >= 2 ? magic(a.heads) : 0u;
   const float scale_log2 = (1.0f / sqrtf((float)HD)) * 1.4426950408889634f;
-  attn_tc_kernel<<<grid, N_THREADS, SMEM_BYTES, st>>>(tm, a.keypad, (bf16*)a.ctx, sh, (int)n_items, scale_log2);
+  alignas(64) CUtensorMap tmc;   // ctx [B*M, D]: one warp's 32 rows x 64 columns per store
+  W2VS_TRY(tc::make_map(&tmc, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.ctx, (uint64_t)a.D, (uint64_t)a.B * sh.M,
+                        (uint64_t)a.D, HD, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+  attn_tc_kernel<<<grid, N_THREADS, SMEM_BYTES, st>>>(tm, tmc, a.keypad, a.pad_blk, (bf16*)a.ctx, sh, (int)n_items,
+                                                      scale_log2);
   W2VS_CHECK_LAUNCH("attn_tc_kernel");
   return W2VS_OK;
 }

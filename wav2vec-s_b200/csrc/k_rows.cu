@@ -186,7 +186,8 @@ w2vs_status_t launch_layernorm(const LayerNormArgs& a, cudaStream_t st) {
 __global__ void __launch_bounds__(256)
 prep_masks_kernel(const int32_t* __restrict__ lengths, const uint8_t* __restrict__ sample_mask,
                   int mask_len, uint8_t* __restrict__ frame_pad, int32_t* __restrict__ pos,
-                  uint8_t* __restrict__ keypad, int T, int T2, int M, int main_ctx, int rc) {
+                  uint8_t* __restrict__ keypad, uint8_t* __restrict__ pad_blk, int T, int T2, int M, int main_ctx,
+                  int rc) {
   __shared__ int s_part[256];
   const int b = blockIdx.x, tid = threadIdx.x;
   const int w = mask_len > 0 ? mask_len / T : 0;
@@ -233,11 +234,22 @@ prep_masks_kernel(const int32_t* __restrict__ lengths, const uint8_t* __restrict
     }
     keypad[(size_t)b * M + m] = kp ? 1 : 0;
   }
+  // pad_blk[b][j] = any padded key among tokens [128 j, 128 j + 128): lets the attention kernel skip the
+  // per-key padding bytes of key tiles that have none
+  if (pad_blk != nullptr) {
+    __syncthreads();
+    const int nblk = (M + 127) / 128;
+    for (int j = tid; j < nblk; j += 256) {
+      uint8_t any = 0;
+      for (int m = 128 * j; m < min(M, 128 * j + 128); ++m) any |= keypad[(size_t)b * M + m];
+      pad_blk[(size_t)b * nblk + j] = any;
+    }
+  }
 }
 
 w2vs_status_t launch_prep_masks(const PrepArgs& a, cudaStream_t st) {
   prep_masks_kernel<<<a.B, 256, 0, st>>>(a.lengths, a.sample_mask, a.mask_len, a.frame_pad, a.pos,
-                                         a.keypad, a.T, a.T2, a.M, a.main_ctx, a.rc);
+                                         a.keypad, a.pad_blk, a.T, a.T2, a.M, a.main_ctx, a.rc);
   W2VS_CHECK_LAUNCH("prep_masks_kernel");
   return W2VS_OK;
 }

@@ -29,6 +29,7 @@ w2vs_status_t launch_layernorm(const LayerNormArgs& a, cudaStream_t st);
 struct PrepArgs {
   const int32_t* lengths; const uint8_t* sample_mask; int mask_len;
   uint8_t* frame_pad; int32_t* pos; uint8_t* keypad;
+  uint8_t* pad_blk;                 // [B][ceil(M/128)] any-padding flags per 128 tokens (may be NULL)
   int B, T, T2, M, main_ctx, rc;
 };
 w2vs_status_t launch_prep_masks(const PrepArgs& a, cudaStream_t st);
@@ -81,6 +82,7 @@ struct AttnArgs {
   const void* qkv; const uint8_t* keypad; void* ctx; int dtype;
   int B, T2, main_ctx, rc, heads, D;
   int n_step_q, n_step_keys; const void* kv_cache; int64_t kv_rows;
+  const uint8_t* pad_blk;           // optional [B][ceil(M/128)] flags from prep_masks (block mode, tcgen05 kernel)
 };
 w2vs_status_t launch_attention_simt(const AttnArgs& a, cudaStream_t st);
 w2vs_status_t launch_attention_mma(const AttnArgs& a, cudaStream_t st);   // mma.sync flash kernel (also step mode)

@@ -239,6 +239,7 @@ void make_workspace(const w2vs_config* cfg, const Geometry& g, int B, Workspace*
   ws->frame_pad = b.take((size_t)B * g.T);
   ws->pos = b.take((size_t)B * g.T * 4);
   ws->keypad = b.take((size_t)B * g.M);
+  ws->pad_blk = b.take((size_t)B * ((g.M + 127) / 128));
   const size_t tok = (size_t)B * g.M + 128;  // slack rows: tile tails of TMA loads stay in-bounds anyway
   ws->x = b.take(tok * D * 4);
   ws->xa = b.take(tok * D * as);

@@ -68,6 +68,7 @@ struct Workspace {
   size_t frame_pad;            // u8 [B][T]
   size_t pos;                  // i32 [B][T]
   size_t keypad;               // u8 [B][M]
+  size_t pad_blk;              // u8 [B][ceil(M/128)]
   size_t x;                    // fp32 [B*M][D] residual stream
   size_t xa;                   // act [B*M][D]
   size_t qkv;                  // act [B*M][3D]
