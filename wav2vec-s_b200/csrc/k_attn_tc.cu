@@ -52,7 +52,10 @@ constexpr int TILE_BYTES = 128 * HD * 2;     // 16 KB: Q, K or V tile
 constexpr int NS = 2;                        // K ring and V ring depth
 constexpr int N_SOFTMAX_WARPS = 4;            // per group
 constexpr int N_GROUPS = 2, N_THREADS = 384;  // warps 0-7 softmax (two groups), 8-9 MMA, 10-11 idle
-constexpr int REGS_SOFTMAX = 232, REGS_OTHER = 40;
+// setmaxnreg moves registers inside what the CTA was launched with (384 threads x 168 registers, the cap that
+// __launch_bounds__(384, 1) gives ptxas): asking for more than the MMA warpgroup gives back blocks forever.
+constexpr int REGS_LAUNCH = 168, REGS_SOFTMAX = 224, REGS_OTHER = 56;
+static_assert(256 * REGS_SOFTMAX + 128 * REGS_OTHER <= 384 * REGS_LAUNCH, "setmaxnreg pool overdrawn");
 constexpr int O_STAGE_BYTES = 32 * HD * 2;         // one warp's 32 output rows (bf16), 128B-swizzled for the TMA store
 constexpr int GROUP_SMEM = TILE_BYTES * (1 + 2 * NS) + N_SOFTMAX_WARPS * O_STAGE_BYTES;
 constexpr int SMEM_BYTES = N_GROUPS * GROUP_SMEM + 256 /*barriers*/ + 1024 /*align*/;
@@ -216,6 +219,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
   const int D = sh.D;
   const int vcta = 2 * blockIdx.x + grp;
+#ifdef W2VS_ATTN_ONE_GROUP      // experiment: group 1 idles (measures one pipeline alone on the SM)
+  if (grp == 1) n_items = 0;
+#endif
 #ifdef W2VS_ATTN_TRACE
   const bool trace_on = blockIdx.x == 0 && lane == 0 && (warp == 1 || warp == 2 * N_SOFTMAX_WARPS);
 #endif
@@ -413,7 +419,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
         TRACE(0, g, 8);
         if (it + 1 < n_kt) prefetch_flags(im, it + 1);
         else if (have_next) { const Item nx = item_of(sh, wnext); prefetch_flags(nx, 0); }
-        TRACE(0, g, 10);
         // ---- visible column range of this row.  Rows of a warp are consecutive tokens, so lo and hi are
         //      non-decreasing in the lane index: the warp-wide classification needs lanes 0 and 31 only.
         int lo = 0, hi = 0;
@@ -476,6 +481,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
             mxc = fmaxf(mxc, fmaxf(__uint_as_float(r[c][j + 4]), __uint_as_float(r[c][j + 5])));
             mxd = fmaxf(mxd, fmaxf(__uint_as_float(r[c][j + 6]), __uint_as_float(r[c][j + 7])));
           }
+          if (c == 0) TRACE(0, g, 10);
+          if (c == 2) TRACE(0, g, 14);
         }
         mxa = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
         const float mx = mxa;
@@ -521,7 +528,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
             for (int j = 0; j < 32; j += 2) {
               float a0, a1, p0, p1;
               unpack2(ffma2(pack2(__uint_as_float(r[c][j]), __uint_as_float(r[c][j + 1])), sc2, nm2), a0, a1);
-              if ((j >> 1) % 3 == 2) {          // 5 of 16 pairs on the FMA pipe, 11 on the MUFU pipe
+#ifndef W2VS_ATTN_EMUL_MOD
+#define W2VS_ATTN_EMUL_MOD 3
+#endif
+              if (W2VS_ATTN_EMUL_MOD > 0 && (j >> 1) % W2VS_ATTN_EMUL_MOD == W2VS_ATTN_EMUL_MOD - 1) {   // MOD 3: 5 of 16 pairs on the FMA pipe
                 ex2_emul2(a0, a1, p0, p1);
               } else {
                 p0 = ex2_approx(a0);

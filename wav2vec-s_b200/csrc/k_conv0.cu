@@ -137,7 +137,7 @@ conv0_kernel(const TIn* __restrict__ wav, int64_t wav_ld, const float* __restric
             v1 = fmaf(v1, sc.y, sh.y);
           }
         }
-        gelu_erf2(v0, v1);
+        gelu2<TOut>(v0, v1);
         if (sizeof(TOut) == 2) {
           *reinterpret_cast<uint32_t*>(o + c) = pack_bf16x2(v0, v1);
         } else {

@@ -41,6 +41,15 @@ constexpr int N_THREADS = 64 + 32 * N_EPI_WARPS;
 // the critical path of every stage, so they take the two highest ids; the epilogue warps are 0..7.
 constexpr int PRODUCER_WARP = N_EPI_WARPS, MMA_WARP = N_EPI_WARPS + 1;
 constexpr int CHUNK = 32;                  // columns per epilogue chunk
+// In-place residual (C += A.W^T + bias): true = the staged tile is added to C by the TMA reduction path
+// (cp.reduce.async.bulk.tensor .add, fp32 adds in L2) -- no residual load, no second pass through smem;
+// false = the residual chunk is TMA-loaded into the staging slot and added by the epilogue threads.
+// Measured on B200 (cfg3, 24 layers): out_proj 5.5 ms -> 6.4 ms with the reduction path (fc2 unchanged): the
+// L2 reduction units sustain less than the 4.3 TB/s the K=1024 product moves, so the default stays 0.
+#ifndef W2VS_GEMM_TMA_REDUCE
+#define W2VS_GEMM_TMA_REDUCE 0
+#endif
+constexpr bool kTmaReduce = W2VS_GEMM_TMA_REDUCE != 0;
 constexpr int SMEM_LIMIT = 232448;
 
 template <int BN, typename TC> struct Cfg2 {
@@ -182,7 +191,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
       for (int i = lane; i < BN / 2; i += 32) bs[i] = (bias != nullptr && colw + i < N) ? bias[colw + i] : 0.f;
       // residual chunk 0 prefetch (overlaps the wait for the accumulator)
-      if (has_residual && lane == 0) {
+      if (!kTmaReduce && has_residual && lane == 0) {
         bulk_wait_read<0>();                           // earlier stores from slot 0/1 have been read out
         mbar_expect_tx(my_res_bar, C2::kSlotBytes);
         tma_load_2d(slot0, &tmC, my_res_bar, colw, row0);
@@ -197,7 +206,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int c = 0; c < C2::kChunksPerWarp; ++c) {
         const int sl = c & 1;
         const uint32_t slot = slot0 + sl * C2::kSlotBytes;
-        if (has_residual) {
+        if (!kTmaReduce && has_residual) {
           if (c + 1 < C2::kChunksPerWarp && lane == 0) {
             bulk_wait_read<0>();                       // the store that used the other slot has drained it
             mbar_expect_tx(my_res_bar + 8 * (sl ^ 1), C2::kSlotBytes);
@@ -214,9 +223,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int j = 0; j < 32; j += 2) {
           const float2 bb = *reinterpret_cast<const float2*>(bs + c * CHUNK + j);   // smem broadcast
           unpack2(fadd2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), pack2(bb.x, bb.y)), v[j], v[j + 1]);
-          if (gelu) gelu_erf2(v[j], v[j + 1]);
+          if (gelu) gelu2<TC>(v[j], v[j + 1]);
         }
-        if (has_residual) {
+        if (!kTmaReduce && has_residual) {
           ok = mbar_wait(my_res_bar + 8 * sl, (res_phase >> sl) & 1u);
           res_phase ^= 1u << sl;
         }
@@ -228,7 +237,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int j = 0; j < 8; ++j) {
             const uint32_t a = rowaddr + ((uint32_t)(j ^ (lane & 7)) << 4);
             float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            if (has_residual) {
+            if (!kTmaReduce && has_residual) {
               const uint4 rr = lds128(a);
               o.x += __uint_as_float(rr.x); o.y += __uint_as_float(rr.y);
               o.z += __uint_as_float(rr.z); o.w += __uint_as_float(rr.w);
@@ -248,7 +257,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         fence_async_smem();                            // generic-proxy writes -> visible to the TMA engine
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&tmC, slot, colw + c * CHUNK, row0);
+          if (kTmaReduce && has_residual) tma_reduce_add_2d(&tmC, slot, colw + c * CHUNK, row0);
+          else tma_store_2d(&tmC, slot, colw + c * CHUNK, row0);
           bulk_commit();
         }
       }

@@ -70,7 +70,9 @@ layernorm_rows_kernel(const TIn* x, int64_t ldx, const float* __restrict__ gamma
     if (c0 < N) {
       if (gelu) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[j][e] = gelu_erf(v[j][e]);
+        for (int e = 0; e < 8; e += 2) {
+          if (out_f32) gelu_erf2(v[j][e], v[j][e + 1]); else gelu2<TAct>(v[j][e], v[j][e + 1]);
+        }
       }
       if (out_f32) store8(out_f32 + (size_t)row * ldo + c0, v[j]);
       if (out_act) store8(out_act + (size_t)row * ldo + c0, v[j]);
@@ -129,7 +131,9 @@ layernorm_f32_kernel(const float* x, int64_t ldx, const float* __restrict__ gamm
     y.y = (v[j].y - mean) * rstd * g.y + bt.y;
     y.z = (v[j].z - mean) * rstd * g.z + bt.z;
     y.w = (v[j].w - mean) * rstd * g.w + bt.w;
-    if (gelu) { y.x = gelu_erf(y.x); y.y = gelu_erf(y.y); y.z = gelu_erf(y.z); y.w = gelu_erf(y.w); }
+    if (gelu) {
+      if (out_f32) { gelu_erf2(y.x, y.y); gelu_erf2(y.z, y.w); } else { gelu2<TAct>(y.x, y.y); gelu2<TAct>(y.z, y.w); }
+    }
     const size_t o = (size_t)row * ldo + 4 * lane + 128 * j;
     if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = y;
     if (out_act) {
