@@ -8,7 +8,7 @@
 
 int main() {
   using namespace w2vs;
-  const int B = 8, T2 = 1000, main_ctx = 16, rc = 8, heads = 16, D = 1024;
+  const int B = 64, T2 = 1000, main_ctx = 16, rc = 8, heads = 16, D = 1024;
   const int M = T2 + (T2 / main_ctx) * rc;
   bf16 *qkv, *ctx; uint8_t* kp;
   if (cudaMalloc(&qkv, (size_t)B * M * 3 * D * 2 + (1 << 20)) != cudaSuccess) { printf("alloc failed\n"); return 1; }
@@ -25,6 +25,7 @@ int main() {
   a.qkv = qkv; a.keypad = kp; a.ctx = ctx; a.dtype = W2VS_BF16; a.B = B; a.T2 = T2; a.main_ctx = main_ctx; a.rc = rc;
   a.heads = heads; a.D = D;
   { int nb = 0; cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, attn_tc_kernel, N_THREADS, SMEM_BYTES);
     cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, attn_tc_kernel);
     printf("occupancy: %d CTAs/SM (regs %d, static smem %zu, dyn smem %d)\n", nb, fa.numRegs, fa.sharedSizeBytes, SMEM_BYTES); }
@@ -36,6 +37,7 @@ int main() {
   cudaDeviceSynchronize();
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   printf("attn_tc: %.1f us per launch (B=%d)  err=%s\n", ms * 100, B, cudaGetErrorString(cudaGetLastError()));
+#ifdef W2VS_ATTN_TRACE
   static long long tr[2][64][16];
   cudaMemcpyFromSymbol(tr, g_attn_trace, sizeof(tr));
   long long t0 = tr[0][0][0];
@@ -51,5 +53,6 @@ int main() {
     for (int e = 0; e < 8; ++e) printf(" %7lld", tr[1][it][e] ? tr[1][it][e] - t0 : -1);
     printf("\n");
   }
+#endif
   return 0;
 }

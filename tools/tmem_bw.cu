@@ -74,6 +74,30 @@ __global__ void k_alu(int iters, long long* out, float* sink, float seed) {
   float s = 0; for (int j = 0; j < 16; ++j) s += x[j];
   sink[threadIdx.x] = s;
 }
+// dependent-chain latency (one chain per thread): cycles per op
+template <int OP>
+__global__ void k_lat(int iters, long long* out, float* sink, float seed) {
+  float a = seed + threadIdx.x * 1e-6f, b = seed * 0.5f, c = seed * 0.25f;
+  uint64_t v;
+  asm volatile("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(a), "f"(b));
+  long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (OP == 0) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a) : "f"(b), "f"(c));
+      if (OP == 1) asm volatile("fma.rn.f32x2 %0, %0, %0, %0;" : "+l"(v));
+      if (OP == 2) asm volatile("add.rn.f32x2 %0, %0, %0;" : "+l"(v));
+      if (OP == 3) asm volatile("max.f32 %0, %0, %1;" : "+f"(a) : "f"(b));
+      if (OP == 4) asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(a) : "f"(b), "f"(c));
+      if (OP == 5) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a));
+    }
+  }
+  long long t1 = clock64();
+  if (threadIdx.x == 0) out[0] = t1 - t0;
+  float x, y;
+  asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+  sink[threadIdx.x] = a + x + y;
+}
 int main() {
   long long* out; uint32_t* sink; cudaMalloc(&out, 64 * 8); cudaMalloc(&sink, 4096 * 4);
   long long h[32];
@@ -102,5 +126,17 @@ int main() {
       printf("%-12s %3d threads: %.2f cycles per warp-instruction per warp, %.1f thread-ops/clk/SM\n", names[op], nthreads,
              (double)h[0] / 16000.0, 16000.0 * nthreads / (double)h[0]);
     }
+  const char* lnames[] = {"fma.f32", "fma.f32x2", "add.f32x2", "max.f32", "max3.f32", "ex2.approx"};
+  for (int op = 0; op < 6; ++op) {
+    if (op == 0) k_lat<0><<<1, 32>>>(1000, out, (float*)sink, 0.5f);
+    if (op == 1) k_lat<1><<<1, 32>>>(1000, out, (float*)sink, 0.5f);
+    if (op == 2) k_lat<2><<<1, 32>>>(1000, out, (float*)sink, 0.5f);
+    if (op == 3) k_lat<3><<<1, 32>>>(1000, out, (float*)sink, 0.5f);
+    if (op == 4) k_lat<4><<<1, 32>>>(1000, out, (float*)sink, 0.5f);
+    if (op == 5) k_lat<5><<<1, 32>>>(1000, out, (float*)sink, 0.5f);
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+    printf("latency %-12s: %.2f cycles per dependent op\n", lnames[op], (double)h[0] / 16000.0);
+  }
   return 0;
 }

@@ -5,26 +5,27 @@
 // visibility derived from (T', main, rc) and the key-padding bytes; key tiles invisible to a whole query tile
 // are never loaded, tiles entirely below the block diagonal skip the per-element mask.
 //
-// One persistent CTA per SM runs two independent pipelines ("groups", each with its own work-item stream, smem
-// rings, barriers and half of TMEM); one work item = 128 query tokens of one (utterance, head).  Two groups
-// per SM let one group's load/max/store phases hide under the other's exponentials.  The register file is
-// repartitioned with setmaxnreg (softmax warpgroups 216 registers, MMA warpgroup 40): register allocation is
-// per 4 warps, so two 5-warp CTAs per SM would not fit.
-// Roles per group (warps 0-3 / 4-7 softmax of group 0 / 1, warp 8 / 9 MMA of group 0 / 1, warps 10-11 idle):
-//   4 warps    softmax     one query row per thread (TMEM lane = row): the 128 scores of a key tile are read from
+// Three persistent CTAs per SM, each an independent pipeline over its own list of work items (one item = 128
+// query tokens of one (utterance, head)); key tiles are 64 tokens.  The kernel is latency bound per warp (TMEM
+// load -> row max -> exponentials -> P store is one dependent chain per tile) and throughput bound by the MUFU /
+// FMA pipes (16 exp2 / clk / SM), so what matters is how many independent softmax warps each SM sub-partition has
+// to interleave: three here (a 128-column score tile per thread needs 128+ live registers and 256 TMEM columns
+// per pipeline, which caps an SM at two pipelines; measured 2150 cycles per 128x128 tile against a pipe bound of
+// about 900).  Per CTA: TMEM 128 columns (S 64 + O 64), smem 64 KB (Q 16, K 2x8, V 2x8, P 16), 160 threads.
+// Roles (warps 0-3 softmax, warp 4 MMA issuer):
+//   4 warps    softmax     one query row per thread (TMEM lane = row): the 64 scores of a key tile are read from
 //                          TMEM exactly once into registers (tcgen05.ld) and S is handed back to the MMA thread at
 //                          once, so S(g+1) is computed while this tile's exponentials run; range mask, row max
 //                          (thread-local, no cross-thread traffic), lazy rescale of O (only when the max grows by
-//                          more than 2^8), exp2 (ex2.approx, packed f32x2 FMAs/adds around it), row sum, bf16 P ->
-//                          TMEM (tcgen05.st); per item: O / l -> bf16 -> global.
+//                          more than 2^8), exp2 (ex2.approx, part of it emulated on the FMA pipe), row sum, bf16 P
+//                          -> smem in the K-major 128B-swizzled operand layout; per item: O / l -> bf16 -> staged
+//                          in the P buffer -> TMA store.
 //   1 warp     MMA issuer  (one thread; it also issues the TMA loads, at the points where it has just observed that a
 //                          ring slot is free: S(g) retired -> K(g+2); PV(g) retired -> V(g+2); last S of an item
 //                          -> next Q -- no loader warp, no "empty" barriers)
-//                          S = Q K^T  (tcgen05.mma M=128,N=128,K=64: A,B K-major from smem -> TMEM cols 0..127)
-//                          O += P V   (M=128,N=64,K=128: A = P bf16 from TMEM cols 128..191, B = V MN-major from
-//                          smem -> TMEM cols 192..255); owns the TMEM allocation (256 columns).
-// The kernel is bound by the MUFU pipe (16 exp2 / clk / SM: 1024 cycles per 128x128 tile) once everything else
-// overlaps.  TMEM budget: S 128 + P 64 + O 64 = 256 columns per group, 512 per CTA.
+//                          S = Q K^T  (tcgen05.mma M=128,N=64,K=64: A,B K-major from smem -> TMEM cols 0..63)
+//                          O += P V   (M=128,N=64,K=64: A = bf16 P K-major from smem, B = V MN-major from smem
+//                          -> TMEM cols 64..127); owns the TMEM allocation.
 #include <math.h>
 #include <limits.h>
 #include <cuda.h>
@@ -47,19 +48,33 @@ namespace w2vs {
 namespace {
 using namespace tc;
 
-constexpr int QT = 128, KT = 128, HD = 64;
-constexpr int TILE_BYTES = 128 * HD * 2;     // 16 KB: Q, K or V tile
+constexpr int QT = 128, KT = 64, HD = 64;
+constexpr int Q_BYTES = QT * HD * 2;         // 16 KB
+constexpr int KV_BYTES = KT * HD * 2;        // 8 KB: K or V tile
+constexpr int P_BYTES = QT * KT * 2;         // 16 KB: bf16 P (A operand of PV), reused as the output staging tile
 constexpr int NS = 2;                        // K ring and V ring depth
-constexpr int N_SOFTMAX_WARPS = 4;            // per group
-constexpr int N_GROUPS = 2, N_THREADS = 384;  // warps 0-7 softmax (two groups), 8-9 MMA, 10-11 idle
-// setmaxnreg moves registers inside what the CTA was launched with (384 threads x 168 registers, the cap that
-// __launch_bounds__(384, 1) gives ptxas): asking for more than the MMA warpgroup gives back blocks forever.
-constexpr int REGS_LAUNCH = 168, REGS_SOFTMAX = 224, REGS_OTHER = 56;
-static_assert(256 * REGS_SOFTMAX + 128 * REGS_OTHER <= 384 * REGS_LAUNCH, "setmaxnreg pool overdrawn");
-constexpr int O_STAGE_BYTES = 32 * HD * 2;         // one warp's 32 output rows (bf16), 128B-swizzled for the TMA store
-constexpr int GROUP_SMEM = TILE_BYTES * (1 + 2 * NS) + N_SOFTMAX_WARPS * O_STAGE_BYTES;
-constexpr int SMEM_BYTES = N_GROUPS * GROUP_SMEM + 256 /*barriers*/ + 1024 /*align*/;
-constexpr uint32_t TMEM_COLS = 512, GROUP_COLS = 256, S_COL = 0, P_COL = 128, O_COL = 192;
+constexpr int N_SOFTMAX_WARPS = 4;
+constexpr int N_THREADS = 160;               // warps 0-3 softmax, warp 4 MMA
+constexpr int CTAS_PER_SM = 3;
+constexpr int SMEM_BYTES = Q_BYTES + 2 * NS * KV_BYTES + P_BYTES + 256 /*barriers*/ + 1024 /*align*/;
+constexpr uint32_t TMEM_COLS = 128, S_COL = 0, O_COL = 64;
+// barrier waits per role: parked (suspend-time hint) or spinning, see tc_common.cuh
+#ifndef W2VS_ATTN_MMA_PARK
+#define W2VS_ATTN_MMA_PARK 0
+#endif
+#ifndef W2VS_ATTN_SOFTMAX_PARK
+#define W2VS_ATTN_SOFTMAX_PARK 0
+#endif
+#if W2VS_ATTN_MMA_PARK
+#define MMA_WAIT mbar_wait_park
+#else
+#define MMA_WAIT mbar_wait
+#endif
+#if W2VS_ATTN_SOFTMAX_PARK
+#define SOFTMAX_WAIT mbar_wait_park
+#else
+#define SOFTMAX_WAIT mbar_wait
+#endif
 constexpr float RESCALE_THRESHOLD = 8.0f;    // log2 units
 
 __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
@@ -97,6 +112,15 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -197,67 +221,59 @@ __device__ __forceinline__ Item item_of(const Shape& sh, const Walker& wk) {
   return it;
 }
 
-__global__ void __launch_bounds__(N_THREADS, 1)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmCtx,
-               const uint8_t* __restrict__ keypad, const uint8_t* __restrict__ pad_blk, bf16* __restrict__ ctx, Shape sh,
-               int n_items, float scale_log2) {
+__global__ void __launch_bounds__(N_THREADS, CTAS_PER_SM)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+               const __grid_constant__ CUtensorMap tmCtx, const uint8_t* __restrict__ keypad,
+               const uint8_t* __restrict__ pad_blk, bf16* __restrict__ ctx, Shape sh, int n_items, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int grp = warp < 2 * N_SOFTMAX_WARPS ? warp / N_SOFTMAX_WARPS : (warp - 2 * N_SOFTMAX_WARPS) & 1;
-  const bool is_softmax = warp < 2 * N_SOFTMAX_WARPS, is_mma = warp == 2 * N_SOFTMAX_WARPS || warp == 2 * N_SOFTMAX_WARPS + 1;
-  const uint32_t sQ = smem_base + grp * GROUP_SMEM;
-  const uint32_t sK = sQ + TILE_BYTES;
-  const uint32_t sV = sK + NS * TILE_BYTES;
-  const uint32_t sO = sV + NS * TILE_BYTES;                 // [4 warps][32 rows][128 B]
-  const uint32_t bars0 = smem_base + N_GROUPS * GROUP_SMEM;
-  const uint32_t bars = bars0 + grp * 96;
+  const bool is_softmax = warp < N_SOFTMAX_WARPS;
+  const uint32_t sQ = smem_base;
+  const uint32_t sK = sQ + Q_BYTES;
+  const uint32_t sV = sK + NS * KV_BYTES;
+  const uint32_t sP = sV + NS * KV_BYTES;                   // [128 rows][128 B], 128B-swizzled
+  const uint32_t bars = sP + P_BYTES;
   const uint32_t bar_qfull = bars, bar_kfull = bars + 8, bar_vfull = bar_kfull + 8 * NS, bar_sfull = bar_vfull + 8 * NS,
                  bar_sfree = bar_sfull + 8, bar_pfull = bar_sfree + 8, bar_pvdone = bar_pfull + 8;
-  const uint32_t tmem_slot = bars0 + 2 * 96;
+  const uint32_t tmem_slot = bars + 96;
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
   const int D = sh.D;
-  const int vcta = 2 * blockIdx.x + grp;
-#ifdef W2VS_ATTN_ONE_GROUP      // experiment: group 1 idles (measures one pipeline alone on the SM)
-  if (grp == 1) n_items = 0;
-#endif
+  const int vcta = blockIdx.x;
 #ifdef W2VS_ATTN_TRACE
-  const bool trace_on = blockIdx.x == 0 && lane == 0 && (warp == 1 || warp == 2 * N_SOFTMAX_WARPS);
+  const bool trace_on = blockIdx.x == 0 && lane == 0 && (warp == 1 || warp == N_SOFTMAX_WARPS);
 #endif
 
-  if (lane == 0 && is_mma) {            // each MMA warp initialises its group's barriers
+  if (threadIdx.x == N_SOFTMAX_WARPS * 32) {
     mbar_init(bar_qfull, 1);
     for (int s = 0; s < NS; ++s) { mbar_init(bar_kfull + 8 * s, 1); mbar_init(bar_vfull + 8 * s, 1); }
     mbar_init(bar_sfull, 1); mbar_init(bar_sfree, N_SOFTMAX_WARPS); mbar_init(bar_pfull, N_SOFTMAX_WARPS); mbar_init(bar_pvdone, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
-  if (warp == 2 * N_SOFTMAX_WARPS) {
+  if (warp == N_SOFTMAX_WARPS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_all = *tmem_slot_ptr;
-  const uint32_t tmem_base = tmem_all + grp * GROUP_COLS;
+  const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (!is_softmax) {
-    // warpgroup 2 (warps 8-11) gives registers back: the softmax warpgroups hold 128 scores per thread
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_OTHER));
     // ===================== MMA issuer + TMA loader (one thread) =====================
     // The thread that issues the MMAs also knows when each ring slot becomes free (it commits the MMAs that
     // read them), so it issues the TMA loads in its idle time: after S(g+1) is issued it waits for that MMA
-    // (about 260 cycles, it would be waiting for P(g) anyway) and loads K(g+1+NS); after PV(g) it loads
-    // V(g+NS).  The softmax warps stay perfectly balanced (no warp doubles as loader).
-    if (is_mma && lane == 0) {
-      // D=f32, A=B=bf16; QK: both K-major, N=128; PV: B MN-major (bit 16), N=64; M=128
+    // (it would be waiting for P(g) anyway) and loads K(g+1+NS); after PV(g) it loads V(g+NS).
+    if (lane == 0) {
+      // D=f32, A=B=bf16; QK: both K-major, N=64; PV: A K-major (P), B MN-major (bit 16), N=64; M=128
       constexpr uint32_t idesc_qk = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KT >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
       constexpr uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) |
                                     ((uint32_t)(QT >> 4) << 24);
-      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmQKV) : "memory");
-      const uint64_t dQ = umma_desc_sw128(sQ), dK = umma_desc_sw128(sK), dV = umma_desc_mn_sw128(sV);
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmQ) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmKV) : "memory");
+      const uint64_t dQ = umma_desc_sw128(sQ), dK = umma_desc_sw128(sK), dV = umma_desc_mn_sw128(sV), dP = umma_desc_sw128(sP);
       bool ok = true;
       // ---- load cursor: (work item, tile in item, global tile index) of the next K tile and of the next V tile
       struct Cur { Walker wk; int it, g, n_kt, n0, seg1, hcol, row; };
@@ -271,16 +287,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
         if (c.wk.w >= n_items) return;
         const int k0 = c.it < c.n0 ? c.it * KT : c.seg1 + (c.it - c.n0) * KT;
         const int sl = c.g % NS;
-        mbar_expect_tx(bar0 + 8 * sl, TILE_BYTES);
-        tma_load_2d(smem0 + sl * TILE_BYTES, &tmQKV, bar0 + 8 * sl, col0 + c.hcol, c.row + k0);
+        mbar_expect_tx(bar0 + 8 * sl, KV_BYTES);
+        tma_load_2d(smem0 + sl * KV_BYTES, &tmKV, bar0 + 8 * sl, col0 + c.hcol, c.row + k0);
         ++c.g;
         if (++c.it == c.n_kt) { c.it = 0; c.wk.next(sh); cur_item(c); }
       };
       auto load_q = [&](const Walker& wq) {
         if (wq.w >= n_items) return;
         const Item q = item_of(sh, wq);
-        mbar_expect_tx(bar_qfull, TILE_BYTES);
-        tma_load_2d(sQ, &tmQKV, bar_qfull, q.h * HD, q.row_base + q.q_first);
+        mbar_expect_tx(bar_qfull, Q_BYTES);
+        tma_load_2d(sQ, &tmQ, bar_qfull, q.h * HD, q.row_base + q.q_first);
       };
       Cur ck, cv;
       ck.wk.init(sh, vcta); ck.it = 0; ck.g = 0; cur_item(ck);
@@ -294,9 +310,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
 
       auto issue_s = [&](int g) {     // S(g) = Q K(g)^T
         const int sl = g % NS;
-        if (!mbar_wait(bar_kfull + 8 * sl, (g / NS) & 1)) return false;
+        if (!MMA_WAIT(bar_kfull + 8 * sl, (g / NS) & 1)) return false;
         tc_fence_after();
-        const uint64_t dk = dK + (uint64_t)((sl * TILE_BYTES) >> 4);
+        const uint64_t dk = dK + (uint64_t)((sl * KV_BYTES) >> 4);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
           umma_ss(tmem_base + S_COL, dQ + 2 * k, dk + 2 * k, idesc_qk, k > 0 ? 1u : 0u);
@@ -307,12 +323,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       for (; wk.w < n_items && ok; wk.next(sh), wnext.next(sh), ++wi) {
         const Item im = item_of(sh, wk);
         const int n = im.ts.n_kt;
-        if (!(ok = mbar_wait(bar_qfull, wi & 1))) break;
-        if (gt > 0 && !(ok = mbar_wait(bar_sfree, (gt - 1) & 1))) break;   // softmax has read the previous item's last S
+        if (!(ok = MMA_WAIT(bar_qfull, wi & 1))) break;
+        if (gt > 0 && !(ok = MMA_WAIT(bar_sfree, (gt - 1) & 1))) break;   // softmax has read the previous item's last S
         tc_fence_after();
         if (!(ok = issue_s(gt))) break;
         if (n == 1) {     // the item's only S: once it has retired, K's slot and Q are free
-          if (!(ok = mbar_wait(bar_sfull, gt & 1))) break;
+          if (!(ok = MMA_WAIT(bar_sfull, gt & 1))) break;
           load_kv(ck, bar_kfull, sK, D);
           load_q(wnext);
         }
@@ -320,33 +336,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
           const int g = gt + it;
           TRACE(1, g, 0);
           if (it == 0 && n > 1) {   // S(g) of the item's first tile was issued above: free its K slot when it retires
-            if (!(ok = mbar_wait(bar_sfull, g & 1))) break;
+            if (!(ok = MMA_WAIT(bar_sfull, g & 1))) break;
             load_kv(ck, bar_kfull, sK, D);
           }
           if (it + 1 < n) {
-            if (!(ok = mbar_wait(bar_sfree, g & 1))) break;          // softmax holds S(g) in registers
+            if (!(ok = MMA_WAIT(bar_sfree, g & 1))) break;          // softmax holds S(g) in registers
             tc_fence_after();
             TRACE(1, g, 1);
             if (!(ok = issue_s(g + 1))) break;
             TRACE(1, g, 2);
-            if (!(ok = mbar_wait(bar_sfull, (g + 1) & 1))) break;    // S(g+1) retired (idle time: P(g) is not ready yet)
+            if (!(ok = MMA_WAIT(bar_sfull, (g + 1) & 1))) break;    // S(g+1) retired (idle time: P(g) is not ready yet)
             load_kv(ck, bar_kfull, sK, D);                             // K(g+1+NS)
             if (it + 2 == n) load_q(wnext);                            // it was the item's last S: Q is free
             TRACE(1, g, 6);
           }
           const int sl = g % NS;
-          if (!(ok = mbar_wait(bar_vfull + 8 * sl, (g / NS) & 1))) break;
+          if (!(ok = MMA_WAIT(bar_vfull + 8 * sl, (g / NS) & 1))) break;
           TRACE(1, g, 3);
-          if (!(ok = mbar_wait(bar_pfull, g & 1))) break;            // P(g) is in TMEM, O has been rescaled
+          if (!(ok = MMA_WAIT(bar_pfull, g & 1))) break;            // P(g) is in smem, O has been rescaled
           tc_fence_after();
           TRACE(1, g, 4);
-          const uint64_t dv = dV + (uint64_t)((sl * TILE_BYTES) >> 4);
+          const uint64_t dv = dV + (uint64_t)((sl * KV_BYTES) >> 4);
 #pragma unroll
           for (int k = 0; k < KT / 16; ++k)
-            umma_ts(tmem_base + O_COL, tmem_base + P_COL + k * 8, dv + (2048 >> 4) * k, idesc_pv, (it > 0 || k > 0) ? 1u : 0u);
+            umma_ss(tmem_base + O_COL, dP + 2 * k, dv + (2048 >> 4) * k, idesc_pv, (it > 0 || k > 0) ? 1u : 0u);
           tc_commit_1sm(bar_pvdone);
           TRACE(1, g, 5);
-          if (!(ok = mbar_wait(bar_pvdone, g & 1))) break;           // PV(g) retired: V's slot is free
+          if (!(ok = MMA_WAIT(bar_pvdone, g & 1))) break;           // PV(g) retired: V's slot is free
           load_kv(cv, bar_vfull, sV, 2 * D);                           // V(g+NS)
           TRACE(1, g, 7);
         }
@@ -354,96 +370,100 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_SOFTMAX));
     // ===================== softmax warps: one query row per thread =====================
-    // Visibility of the 128 key columns of a tile for one query row is a contiguous column range [lo, hi):
+    // Visibility of the 64 key columns of a tile for one query row is a contiguous column range [lo, hi):
     //   main keys: columns whose block <= qblock(row)  ->  [0, (qb+1)*main - k0)
     //   look-ahead keys: the rc copies owned by qblock(row)  ->  [T2 + qb*rc - k0, +rc)
     // so 32-column chunks are classified per warp as all-visible (no masking), none-visible (not loaded, no
     // exponentials: P = 0) or partial (one range compare per element).  Key padding (any mask, not only a
-    // ragged tail) is detected per warp from the tile's 128 padding bytes and handled per element.
+    // ragged tail) is detected per warp from the tile's 64 padding bytes and handled per element.
     const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;                 // row inside the query tile == TMEM lane
     const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const int T2 = sh.T2, main_ctx = sh.main_ctx, rc = sh.rc, rcd = sh.rcd, nb = sh.nb;
+    const uint32_t p_row = sP + (uint32_t)row * 128;     // this thread's row of the P tile / of the output staging tile
+    const int T2 = sh.T2, main_ctx = sh.main_ctx, rc = sh.rc, nb = sh.nb;
     bool ok = true;
     int gt = 0;
-    // Key padding.  prep_masks leaves one "any padded key" flag per 128 tokens (pad_blk); the two flags a key
-    // tile can touch are fetched one tile ahead with volatile loads and only looked at when that tile starts,
-    // so the common case (no padding in the tile) costs two uniform byte loads off the critical path.  Only
-    // flagged tiles (or callers without pad_blk) read their 128 padding bytes (4 per lane).
+    // Key padding.  prep_masks leaves one "any padded key" flag per 128 tokens (pad_blk); the flags of an
+    // utterance (lane j holds block j) are fetched one work item ahead and folded into a bit mask, so the common
+    // case (no padding in a key tile) costs one or two bit tests.  Only flagged tiles (or callers without
+    // pad_blk, or utterances of more than 32 blocks) read their 64 padding bytes (2 per lane).
     const int pad_stride = (sh.M + 127) >> 7;
-    uint32_t pf0 = 0, pf1 = 0;
-    auto ldu8 = [](const uint8_t* p_) {
-      uint32_t v;
-      asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p_));
+    const bool flags_usable = pad_blk != nullptr && pad_stride <= 32;
+    auto fetch_flags = [&](int b_) -> uint32_t {      // this lane's flag of utterance b_ (raw load, consumed later)
+      uint32_t v = 0;
+      if (flags_usable && lane < pad_stride)
+        asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(pad_blk + (size_t)b_ * pad_stride + lane));
       return v;
-    };
-    auto prefetch_flags = [&](const Item& pi, int it_) {
-      if (pad_blk == nullptr) return;
-      int k0_, cnt_; bool s1_;
-      pi.ts.get(it_, k0_, cnt_, s1_);
-      const uint8_t* p_ = pad_blk + (size_t)pi.b * pad_stride;
-      pf0 = ldu8(p_ + (k0_ >> 7));
-      pf1 = ldu8(p_ + ((k0_ + cnt_ - 1) >> 7));
     };
     Walker wk, wnext;
     wk.init(sh, vcta);
     wnext = wk;
     wnext.next(sh);
     Item im;
-    if (wk.w < n_items) { im = item_of(sh, wk); prefetch_flags(im, 0); }
+    uint32_t flag_raw = 0;
+    if (wk.w < n_items) { im = item_of(sh, wk); flag_raw = fetch_flags(im.b); }
     for (; wk.w < n_items && ok; wk.next(sh), wnext.next(sh)) {
       const int n_kt = im.ts.n_kt;
       const bool have_next = wnext.w < n_items;
+      const uint32_t flag_mask = flags_usable ? __ballot_sync(0xffffffffu, flag_raw != 0) : 0xffffffffu;
+      if (have_next) flag_raw = fetch_flags(fdiv(wnext.hb, sh.magic_H));   // next item's utterance
       // rows past the end of the tile behave like the last valid row (their output is never stored); this keeps
       // the chunk classification uniform across the warp
       const int my_qb = row < im.q_count ? qblock_of(sh, im.q_first + row) : im.qb_hi;
+      // leading main-key tiles that every row of this warp sees completely (rows of a warp are consecutive
+      // tokens, lane 0 has the smallest block): they skip the range arithmetic and the masks altogether
+      const int n_fullvis = min((__shfl_sync(0xffffffffu, my_qb, 0) + 1) * main_ctx, im.ts.seg0_end) / KT;
       float m_ref = -INFINITY;
-      uint64_t l2 = pack2(0.f, 0.f);                     // row sum (two accumulators)
-      int k0, cnt; bool s1;
+      uint64_t l2a = pack2(0.f, 0.f), l2b = pack2(0.f, 0.f);   // row sum (four accumulators)
+      // the P buffer doubles as this warp's output staging tile: the previous item's TMA store must have read it
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
 
       for (int it = 0; it < n_kt && ok; ++it) {
         const int g = gt + it;
-        im.ts.get(it, k0, cnt, s1);
         TRACE(0, g, 0);
-        uint32_t kp_cur = 0;               // byte k: column 4*lane+k of this tile is padded
-        if (pad_blk == nullptr || (pf0 | pf1) != 0) {
-          const uint8_t* p_ = keypad + im.row_base + k0;
-          const int last = cnt - 1, kr = cnt - 4 * lane;
+        uint32_t kp_cur = 0;               // byte k: column 2*lane+k of this tile is padded
+        bool has_pad = false;
+        int lo = 0;
+        uint32_t span = KT;
+        bool all_vis[2] = {true, true}, none_vis[2] = {false, false};
+        if (!(it < n_fullvis && ((flag_mask >> (it >> 1)) & 1u) == 0)) {
+          int k0, cnt; bool s1;
+          im.ts.get(it, k0, cnt, s1);
+          if (((flag_mask >> (k0 >> 7)) | (flag_mask >> ((k0 + cnt - 1) >> 7))) & 1u) {
+            const uint8_t* p_ = keypad + im.row_base + k0;
+            const int last = cnt - 1, kr = cnt - 2 * lane;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            kp_cur |= (uint32_t)(kr > k && p_[min(4 * lane + k, last)] != 0) << (8 * k);
-        }
-        const bool has_pad = __any_sync(0xffffffffu, kp_cur != 0);
-        TRACE(0, g, 8);
-        if (it + 1 < n_kt) prefetch_flags(im, it + 1);
-        else if (have_next) { const Item nx = item_of(sh, wnext); prefetch_flags(nx, 0); }
-        // ---- visible column range of this row.  Rows of a warp are consecutive tokens, so lo and hi are
-        //      non-decreasing in the lane index: the warp-wide classification needs lanes 0 and 31 only.
-        int lo = 0, hi = 0;
-        if (!s1) { hi = min(max((my_qb + 1) * main_ctx - k0, 0), cnt); }
-        else if (my_qb <= nb - 1) { lo = min(max(T2 + my_qb * rc - k0, 0), cnt); hi = min(max(T2 + (my_qb + 1) * rc - k0, 0), cnt); }
-        else { lo = hi = cnt; }             // past the last owner block: sees no look-ahead copy
-        const uint32_t span = (uint32_t)(hi - lo);
-        const int lo_min = __shfl_sync(0xffffffffu, lo, 0), lo_max = __shfl_sync(0xffffffffu, lo, 31);
-        const int hi_min = __shfl_sync(0xffffffffu, hi, 0), hi_max = __shfl_sync(0xffffffffu, hi, 31);
-        bool all_vis[4], none_vis[4];
+            for (int k = 0; k < 2; ++k)
+              kp_cur |= (uint32_t)(kr > k && p_[min(2 * lane + k, last)] != 0) << (8 * k);
+          }
+          has_pad = __any_sync(0xffffffffu, kp_cur != 0);
+          // ---- visible column range of this row.  lo and hi are non-decreasing in the lane index: the warp-wide
+          //      classification needs lanes 0 and 31 only.
+          int hi = 0;
+          if (!s1) { hi = min(max((my_qb + 1) * main_ctx - k0, 0), cnt); }
+          else if (my_qb <= nb - 1) { lo = min(max(T2 + my_qb * rc - k0, 0), cnt); hi = min(max(T2 + (my_qb + 1) * rc - k0, 0), cnt); }
+          else { lo = hi = cnt; }             // past the last owner block: sees no look-ahead copy
+          span = (uint32_t)(hi - lo);
+          const int lo_min = __shfl_sync(0xffffffffu, lo, 0), lo_max = __shfl_sync(0xffffffffu, lo, 31);
+          const int hi_min = __shfl_sync(0xffffffffu, hi, 0), hi_max = __shfl_sync(0xffffffffu, hi, 31);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int c0 = c * 32;
-          all_vis[c] = !has_pad && lo_max <= c0 && c0 + 32 <= hi_min;
-          none_vis[c] = hi_max <= c0 || lo_min >= c0 + 32;
+          for (int c = 0; c < 2; ++c) {
+            const int c0 = c * 32;
+            all_vis[c] = !has_pad && lo_max <= c0 && c0 + 32 <= hi_min;
+            none_vis[c] = hi_max <= c0 || lo_min >= c0 + 32;
+          }
         }
         TRACE(0, g, 9);
-        ok = mbar_wait(bar_sfull, g & 1);
+        ok = SOFTMAX_WAIT(bar_sfull, g & 1);
         tc_fence_after();
         TRACE(0, g, 2);
 
         // ---- this row's scores -> registers (one TMEM read per score); S goes back to the MMA thread at once
-        uint32_t r[4][32];
+        uint32_t r[2][32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 2; ++c)
           if (!none_vis[c]) tmem_ld32(tlane + S_COL + c * 32, r[c]);
         tmem_ld_wait();
         tc_fence_before();
@@ -452,14 +472,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
         TRACE(0, g, 1);
 
         // ---- mask (partial chunks) and row maximum
-        uint32_t pb[4] = {0u, 0u, 0u, 0u};          // pb[k] bit L = padding of column 4L + k
+        uint32_t pb[2] = {0u, 0u};                  // pb[k] bit L = padding of column 2L + k
         if (has_pad) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) pb[k] = __ballot_sync(0xffffffffu, (kp_cur >> (8 * k)) & 0xffu);
+          for (int k = 0; k < 2; ++k) pb[k] = __ballot_sync(0xffffffffu, (kp_cur >> (8 * k)) & 0xffu);
         }
-        float mxa = -INFINITY, mxb = -INFINITY, mxc = -INFINITY, mxd = -INFINITY;
+        float mx8[8];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int k = 0; k < 8; ++k) mx8[k] = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
           if (none_vis[c]) continue;
           if (!all_vis[c]) {
             const int off = c * 32 - lo;
@@ -469,23 +491,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const bool padj = (pb[j & 3] >> (c * 8 + (j >> 2))) & 1u;
+                const bool padj = (pb[j & 1] >> (c * 16 + (j >> 1))) & 1u;
                 r[c][j] = ((uint32_t)(off + j) < span && !padj) ? r[c][j] : 0xff800000u;
               }
             }
           }
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {   // four independent 3-input max chains
-            mxa = fmaxf(mxa, fmaxf(__uint_as_float(r[c][j]), __uint_as_float(r[c][j + 1])));
-            mxb = fmaxf(mxb, fmaxf(__uint_as_float(r[c][j + 2]), __uint_as_float(r[c][j + 3])));
-            mxc = fmaxf(mxc, fmaxf(__uint_as_float(r[c][j + 4]), __uint_as_float(r[c][j + 5])));
-            mxd = fmaxf(mxd, fmaxf(__uint_as_float(r[c][j + 6]), __uint_as_float(r[c][j + 7])));
+          for (int j = 0; j < 32; j += 16) {   // eight independent 3-input max chains
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              mx8[k] = fmaxf(mx8[k], fmaxf(__uint_as_float(r[c][j + 2 * k]), __uint_as_float(r[c][j + 2 * k + 1])));
           }
-          if (c == 0) TRACE(0, g, 10);
-          if (c == 2) TRACE(0, g, 14);
         }
-        mxa = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
-        const float mx = mxa;
+        const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
+                               fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
         TRACE(0, g, 3);
         // ---- running maximum with lazy rescale (exact: the final normalisation uses the same reference)
         const float m_tile = mx * scale_log2;               // -inf stays -inf
@@ -494,31 +513,35 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
         if (grow) {
           alpha = ex2_approx(m_ref - m_tile);
           m_ref = m_tile;
-          l2 = ffma2(l2, pack2(alpha, alpha), pack2(0.f, 0.f));
+          l2a = fmul2(l2a, pack2(alpha, alpha));
+          l2b = fmul2(l2b, pack2(alpha, alpha));
         }
         if (it > 0) {
-          ok = mbar_wait(bar_pvdone, (g - 1) & 1) && ok;    // PV(g-1) retired: P is free, O is stable
+          ok = SOFTMAX_WAIT(bar_pvdone, (g - 1) & 1) && ok;    // PV(g-1) retired: the P buffer is free, O is stable
           tc_fence_after();
           TRACE(0, g, 7);
           if (__any_sync(0xffffffffu, grow)) {
-#pragma unroll
-            for (int c = 0; c < HD / 32; ++c) {
-              uint32_t o[32];
-              tmem_ld32(tlane + O_COL + c * 32, o);
+            // rare (the first tiles of an item): 8 columns at a time, the 64 scores stay in registers meanwhile
+#pragma unroll 1
+            for (int c = 0; c < HD / 8; ++c) {
+              uint32_t o[8];
+              tmem_ld8(tlane + O_COL + c * 8, o);
               tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
-              tmem_st32(tlane + O_COL + c * 32, o);
+              for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+              tmem_st8(tlane + O_COL + c * 8, o);
             }
+            tmem_st_wait();
           }
         }
         TRACE(0, g, 4);
         const float m_use = m_ref == -INFINITY ? 0.f : m_ref;
         const uint64_t sc2 = pack2(scale_log2, scale_log2), nm2 = pack2(-m_use, -m_use);
 
-        // ---- P = exp2(s * scale - m), row sum, bf16 P -> TMEM
+        // ---- P = exp2(s * scale - m), row sum, bf16 P -> smem (K-major operand layout: this thread's row is 128
+        //      contiguous bytes whose 16-byte chunks are XOR-swizzled with the row index)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t pk[16];
           if (none_vis[c]) {
 #pragma unroll
@@ -529,23 +552,25 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
               float a0, a1, p0, p1;
               unpack2(ffma2(pack2(__uint_as_float(r[c][j]), __uint_as_float(r[c][j + 1])), sc2, nm2), a0, a1);
 #ifndef W2VS_ATTN_EMUL_MOD
-#define W2VS_ATTN_EMUL_MOD 3
+#define W2VS_ATTN_EMUL_MOD 4
 #endif
-              if (W2VS_ATTN_EMUL_MOD > 0 && (j >> 1) % W2VS_ATTN_EMUL_MOD == W2VS_ATTN_EMUL_MOD - 1) {   // MOD 3: 5 of 16 pairs on the FMA pipe
+              if (W2VS_ATTN_EMUL_MOD > 0 && (j >> 1) % W2VS_ATTN_EMUL_MOD == W2VS_ATTN_EMUL_MOD - 1) {   // MOD 4: 4 of 16 pairs on the FMA pipe
                 ex2_emul2(a0, a1, p0, p1);
               } else {
                 p0 = ex2_approx(a0);
                 p1 = ex2_approx(a1);
               }
-              l2 = fadd2(l2, pack2(p0, p1));
+              if (j & 2) l2b = fadd2(l2b, pack2(p0, p1)); else l2a = fadd2(l2a, pack2(p0, p1));
               pk[j >> 1] = pack_bf16x2(p0, p1);
             }
           }
-          tmem_st16(tlane + P_COL + c * 16, pk);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            sts128(p_row + ((uint32_t)((c * 4 + q) ^ (row & 7)) << 4), make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]));
         }
         TRACE(0, g, 5);
-        tmem_st_wait();
-        tc_fence_before();
+        fence_async_smem();          // P (generic-proxy writes) -> visible to the tensor core's async-proxy reads
+        tc_fence_before();           // orders the rescale's TMEM accesses before the arrive
         __syncwarp();
         if (lane == 0) mbar_arrive_local(bar_pfull);
         TRACE(0, g, 6);
@@ -554,7 +579,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
 
       // ---- epilogue: O / l -> bf16 -> ctx.  The next item is worked out while PV(last) is still in flight.
       float la, lb;
-      unpack2(l2, la, lb);
+      unpack2(fadd2(l2a, l2b), la, lb);
       const float l = la + lb;
       const float inv = l > 0.f ? 1.0f / l : 0.f;
       const int out_row0 = im.row_base + im.q_first + quarter * 32;      // first token row this warp writes
@@ -562,15 +587,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       const int n_valid = min(max(im.q_count - quarter * 32, 0), 32);    // valid rows of this warp
       TRACE(0, gt - 1, 11);
       if (have_next) im = item_of(sh, wnext);
-      TRACE(0, gt - 1, 14);
-      ok = mbar_wait(bar_pvdone, (gt - 1) & 1) && ok;
+      ok = SOFTMAX_WAIT(bar_pvdone, (gt - 1) & 1) && ok;                    // last PV retired: O is final, P buffer is free
       tc_fence_after();
       TRACE(0, gt - 1, 12);
-      const uint32_t stage = sO + quarter * O_STAGE_BYTES;
       if (n_valid == 32) {
-        // full warp tile: rows -> 128B-swizzled staging -> one TMA store
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store has drained the slot
-        __syncwarp();
+        // full warp tile: rows -> 128B-swizzled staging (this warp's 32 rows of the P buffer) -> one TMA store
 #pragma unroll
         for (int c = 0; c < HD / 32; ++c) {
           uint32_t o[32];
@@ -578,7 +599,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
           tmem_ld_wait();
 #pragma unroll
           for (int gq = 0; gq < 4; ++gq) {
-            const uint32_t a = stage + lane * 128 + ((uint32_t)((c * 4 + gq) ^ (lane & 7)) << 4);
+            const uint32_t a = p_row + ((uint32_t)((c * 4 + gq) ^ (row & 7)) << 4);
             sts128(a, make_uint4(pack_bf16x2(__uint_as_float(o[8 * gq + 0]) * inv, __uint_as_float(o[8 * gq + 1]) * inv),
                                  pack_bf16x2(__uint_as_float(o[8 * gq + 2]) * inv, __uint_as_float(o[8 * gq + 3]) * inv),
                                  pack_bf16x2(__uint_as_float(o[8 * gq + 4]) * inv, __uint_as_float(o[8 * gq + 5]) * inv),
@@ -588,7 +609,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d_(&tmCtx, stage, out_col, out_row0);
+          tma_store_2d_(&tmCtx, sP + (uint32_t)quarter * 32 * 128, out_col, out_row0);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       } else {
@@ -620,8 +641,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2 * N_SOFTMAX_WARPS) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_all), "r"(TMEM_COLS) : "memory");
+  if (warp == N_SOFTMAX_WARPS) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 }  // namespace
@@ -637,21 +658,26 @@ w2vs_status_t launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
   sh.D = a.D; sh.H = a.heads; sh.B = a.B;
   sh.n_main_tiles = (a.T2 + QT - 1) / QT;
   sh.n_tiles = sh.n_main_tiles + (sh.M - a.T2 + QT - 1) / QT;
-  alignas(64) CUtensorMap tm;
-  W2VS_TRY(tc::make_map(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.qkv, (uint64_t)3 * a.D, (uint64_t)a.B * sh.M,
-                        (uint64_t)3 * a.D, HD, 128, CU_TENSOR_MAP_SWIZZLE_128B));
+  alignas(64) CUtensorMap tmq, tmkv;   // same token buffer, boxes of 128 (Q) and 64 (K, V) rows x 64 columns
+  W2VS_TRY(tc::make_map(&tmq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.qkv, (uint64_t)3 * a.D, (uint64_t)a.B * sh.M,
+                        (uint64_t)3 * a.D, HD, QT, CU_TENSOR_MAP_SWIZZLE_128B));
+  W2VS_TRY(tc::make_map(&tmkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.qkv, (uint64_t)3 * a.D, (uint64_t)a.B * sh.M,
+                        (uint64_t)3 * a.D, HD, KT, CU_TENSOR_MAP_SWIZZLE_128B));
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) { set_error("attn_tc smem attribute: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
+    // three CTAs per SM need 3 x 65 KB: ask for the largest shared-memory carve-out (the default sizes it for one CTA)
+    e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) { set_error("attn_tc carve-out attribute: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
     attr_done = true;
   }
   const int64_t n_items = (int64_t)sh.n_tiles * a.heads * a.B;
   W2VS_REQUIRE(n_items < (1ll << 31), "attention problem too large");
-  const int max_ctas = tc::num_sms();         // persistent: one CTA (two pipelines) per SM
-  const int grid = (int)((n_items + 1) / 2 < max_ctas ? (n_items + 1) / 2 : max_ctas);
+  const int max_ctas = CTAS_PER_SM * tc::num_sms();     // persistent: three single-pipeline CTAs per SM
+  const int grid = (int)(n_items < max_ctas ? n_items : max_ctas);
   sh.HB = a.heads * a.B;
-  sh.n_vcta = 2 * grid;
+  sh.n_vcta = grid;
   sh.g_div = sh.n_vcta / sh.HB;
   sh.g_mod = sh.n_vcta % sh.HB;
   // magic multipliers: floor(x / d) == umulhi(x, ceil(2^32 / d)) holds for x < 2^32 / d
@@ -665,8 +691,8 @@ w2vs_status_t launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
   alignas(64) CUtensorMap tmc;   // ctx [B*M, D]: one warp's 32 rows x 64 columns per store
   W2VS_TRY(tc::make_map(&tmc, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.ctx, (uint64_t)a.D, (uint64_t)a.B * sh.M,
                         (uint64_t)a.D, HD, 32, CU_TENSOR_MAP_SWIZZLE_128B));
-  attn_tc_kernel<<<grid, N_THREADS, SMEM_BYTES, st>>>(tm, tmc, a.keypad, a.pad_blk, (bf16*)a.ctx, sh, (int)n_items,
-                                                      scale_log2);
+  attn_tc_kernel<<<grid, N_THREADS, SMEM_BYTES, st>>>(tmq, tmkv, tmc, a.keypad, a.pad_blk, (bf16*)a.ctx, sh,
+                                                      (int)n_items, scale_log2);
   W2VS_CHECK_LAUNCH("attn_tc_kernel");
   return W2VS_OK;
 }
