@@ -1,5 +1,5 @@
 """Per-stage max-abs-rel error of the CUDA path vs the reference golden vectors / the oracle (GPU box).
-    python tools/parity_report.py > gpurun_out/parity_report.txt"""
+    python tests/parity_report.py > gpurun_out/parity_report.txt"""
 import os, sys, warnings
 import numpy as np
 import torch

@@ -551,10 +551,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             for (int j = 0; j < 32; j += 2) {
               float a0, a1, p0, p1;
               unpack2(ffma2(pack2(__uint_as_float(r[c][j]), __uint_as_float(r[c][j + 1])), sc2, nm2), a0, a1);
+              // W2VS_ATTN_EMUL_MOD = n > 0 moves every n-th pair of exponentials to the FMA pipe (ex2_emul2).  Measured
+              // at cfg3 (B200, per layer call): n = 0: 484 us, 8: 491, 5: 494, 4: 498, 3: 506 -- with three CTAs per
+              // SM the kernel is bound by issued instructions, not by the MUFU pipe, so the default is off.
 #ifndef W2VS_ATTN_EMUL_MOD
-#define W2VS_ATTN_EMUL_MOD 4
+#define W2VS_ATTN_EMUL_MOD 0
 #endif
-              if (W2VS_ATTN_EMUL_MOD > 0 && (j >> 1) % W2VS_ATTN_EMUL_MOD == W2VS_ATTN_EMUL_MOD - 1) {   // MOD 4: 4 of 16 pairs on the FMA pipe
+              if (W2VS_ATTN_EMUL_MOD > 0 && (j >> 1) % (W2VS_ATTN_EMUL_MOD > 0 ? W2VS_ATTN_EMUL_MOD : 1) == W2VS_ATTN_EMUL_MOD - 1) {
                 ex2_emul2(a0, a1, p0, p1);
               } else {
                 p0 = ex2_approx(a0);
