@@ -356,16 +356,42 @@ def main():
     def step_device():
         return model.extract_features(wav_dev, None)[0]
 
-    out_host = None
+    # End to end through the public API with HOST buffers: every step copies its waveforms from pinned host
+    # memory and reads its result back to pinned host memory.  The copies run on their own streams with two
+    # buffers each, so the H2D of step i+1 and the D2H of step i-1 overlap the kernels of step i (what a user
+    # feeding the encoder from a data loader does); all of it sits inside the timed region.
+    main_stream = torch.cuda.current_stream()
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    x_dev = [torch.empty_like(wav_host, device=dev) for _ in range(2)]
+    out_host = [None, None]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]      # x_dev[k] consumed by the encoder
+    ev_out = [torch.cuda.Event() for _ in range(2)]       # out_host[k] written
+    e2e_i = [0]
 
     def step_e2e():
-        nonlocal out_host
-        x = wav_host.to(dev, non_blocking=True)
-        y = model.extract_features(x, None)[0]
-        if out_host is None:
-            out_host = torch.empty(y.shape, dtype=y.dtype, pin_memory=True)
-        out_host.copy_(y, non_blocking=True)
+        i = e2e_i[0]; k = i & 1
+        e2e_i[0] += 1
+        with torch.cuda.stream(s_in):
+            if i >= 2:
+                s_in.wait_event(ev_free[k])
+            x_dev[k].copy_(wav_host, non_blocking=True)
+            ev_in[k].record(s_in)
+        main_stream.wait_event(ev_in[k])
+        y = model.extract_features(x_dev[k], None)[0]
+        ev_free[k].record(main_stream)
+        if out_host[k] is None:
+            out_host[k] = torch.empty(y.shape, dtype=y.dtype, pin_memory=True)
+        s_out.wait_stream(main_stream)
+        with torch.cuda.stream(s_out):
+            out_host[k].copy_(y, non_blocking=True)
+            ev_out[k].record(s_out)
+        y.record_stream(s_out)
         return y
+
+    def drain_e2e():
+        main_stream.wait_stream(s_out)
+        main_stream.wait_stream(s_in)
 
     for _ in range(a.warmup):
         y = step_device()
@@ -391,11 +417,13 @@ def main():
     # ---- timed region: end to end through the public API (pinned host in, host out) ---------
     for _ in range(2):
         step_e2e()
+    drain_e2e()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for _ in range(a.steps):
         step_e2e()
+    drain_e2e()          # the last read-back is part of the timed region
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
@@ -423,7 +451,8 @@ def main():
             "clocks": clocks,
             "e2e": {"value": audio_s / (ms_e2e / a.steps / 1e3), "unit": "audio-s/s",
                     "h2d_bytes_per_step": wav_host.numel() * wav_host.element_size(),
-                    "d2h_bytes_per_step": out_host.numel() * out_host.element_size()},
+                    "d2h_bytes_per_step": out_host[0].numel() * out_host[0].element_size(),
+                    "pipeline": "double-buffered copy streams (H2D of step i+1 and D2H of step i-1 overlap step i)"},
             "gpu_launches": int(launches),
             "step_tflops": fl["total"] * B / (ms_step / 1e3) / 1e12,
             "step_frac_of_bf16_sustained": fl["total"] * B / (ms_step / 1e3) / 1e12 / pk["bf16_tflops_sustained"],

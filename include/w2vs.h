@@ -172,7 +172,8 @@ typedef enum {
   W2VS_GEMM_AUTO = 0,
   W2VS_GEMM_SIMT = 1,          /* fp32-accurate CUDA-core kernel */
   W2VS_GEMM_TCGEN05 = 2,       /* tcgen05, one CTA per tile */
-  W2VS_GEMM_TCGEN05_2CTA = 3   /* tcgen05 cta_group::2 CTA pairs, TMA-store epilogue (default for bf16) */
+  W2VS_GEMM_TCGEN05_2CTA = 3,  /* tcgen05 cta_group::2 CTA pairs, TMA-store epilogue (default for bf16) */
+  W2VS_GEMM_SKINNY = 4         /* M <= 64: weight-streaming mma.sync kernel (default for incremental steps) */
 } w2vs_gemm_impl_t;
 #define W2VS_EPI_GELU 1
 /* C[M,N] = A[M,K] . W[N,K]^T + bias (+GELU) (+residual fp32, may alias C when C is fp32).

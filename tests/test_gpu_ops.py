@@ -42,6 +42,26 @@ def test_gemm_bf16(impl, M, N, K):
         assert rel(y, ref) < tol, (impl, M, N, K, gelu, use_res)
 
 
+@pytest.mark.parametrize("M", [1, 7, 16, 24, 33, 48, 64])
+@pytest.mark.parametrize("N,K", [(1024, 1024), (3072, 1024), (4096, 1024), (1024, 4096), (1024, 512), (512, 256)])
+def test_gemm_skinny_bf16(M, N, K):
+    """Weight-streaming kernel of the incremental steps (M <= 64) against the fp32 restatement and against
+    what AUTO picks for these shapes (it must be this kernel)."""
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(DEV, torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) * 0.05).to(DEV, torch.bfloat16)
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(M, N, generator=g).to(DEV)
+    for gelu, use_res, odt in [(False, False, torch.bfloat16), (True, False, torch.bfloat16), (False, True, torch.float32),
+                               (False, False, torch.float32)]:
+        y = ops.gemm(A, W, bias, res if use_res else None, out_dtype=odt, gelu=gelu, impl=cabi.GEMM_SKINNY)
+        ref = _gemm_ref(A, W, bias, res if use_res else None, gelu)
+        tol = 1e-2 if odt == torch.bfloat16 else 2e-5 * max(1, K // 512) + 1e-5
+        assert rel(y, ref) < tol, (M, N, K, gelu, use_res)
+        y2 = ops.gemm(A, W, bias, res if use_res else None, out_dtype=odt, gelu=gelu, impl=cabi.GEMM_AUTO)
+        assert torch.equal(y, y2)
+
+
 @pytest.mark.parametrize("impl", [cabi.GEMM_TCGEN05_2CTA, cabi.GEMM_TCGEN05, cabi.GEMM_SIMT])
 @pytest.mark.parametrize("rows,C,k,s", [(1000, 512, 3, 2), (777, 512, 2, 2), (300, 64, 3, 2), (129, 64, 2, 2)])
 def test_gemm_strided_conv_view(impl, rows, C, k, s):

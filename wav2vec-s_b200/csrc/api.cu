@@ -405,7 +405,9 @@ namespace w2vs {
 w2vs_status_t launch_gemm(int impl, const GemmArgs& g, cudaStream_t st) {
   W2VS_REQUIRE(g.dtype_ab == W2VS_F32 || g.dtype_ab == W2VS_BF16, "GEMM operand dtype");
   W2VS_REQUIRE(g.dtype_c == W2VS_F32 || g.dtype_c == W2VS_BF16, "GEMM output dtype");
-  if (impl == W2VS_GEMM_AUTO) impl = g.dtype_ab == W2VS_BF16 ? W2VS_GEMM_TCGEN05_2CTA : W2VS_GEMM_SIMT;
+  if (impl == W2VS_GEMM_AUTO)
+    impl = g.dtype_ab != W2VS_BF16 ? W2VS_GEMM_SIMT : gemm_skinny_applicable(g) ? W2VS_GEMM_SKINNY : W2VS_GEMM_TCGEN05_2CTA;
+  if (impl == W2VS_GEMM_SKINNY) return launch_gemm_skinny(g, st);
   if (impl == W2VS_GEMM_TCGEN05) return launch_gemm_tc(g, st);
   if (impl == W2VS_GEMM_TCGEN05_2CTA) {
     // the pair kernel adds the residual in place; anything else goes through the 1-CTA kernel

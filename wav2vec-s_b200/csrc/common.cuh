@@ -44,6 +44,28 @@ void prof_mark(const char* what, cudaStream_t st);
     }                                                                   \
   } while (0)
 
+// ---- programmatic dependent launch (incremental steps are a chain of ~200 tiny kernels) -------------------------
+// Kernels that start with pdl_prologue() may be launched with launch_pdl(): the grid is set up while its
+// predecessor still runs, and griddepcontrol.wait holds it until the predecessor has completed and flushed its
+// writes -- ordering and results are those of a plain stream launch, the launch latency is hidden.  Both
+// instructions are no-ops for a normal launch.
+extern thread_local bool g_pdl_on;     // set by the incremental driver (stream.cu)
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() { pdl_launch_dependents(); pdl_wait(); }
+template <typename... KArgs, typename... Args>
+static inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_pdl_on ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -70,6 +70,7 @@ attn_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ keypad
   __shared__ __align__(128) bf16 Ks[2][TILE_ELEMS];
   __shared__ __align__(128) bf16 Vs[2][TILE_ELEMS];
   __shared__ int s_kinfo[2][KT];
+  pdl_prologue();
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
@@ -251,8 +252,8 @@ w2vs_status_t launch_attention_mma(const AttnArgs& a, cudaStream_t st) {
   if (a.n_step_q > 0) {
     const int nt = (a.n_step_q + QT - 1) / QT;
     dim3 grid((unsigned)nt, (unsigned)a.heads, (unsigned)a.B);
-    attn_mma_kernel<<<grid, 128, 0, st>>>((const bf16*)a.qkv, nullptr, (bf16*)a.ctx, a.n_step_keys, a.n_step_q, 1, 0,
-                                          a.D, nt, nt, scale_log2, (const bf16*)a.kv_cache, a.kv_rows);
+    launch_pdl(attn_mma_kernel, grid, dim3(128), 0, st, (const bf16*)a.qkv, (const uint8_t*)nullptr, (bf16*)a.ctx,
+               a.n_step_keys, a.n_step_q, 1, 0, a.D, nt, nt, scale_log2, (const bf16*)a.kv_cache, a.kv_rows);
     W2VS_CHECK_LAUNCH("attn_mma_kernel");
     return W2VS_OK;
   }

@@ -323,9 +323,13 @@ w2vs_status_t launch_bn(const GemmArgs& g, cudaStream_t st) {
 
 template <typename TC>
 w2vs_status_t launch_typed(const GemmArgs& g, cudaStream_t st) {
-  if (g.N % 256 == 0) return launch_bn<256, TC>(g, st);
-  if (g.N % 128 == 0) return launch_bn<128, TC>(g, st);
-  if (g.N % 64 == 0 && g.N < 256) return launch_bn<64, TC>(g, st);
+  // Widest tile that still gives every SM pair a tile: with a few hundred rows (incremental steps of a batch of
+  // streams) 256-wide tiles would leave most of the GPU idle while a handful of clusters stream all of W.
+  const int64_t m_tiles = ceil_div64(g.M, 2 * BM);
+  const int clusters = num_sms() / 2;
+  if (g.N % 256 == 0 && (m_tiles * (g.N / 256) >= clusters || g.N % 128 != 0)) return launch_bn<256, TC>(g, st);
+  if (g.N % 128 == 0 && (m_tiles * (g.N / 128) >= clusters || g.N % 64 != 0)) return launch_bn<128, TC>(g, st);
+  if (g.N % 64 == 0) return launch_bn<64, TC>(g, st);
   return launch_bn<256, TC>(g, st);
 }
 

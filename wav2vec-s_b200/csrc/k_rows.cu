@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(256)
 layernorm_rows_kernel(const TIn* x, int64_t ldx, const float* __restrict__ gamma,
                       const float* __restrict__ beta, float* out_f32, TAct* out_act, int64_t ldo,
                       int rows, int N, int gelu) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -85,8 +86,8 @@ static w2vs_status_t ln_dispatch(const LayerNormArgs& a, cudaStream_t st) {
   const int wpb = 8;
   dim3 grid((unsigned)ceil_div64(a.rows, wpb));
 #define W2VS_LN_CASE(NCH)                                                                      \
-  layernorm_rows_kernel<TIn, TAct, NCH><<<grid, wpb * 32, 0, st>>>(                            \
-      (const TIn*)a.x, a.ldx, a.gamma, a.beta, a.out_f32, (TAct*)a.out_act, a.ldo, a.rows, a.N, a.gelu)
+  launch_pdl(layernorm_rows_kernel<TIn, TAct, NCH>, grid, dim3(wpb * 32), 0, st,                \
+             (const TIn*)a.x, a.ldx, a.gamma, a.beta, a.out_f32, (TAct*)a.out_act, a.ldo, a.rows, a.N, a.gelu)
   if (a.N <= 256) W2VS_LN_CASE(1);
   else if (a.N <= 512) W2VS_LN_CASE(2);
   else if (a.N <= 1024) W2VS_LN_CASE(4);
@@ -103,6 +104,7 @@ template <typename TAct, int NV>
 __global__ void __launch_bounds__(256)
 layernorm_f32_kernel(const float* x, int64_t ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
                      float* out_f32, TAct* out_act, int64_t ldo, int rows, int gelu) {
+  pdl_prologue();
   constexpr int N = NV * 128;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -154,8 +156,8 @@ static w2vs_status_t ln_f32_dispatch(const LayerNormArgs& a, cudaStream_t st) {
   const int wpb = 8;
   dim3 grid((unsigned)ceil_div64(a.rows, wpb));
 #define W2VS_LNF_CASE(NV)                                                                          \
-  layernorm_f32_kernel<TAct, NV><<<grid, wpb * 32, 0, st>>>((const float*)a.x, a.ldx, a.gamma, a.beta, a.out_f32, \
-                                                            (TAct*)a.out_act, a.ldo, a.rows, a.gelu)
+  launch_pdl(layernorm_f32_kernel<TAct, NV>, grid, dim3(wpb * 32), 0, st, (const float*)a.x, a.ldx, a.gamma, a.beta, \
+             a.out_f32, (TAct*)a.out_act, a.ldo, a.rows, a.gelu)
   switch (a.N / 128) {
     case 1: W2VS_LNF_CASE(1); break;
     case 2: W2VS_LNF_CASE(2); break;

@@ -39,6 +39,7 @@ __global__ void concat_wav_kernel(float* __restrict__ dst, int64_t dst_bs, const
 // cache[b][row0 + j][0:2D) = qkv[b*n_tok + j][D:3D)   (K | V of this step's tokens)
 __global__ void kv_append_kernel(const uint4* __restrict__ qkv, uint4* __restrict__ cache, int64_t cache_bs_vecs,
                                  int row0, int n_tok, int d_vecs /* D*sizeof/16 */, int B) {
+  pdl_prologue();
   const int64_t per_b = (int64_t)n_tok * 2 * d_vecs;
   const int64_t total = per_b * B;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -88,8 +89,8 @@ w2vs_status_t launch_kv_append(const void* qkv, void* cache, int64_t cache_rows,
   const int d_vecs = D * elem_bytes / 16;
   const int64_t total = (int64_t)n_tok * 2 * d_vecs * B;
   if (total <= 0) return W2VS_OK;
-  kv_append_kernel<<<grid_for(total), 256, 0, st>>>((const uint4*)qkv, (uint4*)cache, cache_rows * 2 * d_vecs, row0,
-                                                    n_tok, d_vecs, B);
+  launch_pdl(kv_append_kernel, dim3(grid_for(total)), dim3(256), 0, st, (const uint4*)qkv, (uint4*)cache,
+             cache_rows * 2 * d_vecs, row0, n_tok, d_vecs, B);
   W2VS_CHECK_LAUNCH("kv_append_kernel");
   return W2VS_OK;
 }

@@ -21,6 +21,7 @@ void set_error(const char* fmt, ...) {
 
 // ---- per-launch device timing ---------------------------------------------------------------------
 thread_local bool g_prof_on = false;
+thread_local bool g_pdl_on = false;
 namespace {
 struct ProfState {
   std::vector<cudaEvent_t> pool;

@@ -246,6 +246,9 @@ w2vs_status_t w2vs_stream_step(const w2vs_config* cfg, const void* d_packed, voi
                                size_t ws_bytes, void* stream) {
   W2VS_TRY(check_supported(cfg));
   W2VS_REQUIRE(d_packed && host_state && d_state && d_ws && n_out, "NULL pointer");
+  // a decision step is a chain of ~200 short kernels: launch the PDL-aware ones (common.cuh) as programmatic
+  // dependents so that their launch latency hides under their predecessors
+  struct PdlScope { PdlScope() { g_pdl_on = true; } ~PdlScope() { g_pdl_on = false; } } pdl_scope;
   StreamHost* hs = reinterpret_cast<StreamHost*>(host_state);
   W2VS_REQUIRE(hs->magic == kMagic, "host_state was not initialised by w2vs_stream_init");
   W2VS_REQUIRE(!hs->finished, "stream already finished");
