@@ -460,9 +460,18 @@ def main():
         if prof is not None and prof.get("gemm", {}).get("count"):
             gm = prof["gemm"]
             ach = fl["gemm"] * B / (gm["ms"] / 1e3) / 1e12
+            traffic, traffic_note = None, None
+            tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic_cfg3.json")
+            if a.workload == "large_64x20s" and os.path.isfile(tpath):
+                tj = json.load(open(tpath))
+                traffic = tj["bytes_per_step_covered"]
+                traffic_note = (f"DRAM bytes of the {tj['launches_covered']} transformer GEMM launches of a step (of "
+                                f"{tj['launches_per_step']}; conv/proj launches not captured), {tj['source']}; algorithmic "
+                                f"bytes of the same launches: {24 * sum(tj['algorithmic_bytes'].values())}")
             line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc2_kernel (all launches of one step)",
                                 "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                                "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
+                                "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic,
+                                "traffic_note": traffic_note,
                                 "peak_source": pk_kind + " (sustained: timed inside a long step)",
                                 "launches_per_step": gm["count"], "ms_per_step": gm["ms"]}
             line["kernel_ms_per_step"] = {k: round(v["ms"], 3) for k, v in prof.items() if "[" not in k and "_kernel" not in k}
