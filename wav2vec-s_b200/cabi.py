@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libw2vs.so")
+# W2VS_LIBRARY selects another build of the same ABI (A/B timing of kernel variants on one GPU box)
+LIB_PATH = os.environ.get("W2VS_LIBRARY") or os.path.join(HERE, "lib", "libw2vs.so")
 
 W2VS_MAX_CONV = 8
 W2VS_ABI_VERSION = 1
