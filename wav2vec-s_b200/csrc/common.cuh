@@ -209,6 +209,20 @@ __device__ __forceinline__ void gelu_tanh2(float& x0, float& x1) {
   const uint64_t hx = fmul2(x, pack2(0.5f, 0.5f));
   unpack2(ffma2(t, hx, hx), x0, x1);
 }
+// packed form: two values in, two values out (no unpacking around the polynomial)
+__device__ __forceinline__ uint64_t gelu_tanh2p(uint64_t x) {
+  float q0, q1;
+  unpack2(fmul2(x, x), q0, q1);
+  const uint64_t x2 = pack2(fminf(q0, 64.f), fminf(q1, 64.f));
+  uint64_t p = ffma2(pack2(-0.00035151765342717335f, -0.00035151765342717335f), x2,
+                     pack2(0.037005651782227346f, 0.037005651782227346f));
+  p = ffma2(p, x2, pack2(0.7975078774034253f, 0.7975078774034253f));
+  float g0, g1;
+  unpack2(fmul2(p, x), g0, g1);
+  const uint64_t t = pack2(tanh_approx(g0), tanh_approx(g1));
+  const uint64_t hx = fmul2(x, pack2(0.5f, 0.5f));
+  return ffma2(t, hx, hx);
+}
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float x2 = fminf(x * x, 64.f);
   float p = fmaf(-0.00035151765342717335f, x2, 0.037005651782227346f);

@@ -71,26 +71,28 @@ conv0_kernel(const TIn* __restrict__ wav, int64_t wav_ld, const float* __restric
   const int nwarps = blockDim.x >> 5;
 
   for (int f0 = FPI * warp; f0 < n_frames; f0 += FPI * nwarps) {
-    float acc[FPI][NI][2];
+    // accumulators as packed f32x2 pairs (channels 2*lane, 2*lane+1 of each 64-channel group): one FFMA2 per tap
+    // and pair instead of two FFMAs, and the LayerNorm / GELU arithmetic below stays packed as well
+    uint64_t acc[FPI][NI];
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
-      const float2 bb = *reinterpret_cast<const float2*>(s_bias + 64 * i + 2 * lane);
+      const uint64_t bb = *reinterpret_cast<const uint64_t*>(s_bias + 64 * i + 2 * lane);
 #pragma unroll
-      for (int f = 0; f < FPI; ++f) { acc[f][i][0] = bb.x; acc[f][i][1] = bb.y; }
+      for (int f = 0; f < FPI; ++f) acc[f][i] = bb;
     }
 #pragma unroll
     for (int j = 0; j < KW; ++j) {
-      float xv[FPI];
+      uint64_t xv[FPI];
 #pragma unroll
-      for (int f = 0; f < FPI; ++f) xv[f] = (f0 + f) < n_frames ? s_x[(f0 + f) * stride + j] : 0.f;   // broadcast
+      for (int f = 0; f < FPI; ++f) {
+        const float xs = (f0 + f) < n_frames ? s_x[(f0 + f) * stride + j] : 0.f;   // broadcast
+        xv[f] = pack2(xs, xs);
+      }
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
-        const float2 ww = *reinterpret_cast<const float2*>(s_w + j * C + 64 * i + 2 * lane);
+        const uint64_t ww = *reinterpret_cast<const uint64_t*>(s_w + j * C + 64 * i + 2 * lane);
 #pragma unroll
-        for (int f = 0; f < FPI; ++f) {
-          acc[f][i][0] = fmaf(ww.x, xv[f], acc[f][i][0]);
-          acc[f][i][1] = fmaf(ww.y, xv[f], acc[f][i][1]);
-        }
+        for (int f = 0; f < FPI; ++f) acc[f][i] = ffma2(ww, xv[f], acc[f][i]);
       }
     }
 #pragma unroll
@@ -98,49 +100,48 @@ conv0_kernel(const TIn* __restrict__ wav, int64_t wav_ld, const float* __restric
       if (f0 + f >= n_frames) break;
       if (MODE == C0_GN_STATS) {
 #pragma unroll
-        for (int i = 0; i < NI; ++i)
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            st_sum[i][h] += acc[f][i][h];
-            st_sq[i][h] = fmaf(acc[f][i][h], acc[f][i][h], st_sq[i][h]);
-          }
+        for (int i = 0; i < NI; ++i) {
+          float a0, a1;
+          unpack2(acc[f][i], a0, a1);
+          st_sum[i][0] += a0; st_sum[i][1] += a1;
+          st_sq[i][0] = fmaf(a0, a0, st_sq[i][0]);
+          st_sq[i][1] = fmaf(a1, a1, st_sq[i][1]);
+        }
         continue;
       }
-      float mean = 0.f, rstd = 1.f;
+      uint64_t rs2 = pack2(1.f, 1.f);
       if (MODE == C0_LN) {
-        float sm = 0.f;
+        uint64_t s2 = pack2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < NI; ++i) sm += acc[f][i][0] + acc[f][i][1];
-        mean = warp_sum(sm) * (1.0f / C);
-        float q = 0.f;
+        for (int i = 0; i < NI; ++i) s2 = fadd2(s2, acc[f][i]);
+        float sa, sb;
+        unpack2(s2, sa, sb);
+        const float mean = warp_sum(sa + sb) * (1.0f / C);
+        const uint64_t nm2 = pack2(-mean, -mean);
+        uint64_t q2 = pack2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < NI; ++i) {
-          const float d0 = acc[f][i][0] - mean, d1 = acc[f][i][1] - mean;
-          q = fmaf(d0, d0, q);
-          q = fmaf(d1, d1, q);
-        }
-        rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / C) + 1e-5f);
+        for (int i = 0; i < NI; ++i) { acc[f][i] = fadd2(acc[f][i], nm2); q2 = ffma2(acc[f][i], acc[f][i], q2); }
+        unpack2(q2, sa, sb);
+        const float rstd = 1.0f / sqrtf(warp_sum(sa + sb) * (1.0f / C) + 1e-5f);
+        rs2 = pack2(rstd, rstd);
       }
       TOut* o = out + ((size_t)b * rows_per_utt + (t_begin + f0 + f)) * C;
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
         const int c = 2 * lane + 64 * i;
-        float v0 = acc[f][i][0], v1 = acc[f][i][1];
+        uint64_t v = acc[f][i];
         if (MODE == C0_LN || MODE == C0_GN_APPLY) {
-          const float2 sc = *reinterpret_cast<const float2*>(s_scale + c);
-          const float2 sh = *reinterpret_cast<const float2*>(s_shift + c);
-          if (MODE == C0_LN) {
-            v0 = (v0 - mean) * rstd * sc.x + sh.x;
-            v1 = (v1 - mean) * rstd * sc.y + sh.y;
-          } else {
-            v0 = fmaf(v0, sc.x, sh.x);
-            v1 = fmaf(v1, sc.y, sh.y);
-          }
+          const uint64_t sc = *reinterpret_cast<const uint64_t*>(s_scale + c);
+          const uint64_t sh = *reinterpret_cast<const uint64_t*>(s_shift + c);
+          v = ffma2(v, MODE == C0_LN ? fmul2(rs2, sc) : sc, sh);     // LN: v is already centred
         }
-        gelu2<TOut>(v0, v1);
+        float v0, v1;
         if (sizeof(TOut) == 2) {
+          unpack2(gelu_tanh2p(v), v0, v1);
           *reinterpret_cast<uint32_t*>(o + c) = pack_bf16x2(v0, v1);
         } else {
+          unpack2(v, v0, v1);
+          gelu_erf2(v0, v1);
           *reinterpret_cast<float2*>(o + c) = make_float2(v0, v1);
         }
       }

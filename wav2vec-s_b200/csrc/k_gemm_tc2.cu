@@ -59,7 +59,10 @@ template <int BN, typename TC> struct Cfg2 {
   static constexpr int kStagingBytes = N_EPI_WARPS * 2 * kSlotBytes;
   static constexpr int kMiscBytes = N_EPI_WARPS * (BN / 2) * 4 /*bias*/ + 512 /*barriers*/ + 1024 /*align*/;
   static constexpr int kStagesFit = (SMEM_LIMIT - kStagingBytes - kMiscBytes) / kStageBytes;
-  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+#ifndef W2VS_GEMM_MAX_STAGES
+#define W2VS_GEMM_MAX_STAGES 8
+#endif
+  static constexpr int kStages = kStagesFit > W2VS_GEMM_MAX_STAGES ? W2VS_GEMM_MAX_STAGES : kStagesFit;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kMiscBytes;
   static constexpr int kChunksPerWarp = BN / 2 / CHUNK;

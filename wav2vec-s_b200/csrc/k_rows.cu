@@ -81,6 +81,60 @@ layernorm_rows_kernel(const TIn* x, int64_t ldx, const float* __restrict__ gamma
   }
 }
 
+// bf16 -> LayerNorm -> GELU -> bf16 (the conv blocks' Fp32LayerNorm + GELU, in place over the GEMM output): same
+// arithmetic as the generic kernel (fp32, mean first, then centred squares) on packed f32x2 pairs -- 8.5 issued
+// instructions per element instead of 14; the generic kernel was issue bound at 79 % on these passes (ncu).
+template <int NCH>
+__global__ void __launch_bounds__(256)
+ln_gelu_bf16_kernel(const bf16* x, int64_t ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    bf16* out, int64_t ldo, int rows) {
+  pdl_prologue();
+  constexpr int N = NCH * 256;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  uint64_t p[NCH][4];
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    const uint4 u = *reinterpret_cast<const uint4*>(x + (size_t)row * ldx + (lane + 32 * j) * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) p[j][e] = pack2(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));
+  }
+  uint64_t s2 = pack2(0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < NCH; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s2 = fadd2(s2, p[j][e]);
+  float sa, sb;
+  unpack2(s2, sa, sb);
+  const float mean = warp_sum(sa + sb) * (1.0f / N);
+  const uint64_t nm2 = pack2(-mean, -mean);
+  uint64_t q2 = pack2(0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < NCH; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { p[j][e] = fadd2(p[j][e], nm2); q2 = ffma2(p[j][e], p[j][e], q2); }
+  unpack2(q2, sa, sb);
+  const float rstd = 1.0f / sqrtf(warp_sum(sa + sb) * (1.0f / N) + 1e-5f);
+  const uint64_t rs2 = pack2(rstd, rstd);
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    const int c0 = (lane + 32 * j) * 8;
+    const ulonglong2 g01 = *reinterpret_cast<const ulonglong2*>(gamma + c0), g23 = *reinterpret_cast<const ulonglong2*>(gamma + c0 + 4);
+    const ulonglong2 b01 = *reinterpret_cast<const ulonglong2*>(beta + c0), b23 = *reinterpret_cast<const ulonglong2*>(beta + c0 + 4);
+    const uint64_t g[4] = {g01.x, g01.y, g23.x, g23.y}, bt[4] = {b01.x, b01.y, b23.x, b23.y};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float y0, y1;
+      unpack2(gelu_tanh2p(ffma2(p[j][e], fmul2(rs2, g[e]), bt[e])), y0, y1);
+      o[e] = pack_bf16x2(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(out + (size_t)row * ldo + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 template <typename TIn, typename TAct>
 static w2vs_status_t ln_dispatch(const LayerNormArgs& a, cudaStream_t st) {
   const int wpb = 8;
@@ -180,6 +234,17 @@ w2vs_status_t launch_layernorm(const LayerNormArgs& a, cudaStream_t st) {
     if (a.N % 128 == 0 && (nv == 1 || nv == 2 || nv == 4 || nv == 6 || nv == 8))
       return a.act_dtype == W2VS_F32 ? ln_f32_dispatch<float>(a, st) : ln_f32_dispatch<bf16>(a, st);
     return a.act_dtype == W2VS_F32 ? ln_dispatch<float, float>(a, st) : ln_dispatch<float, bf16>(a, st);
+  }
+  if (a.act_dtype == W2VS_BF16 && a.gelu && a.out_f32 == nullptr && a.out_act != nullptr && a.N % 256 == 0 && a.N <= 1024 &&
+      a.N != 768) {
+    const dim3 grid((unsigned)ceil_div64(a.rows, 8));
+    switch (a.N / 256) {
+      case 1: launch_pdl(ln_gelu_bf16_kernel<1>, grid, dim3(256), 0, st, (const bf16*)a.x, a.ldx, a.gamma, a.beta, (bf16*)a.out_act, a.ldo, a.rows); break;
+      case 2: launch_pdl(ln_gelu_bf16_kernel<2>, grid, dim3(256), 0, st, (const bf16*)a.x, a.ldx, a.gamma, a.beta, (bf16*)a.out_act, a.ldo, a.rows); break;
+      default: launch_pdl(ln_gelu_bf16_kernel<4>, grid, dim3(256), 0, st, (const bf16*)a.x, a.ldx, a.gamma, a.beta, (bf16*)a.out_act, a.ldo, a.rows); break;
+    }
+    W2VS_CHECK_LAUNCH("layernorm_rows_kernel");
+    return W2VS_OK;
   }
   return a.act_dtype == W2VS_F32 ? ln_dispatch<bf16, float>(a, st) : ln_dispatch<bf16, bf16>(a, st);
 }
