@@ -39,7 +39,10 @@ typedef enum {
   W2VS_CUDA_ERROR = 4          /* a launch or driver call failed */
 } w2vs_status_t;
 
-typedef enum { W2VS_F32 = 0, W2VS_BF16 = 1 } w2vs_dtype_t;
+typedef enum { W2VS_F32 = 0, W2VS_BF16 = 1,
+               W2VS_I16 = 2   /* waveform samples only: 16-bit PCM, read as x / 32768 (what the SimulEval agent does on
+                                 the host, rain/simul/transducer_searcher.py:74-80) */
+} w2vs_dtype_t;
 typedef enum { W2VS_EXTRACTOR_DEFAULT = 0, W2VS_EXTRACTOR_LAYER_NORM = 1 } w2vs_extractor_mode_t;
 typedef enum { W2VS_POS_SIN = 0, W2VS_POS_CONV = 1 } w2vs_pos_type_t;
 typedef enum { W2VS_LAYOUT_BTD = 0, W2VS_LAYOUT_TBD = 1 } w2vs_layout_t;
@@ -124,6 +127,13 @@ typedef struct {
   float* d_tap_post_proj;       /* [B, T, D] after LayerNorm + post_extract_proj */
   float* d_tap_enc_in;          /* [B, M, D] tokens entering layer 0 (incl. rc copies) */
   float* d_tap_layers;          /* [layers, B, M, D] residual stream after each layer */
+  /* Waveform front end folded into the first conv layer's load: with
+   * wav_normalize != 0 every utterance is standardised over its own valid samples, (x - mean) / sqrt(var + 1e-5)
+   * with the biased variance, which is `F.layer_norm(feats, feats.shape)` of the reference data pipeline
+   * (fairseq/data/audio/raw_audio_dataset.py:60-72, `normalize: true`); samples past d_lengths[b] are left as
+   * they are (the collater pads with zeros after normalising).  Not combinable with d_sample_pad_mask. */
+  int32_t wav_normalize;
+  int32_t reserved[3];
 } w2vs_encode_args;
 
 w2vs_status_t w2vs_get_workspace_size(const w2vs_config* cfg, int32_t B, int32_t L,

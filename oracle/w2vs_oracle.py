@@ -364,6 +364,22 @@ def _samples_for_frames(cfg, frames: int) -> int:
     return n
 
 
+def waveform_frontend(samples: Tensor, normalize: bool, lengths: Optional[Tensor] = None) -> Tensor:
+    """The two host-side steps in front of the encoder: 16-bit PCM -> float as the
+    SimulEval agent does (rain/simul/transducer_searcher.py:74-80: ``output / 32768.0`` then float32), and the data
+    pipeline's per-utterance normalisation (fairseq/data/audio/raw_audio_dataset.py:60-72:
+    ``F.layer_norm(feats, feats.shape)`` on each utterance BEFORE the collater pads it with zeros).
+    samples [B, L] int16 or float; lengths [B] valid samples or None.  Returns float32 [B, L]."""
+    x = (samples.double() / 32768.0).float() if samples.dtype == torch.int16 else samples.float()
+    if not normalize:
+        return x
+    out = x.clone()
+    for b in range(x.size(0)):
+        n = x.size(1) if lengths is None else int(lengths[b])
+        out[b, :n] = F.layer_norm(x[b, :n], (n,))
+    return out
+
+
 def max_abs_rel(y: Tensor, ref: Tensor) -> float:
     """Parity metric of SURVEY.md section 8(d): max|y - ref| / max|ref|."""
     return float((y.float() - ref.float()).abs().max() / ref.float().abs().max().clamp_min(1e-30))

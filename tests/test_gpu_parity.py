@@ -142,6 +142,36 @@ def test_rain_forward_vs_reference_golden(name, dtype):
         assert torch.equal(out2["encoder_padding_mask"][0], fm)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("ragged", [False, True])
+def test_waveform_front_end_pcm16_and_normalisation(dtype, ragged):
+    """16-bit PCM in, per-utterance normalisation inside the first conv layer's load:
+    against the oracle's restatement of the two host-side steps followed by the encoder."""
+    from oracle import synth
+    cfg = cases.tiny(layer_norm_first=True, conv_bias=True)
+    sd = synth.make_state_dict(cfg, 21)
+    g = torch.Generator().manual_seed(8)
+    B, L = 3, 11000
+    pcm = (torch.randn(B, L, generator=g) * 3000 + 500).clamp(-32768, 32767).to(torch.int16)   # DC offset, small gain
+    lens, pm = None, None
+    if ragged:
+        lens = synth.make_lengths(B, L, 3)
+        pm = O.lengths_to_padding_mask(lens)
+        pcm = pcm.masked_fill(pm, 0)
+    m = build(W.Wav2VecSModel, cfg, sd, dtype)
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    for normalize in (False, True):
+        m.normalize_waveform = normalize
+        y, fm = m.extract_features(pcm.cuda(), None if pm is None else pm.cuda())
+        x = O.waveform_frontend(pcm, normalize, lens)
+        yo, fmo = O.extract_features(sd, cfg, x, pm)
+        if fmo is not None:
+            assert torch.equal(fm.cpu(), fmo)
+        assert valid_rel_err(y.cpu(), yo, None if fmo is None else fmo.numpy()) < tol, normalize
+    # incremental mode takes PCM chunks as well (no normalisation there)
+    m.normalize_waveform = False
+
+
 def test_sample_mask_and_lengths_agree_with_arbitrary_mask():
     """A sample mask that is not a pure length mask (holes) still follows view(B,T,-1).all(-1)."""
     cfg = cases.tiny()

@@ -107,3 +107,24 @@ def test_stream_unsupported_modes_fail_loudly():
     with pytest.raises(W.cabi.W2vsError) as e:
         m.open_stream(B=1, max_seconds=1.0)
     assert e.value.status == W.cabi.UNSUPPORTED
+
+
+def test_stream_takes_pcm16_chunks():
+    """16-bit PCM chunks (what an audio source delivers; the reference agent divides by 32768 on the host,
+    rain/simul/transducer_searcher.py:74-80) give the same frames as the float waveform."""
+    name = STREAM[0]
+    cfg, sd, wav, _, _ = case_inputs(name)
+    m = build(cfg, sd, torch.float32)
+    pcm = (wav * 3000).clamp(-32768, 32767).to(torch.int16)
+    x = O.waveform_frontend(pcm, False)
+    ref, _ = O.rain_forward(sd, cfg, x, None, finished=True, is_infer=True)
+    st = m.open_stream(B=1, max_seconds=4.0, max_new_samples=9000)
+    outs, pos, L = [], 0, pcm.size(1)
+    src = pcm.cuda()
+    while pos < L:
+        n = min(5120 if pos else 7760, L - pos)
+        outs.append(st.step(src[:, pos:pos + n], EncoderStream.FINAL if pos + n >= L else EncoderStream.NONE))
+        pos += n
+    y = torch.cat(outs, 0).cpu()
+    assert tuple(y.shape) == tuple(ref.shape)
+    assert valid_rel_err(y, ref) < TOL[torch.float32]

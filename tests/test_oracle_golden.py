@@ -77,3 +77,20 @@ def test_frame_padding_formula():
     fm = O.frame_padding_mask(O.lengths_to_padding_mask(lens), T)
     w = L // T
     assert (~fm).sum(1).tolist() == [min(T, -(-int(l) // w)) for l in lens]
+
+
+def test_waveform_frontend_restatement():
+    """oracle.waveform_frontend against the two reference statements it restates, evaluated directly."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(1)
+    pcm = (torch.randn(2, 5000, generator=g) * 2000).to(torch.int16)
+    x = O.waveform_frontend(pcm, False)
+    assert x.dtype == torch.float32
+    assert torch.equal(x, torch.from_numpy((pcm.numpy() / 32768.0).astype("float32")))      # transducer_searcher.py:76-78
+    lens = torch.tensor([5000, 3210])
+    y = O.waveform_frontend(pcm, True, lens)
+    for b in range(2):
+        n = int(lens[b])
+        ref = F.layer_norm(x[b, :n], x[b, :n].shape)                                       # raw_audio_dataset.py:69-72
+        assert torch.equal(y[b, :n], ref)
+        assert torch.equal(y[b, n:], x[b, n:])

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("W2VS_LIBRARY") or os.path.join(HERE, "lib", "libw2vs.
 W2VS_MAX_CONV = 8
 W2VS_ABI_VERSION = 1
 OK, INVALID_VALUE, UNSUPPORTED, WORKSPACE_TOO_SMALL, CUDA_ERROR = range(5)
-F32, BF16 = 0, 1
+F32, BF16, I16 = 0, 1, 2
 EXTRACTOR_DEFAULT, EXTRACTOR_LAYER_NORM = 0, 1
 POS_SIN, POS_CONV = 0, 1
 LAYOUT_BTD, LAYOUT_TBD = 0, 1
@@ -54,6 +54,7 @@ class EncodeArgs(C.Structure):
         ("drop_tail_frames", C.c_int32), ("d_out", C.c_void_p), ("d_out_pad_mask", C.c_void_p),
         ("d_tap_conv_out", C.c_void_p), ("d_tap_post_proj", C.c_void_p),
         ("d_tap_enc_in", C.c_void_p), ("d_tap_layers", C.c_void_p),
+        ("wav_normalize", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 

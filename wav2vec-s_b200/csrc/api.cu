@@ -177,8 +177,9 @@ w2vs_status_t w2vs_encode(const w2vs_config* cfg, const void* d_packed, const w2
   W2VS_REQUIRE(a != nullptr && d_packed != nullptr && d_ws != nullptr, "NULL pointer");
   W2VS_REQUIRE(a->d_wav != nullptr && a->d_out != nullptr, "NULL wav / out");
   W2VS_REQUIRE(a->B >= 1 && a->L >= 1, "B / L");
-  W2VS_REQUIRE(a->wav_dtype == W2VS_F32 || a->wav_dtype == W2VS_BF16, "wav_dtype");
+  W2VS_REQUIRE(a->wav_dtype == W2VS_F32 || a->wav_dtype == W2VS_BF16 || a->wav_dtype == W2VS_I16, "wav_dtype");
   W2VS_REQUIRE(!(a->d_lengths && a->d_sample_pad_mask), "give d_lengths or d_sample_pad_mask, not both");
+  W2VS_REQUIRE(!(a->wav_normalize && a->d_sample_pad_mask), "wav_normalize needs d_lengths (or no padding), not a sample mask");
   W2VS_REQUIRE(a->out_layout == W2VS_LAYOUT_BTD || a->out_layout == W2VS_LAYOUT_TBD, "out_layout");
   Geometry g;
   W2VS_TRY(make_geometry(cfg, a->L, a->main_ctx, a->right_ctx, &g));
@@ -213,6 +214,11 @@ w2vs_status_t w2vs_encode(const w2vs_config* cfg, const void* d_packed, const w2
     c.norm = !conv_has_norm(cfg, 0) ? CONV0_NORM_NONE
              : (cfg->extractor_mode == W2VS_EXTRACTOR_LAYER_NORM ? CONV0_NORM_LAYER : CONV0_NORM_GROUP);
     c.gn_stats = at<float>(d_ws, ws.gn_stats);
+    if (a->wav_normalize) {
+      float* wst = at<float>(d_ws, ws.wav_stats);
+      W2VS_TRY(launch_wav_stats(a->d_wav, a->wav_dtype, a->L, a->d_lengths, a->L, B, wst, st));
+      c.wav_stats = wst; c.wav_lengths = a->d_lengths;
+    }
     W2VS_TRY(launch_conv0(c, st));
   }
   for (int i = 1; i < n; ++i) {

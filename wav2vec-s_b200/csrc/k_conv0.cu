@@ -14,6 +14,7 @@
 //         GN_STATS  per-CTA partial sum / sum of squares per (utterance, channel); a small finalize
 //                   kernel reduces them in a fixed order (fp64) -> bit-reproducible scale / shift
 //         GN_APPLY  y = gelu(GroupNorm(conv + bias)), groups == channels   (extractor_mode = default)
+#include <limits.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -29,7 +30,8 @@ __global__ void __launch_bounds__(256, 2)
 conv0_kernel(const TIn* __restrict__ wav, int64_t wav_ld, const float* __restrict__ w,
              const float* __restrict__ bias, const float* __restrict__ gamma,
              const float* __restrict__ beta, TOut* __restrict__ out, int rows_per_utt, int T0,
-             int stride, float* __restrict__ gn_stats, int frames_per_cta) {
+             int stride, float* __restrict__ gn_stats, int frames_per_cta, const float* __restrict__ wav_stats,
+             const int32_t* __restrict__ wav_lengths) {
   constexpr int C = NI * 64;
   extern __shared__ __align__(16) float smem[];
   float* s_w = smem;                       // [KW][C]  tap-major: a lane's channel pairs are 8-byte contiguous
@@ -46,7 +48,17 @@ conv0_kernel(const TIn* __restrict__ wav, int64_t wav_ld, const float* __restric
   const int n_frames = t_end - t_begin;
   const TIn* x = wav + (size_t)b * wav_ld + (size_t)t_begin * stride;
   const int n_samples = (n_frames - 1) * stride + KW;
-  for (int i = threadIdx.x; i < n_samples; i += blockDim.x) s_x[i] = to_f32(x[i]);
+  if (wav_stats != nullptr) {
+    // waveform front end: standardise the utterance's valid samples on load (kernels.h: launch_wav_stats)
+    const float mean = wav_stats[2 * b], rstd = wav_stats[2 * b + 1];
+    const int n_valid = (wav_lengths != nullptr ? wav_lengths[b] : INT_MAX) - t_begin * stride;
+    for (int i = threadIdx.x; i < n_samples; i += blockDim.x) {
+      const float v = to_f32(x[i]);
+      s_x[i] = i < n_valid ? (v - mean) * rstd : v;
+    }
+  } else {
+    for (int i = threadIdx.x; i < n_samples; i += blockDim.x) s_x[i] = to_f32(x[i]);
+  }
   for (int i = threadIdx.x; i < KW * C; i += blockDim.x) {
     const int j = i / C, c = i % C;
     s_w[i] = w[(size_t)c * KW + j];
@@ -206,7 +218,7 @@ static w2vs_status_t launch_one(const Conv0Args& a, cudaStream_t st) {
   dim3 grid((unsigned)ceil_div64(a.T0, frames_per_cta), (unsigned)a.B);
   conv0_kernel<TIn, TOut, NI, KW, MODE><<<grid, 256, smem, st>>>(
       (const TIn*)a.wav, a.wav_ld, a.w, a.bias, a.gamma, a.beta, (TOut*)a.out, a.rows_per_utt, a.T0,
-      a.stride, a.gn_stats, frames_per_cta);
+      a.stride, a.gn_stats, frames_per_cta, a.wav_stats, a.wav_lengths);
   W2VS_CHECK_LAUNCH("conv0_kernel");
   return W2VS_OK;
 }
@@ -247,7 +259,52 @@ w2vs_status_t launch_conv0(const Conv0Args& a, cudaStream_t st) {
   if (a.wav_dtype == W2VS_F32) {
     return a.out_dtype == W2VS_F32 ? launch_ni<float, float>(a, st) : launch_ni<float, bf16>(a, st);
   }
+  if (a.wav_dtype == W2VS_I16) {
+    return a.out_dtype == W2VS_F32 ? launch_ni<int16_t, float>(a, st) : launch_ni<int16_t, bf16>(a, st);
+  }
   return a.out_dtype == W2VS_F32 ? launch_ni<bf16, float>(a, st) : launch_ni<bf16, bf16>(a, st);
+}
+
+// ---- waveform front end: per-utterance statistics ------------------------------------------------------------------
+// One CTA per utterance, two passes (mean, then centred squares) in fp32 with a fixed reduction order.
+template <typename TIn>
+__global__ void __launch_bounds__(1024)
+wav_stats_kernel(const TIn* __restrict__ wav, int64_t wav_ld, const int32_t* __restrict__ lengths, int L,
+                 float* __restrict__ stats) {
+  __shared__ float s_red[32];
+  __shared__ float s_bcast;
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = lengths != nullptr ? min(max(lengths[b], 1), L) : L;
+  const TIn* x = wav + (size_t)b * wav_ld;
+  auto block_sum = [&](float v) {
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      float t = lane < (int)(blockDim.x >> 5) ? s_red[lane] : 0.f;
+      t = warp_sum(t);
+      if (lane == 0) s_bcast = t;
+    }
+    __syncthreads();
+    return s_bcast;
+  };
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += to_f32(x[i]);
+  const float mean = block_sum(s) / (float)n;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { const float d = to_f32(x[i]) - mean; q = fmaf(d, d, q); }
+  const float var = block_sum(q) / (float)n;
+  if (threadIdx.x == 0) { stats[2 * b] = mean; stats[2 * b + 1] = 1.0f / sqrtf(var + 1e-5f); }
+}
+
+w2vs_status_t launch_wav_stats(const void* wav, int wav_dtype, int64_t wav_ld, const int32_t* lengths, int L, int B,
+                               float* stats, cudaStream_t st) {
+  if (wav_dtype == W2VS_F32) wav_stats_kernel<float><<<B, 1024, 0, st>>>((const float*)wav, wav_ld, lengths, L, stats);
+  else if (wav_dtype == W2VS_I16) wav_stats_kernel<int16_t><<<B, 1024, 0, st>>>((const int16_t*)wav, wav_ld, lengths, L, stats);
+  else wav_stats_kernel<bf16><<<B, 1024, 0, st>>>((const bf16*)wav, wav_ld, lengths, L, stats);
+  W2VS_CHECK_LAUNCH("wav_stats_kernel");
+  return W2VS_OK;
 }
 
 }  // namespace w2vs

@@ -77,6 +77,8 @@ w2vs_status_t launch_concat_wav(float* dst, int64_t dst_bs, const float* srcA, i
   if (total <= 0) return W2VS_OK;
   if (new_dtype == W2VS_F32)
     concat_wav_kernel<float><<<grid_for(total), 256, 0, st>>>(dst, dst_bs, srcA, a_bs, offA, cA, (const float*)src_new, new_bs, n, B);
+  else if (new_dtype == W2VS_I16)   // 16-bit PCM chunks straight from the audio source (x / 32768)
+    concat_wav_kernel<int16_t><<<grid_for(total), 256, 0, st>>>(dst, dst_bs, srcA, a_bs, offA, cA, (const int16_t*)src_new, new_bs, n, B);
   else
     concat_wav_kernel<bf16><<<grid_for(total), 256, 0, st>>>(dst, dst_bs, srcA, a_bs, offA, cA, (const bf16*)src_new, new_bs, n, B);
   W2VS_CHECK_LAUNCH("concat_wav_kernel");

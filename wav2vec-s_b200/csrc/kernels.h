@@ -14,8 +14,14 @@ struct Conv0Args {
   void* out; int out_dtype;
   int B, T0, rows_per_utt, C, k, stride, norm;
   float* gn_stats;   // [B][C][2] scale/shift + [B][ceil(T0/256)][2][C] partials (GroupNorm mode)
+  const float* wav_stats;      // optional [B][2] (mean, rstd): samples are standardised on load (waveform front end)
+  const int32_t* wav_lengths;  // optional [B]: samples at or past the length are left as they are
 };
 w2vs_status_t launch_conv0(const Conv0Args& a, cudaStream_t st);
+// per-utterance (mean, 1/sqrt(var + 1e-5)) over the valid samples: F.layer_norm(feats, feats.shape) of the reference
+// data pipeline (fairseq/data/audio/raw_audio_dataset.py:60-72)
+w2vs_status_t launch_wav_stats(const void* wav, int wav_dtype, int64_t wav_ld, const int32_t* lengths, int L, int B,
+                               float* stats, cudaStream_t st);
 
 // ---- row kernels --------------------------------------------------------------------------------
 struct LayerNormArgs {

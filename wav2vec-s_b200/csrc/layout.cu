@@ -236,6 +236,7 @@ void make_workspace(const w2vs_config* cfg, const Geometry& g, int B, Workspace*
                      ? b.take((size_t)B * cfg->conv_dim[0] * 2 * 4 * (1 + (size_t)(g.conv_len[0] + 255) / 256))
                      : kNone;
   const int D = cfg->embed_dim, F = cfg->ffn_dim;
+  ws->wav_stats = b.take((size_t)B * 2 * 4);
   ws->feats = b.take((size_t)B * g.conv_rows[n - 1] * D * 4);
   ws->frame_pad = b.take((size_t)B * g.T);
   ws->pos = b.take((size_t)B * g.T * 4);

@@ -64,6 +64,7 @@ inline LayerW layer_at(const WeightLayout& wl, int n) {
 struct Workspace {
   size_t conv_a, conv_b;       // act ping/pong [B*rows_i + slack][C_i]
   size_t gn_stats;             // fp32 [B][C0][2] + per-CTA partials (GroupNorm mode only)
+  size_t wav_stats;            // fp32 [B][2]  per-utterance (mean, rstd) of the waveform front end
   size_t feats;                // fp32 [B*rows_last][D]  (post_extract_proj output)
   size_t frame_pad;            // u8 [B][T]
   size_t pos;                  // i32 [B][T]

@@ -254,7 +254,7 @@ w2vs_status_t w2vs_stream_step(const w2vs_config* cfg, const void* d_packed, voi
   W2VS_REQUIRE(!hs->finished, "stream already finished");
   W2VS_REQUIRE(n_new >= 0 && n_new <= hs->max_new, "n_new exceeds max_new_samples");
   W2VS_REQUIRE(n_new == 0 || d_new != nullptr, "d_new_samples is NULL");
-  W2VS_REQUIRE(wav_dtype == W2VS_F32 || wav_dtype == W2VS_BF16, "wav_dtype");
+  W2VS_REQUIRE(wav_dtype == W2VS_F32 || wav_dtype == W2VS_BF16 || wav_dtype == W2VS_I16, "wav_dtype");
   W2VS_REQUIRE(flush == W2VS_FLUSH_NONE || flush == W2VS_FLUSH_FINAL || flush == W2VS_FLUSH_PEEK, "flush mode");
   const int B = hs->B, main_ctx = hs->main_ctx, rc = hs->rc, n = cfg->n_conv;
   StreamLayout L;

@@ -227,6 +227,12 @@ class Wav2VecSModel(nn.Module):
         self.layer_norm = _Params(weight=(self.embed,), bias=(self.embed,))
         nn.init.ones_(self.layer_norm.weight)
         self.max_positions = 8000          # wav2vec_S.py:341 (rain uses 2048; the table grows on demand)
+        # Waveform front end.  ``source`` may be 16-bit PCM (torch.int16), read as
+        # x / 32768 like the SimulEval agent does (rain/simul/transducer_searcher.py:74-80); with
+        # ``normalize_waveform`` every utterance is standardised over its valid samples inside the first conv
+        # layer's load, which is the data pipeline's `normalize: true` (raw_audio_dataset.py:60-72) -- feed RAW
+        # samples then, not pre-normalised ones.  Full-utterance calls only (a stream has no utterance statistics).
+        self.normalize_waveform = bool(getattr(args, "normalize_waveform", False))
         self._packed = None                # (key, uint8 device tensor)
         self._ws = None
         self._ccfg = None
@@ -384,7 +390,7 @@ class Wav2VecSModel(nn.Module):
             raise ValueError("source must be [B, L]")
         if source.device != device:
             raise RuntimeError("source must be on the model's CUDA device")
-        if source.dtype not in (torch.float32, torch.bfloat16):
+        if source.dtype not in (torch.float32, torch.bfloat16, torch.int16):
             source = source.float()
         source = source.contiguous()
         B, L = source.shape
@@ -401,7 +407,15 @@ class Wav2VecSModel(nn.Module):
         out_mask = torch.empty((B, T_out), dtype=torch.bool, device=device)
         a = cabi.EncodeArgs()
         a.d_wav = source.data_ptr()
-        a.wav_dtype = cabi.BF16 if source.dtype == torch.bfloat16 else cabi.F32
+        a.wav_dtype = {torch.bfloat16: cabi.BF16, torch.int16: cabi.I16}.get(source.dtype, cabi.F32)
+        a.wav_normalize = 1 if self.normalize_waveform else 0
+        if self.normalize_waveform and lengths is None and padding_mask is not None:
+            # the statistics need the valid length of each utterance: a length mask gives it, holes do not
+            pmb = padding_mask.to(device=device, dtype=torch.bool)
+            lengths = (~pmb).sum(1).to(torch.int32)
+            if not torch.equal(pmb, torch.arange(pmb.size(1), device=device)[None, :] >= lengths[:, None]):
+                raise ValueError("normalize_waveform needs a length-type padding mask")
+            mask_len, padding_mask = pmb.size(1), None
         a.B, a.L = B, L
         keep = []
         if lengths is not None:
@@ -477,11 +491,11 @@ class EncoderStream:
                 raise ValueError("new_samples must be [B, n]")
             if new_samples.device != self.device:
                 raise RuntimeError("new_samples must be on the model's CUDA device")
-            if new_samples.dtype not in (torch.float32, torch.bfloat16):
+            if new_samples.dtype not in (torch.float32, torch.bfloat16, torch.int16):
                 new_samples = new_samples.float()
             new_samples = new_samples.contiguous()
             src_ptr = new_samples.data_ptr()
-            wdt = cabi.BF16 if new_samples.dtype == torch.bfloat16 else cabi.F32
+            wdt = {torch.bfloat16: cabi.BF16, torch.int16: cabi.I16}.get(new_samples.dtype, cabi.F32)
         # every call can emit at most the frames the new samples complete plus the pending tail
         cap = n_new // 320 + 2 * (self.main + self.rc) + 2
         out = torch.empty((cap, self.B, self.D), dtype=self.dtype, device=self.device)
