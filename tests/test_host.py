@@ -122,3 +122,28 @@ def test_invalid_config_is_rejected_before_any_launch():
     with pytest.raises(cabi.W2vsError) as e:
         m.geometry(8000, 16, 8)
     assert e.value.status == cabi.UNSUPPORTED
+
+
+def test_from_checkpoint_formats():
+    """Checkpoint ingestion: hydra-era {"cfg": {"model": ..}}, argparse-era {"args": ..},
+    and a composite fine-tuned checkpoint with the encoder under a prefix and foreign keys next to it."""
+    import argparse
+    import torch
+    import wav2vec_s_b200 as W
+    from oracle import cases, synth
+    cfg = cases.tiny(layer_norm_first=True, conv_bias=True)
+    sd = synth.make_state_dict(cfg, 3)
+    m1, missing, unexpected = W.Wav2VecSModel.from_checkpoint({"cfg": {"model": dict(cfg)}, "model": sd})
+    assert not unexpected and set(missing) <= {"mask_emb"}
+    m2, missing, unexpected = W.BlockWiseWav2Vec2Model.from_checkpoint(
+        {"args": argparse.Namespace(**cfg), "cfg": None, "model": sd}, main_context=8, right_context=4)
+    assert not unexpected and (m2.encoder.main_context, m2.encoder.right_context) == (8, 4)
+    composite = {"encoder.w2v2_model." + k: v for k, v in sd.items()}
+    composite["decoder.embed_tokens.weight"] = torch.zeros(4, 4)
+    composite["encoder.encoder_proj.weight"] = torch.zeros(4, 4)
+    m3, missing, unexpected = W.Wav2VecSModel.from_checkpoint({"cfg": {"model": {"w2v_args": {"model": dict(cfg)}}},
+                                                               "model": composite})
+    assert not unexpected and set(missing) <= {"mask_emb"}
+    for k, v in m1.state_dict().items():
+        if k in sd:
+            assert torch.equal(v, sd[k]) and torch.equal(m3.state_dict()[k], sd[k]), k

@@ -249,6 +249,46 @@ class Wav2VecSModel(nn.Module):
         """wav2vec2.py:695-699: the quantizer / projection heads never exist here."""
         return None
 
+    # prefixes under which fine-tuned / CAAT checkpoints keep the wav2vec-S encoder
+    # (wav2vec2_asr.py:290-372 `w2v_encoder.w2v_model.`, rain `encoder.w2v2_model.`, unidirect_w2v2_encoder.py:551-552)
+    _CKPT_PREFIXES = ("encoder.w2v2_model.", "w2v_encoder.w2v_model.", "w2v2_model.", "w2v_model.")
+
+    @classmethod
+    def from_checkpoint(cls, ckpt, main_context=None, right_context=None, strict=False):
+        """Build the encoder from a fairseq checkpoint: a path or the loaded
+        dict ``{"cfg": {"model": ...} | "args": Namespace, "model": state_dict}`` that
+        ``checkpoint_utils.load_checkpoint_to_cpu`` returns and ``OnlineW2V2TransformerEncoder.__init__``
+        consumes (unidirect_w2v2_encoder.py:541-555): pre-trained wav2vec-S checkpoints as released, or a
+        fine-tuned ASR / CAAT checkpoint in which the encoder sits under one of ``_CKPT_PREFIXES``.  Returns
+        (model, missing_keys, unexpected_keys); keys of other sub-modules of a composite checkpoint (decoder,
+        joiner, CTC projection) are reported as unexpected and ignored unless ``strict``."""
+        if isinstance(ckpt, (str, bytes)) or hasattr(ckpt, "__fspath__"):
+            ckpt = torch.load(ckpt, map_location="cpu", weights_only=False)
+        if ckpt.get("args") is not None:
+            margs = vars(ckpt["args"]).copy()
+            margs.setdefault("extractor_mode", "layer_norm")       # rain :545-547 for argparse-era checkpoints
+            margs.setdefault("pos_type", "sin")
+        else:
+            model_cfg = ckpt["cfg"]["model"]
+            margs = dict(model_cfg) if isinstance(model_cfg, dict) else dict(vars(model_cfg))
+            inner = margs.get("w2v_args")                          # fine-tuned: the encoder's own args are nested
+            if inner is not None:
+                inner = inner["model"] if isinstance(inner, dict) and "model" in inner else inner
+                margs = dict(inner) if isinstance(inner, dict) else dict(vars(inner))
+        if main_context is not None:
+            margs["main_context"] = main_context
+        if right_context is not None:
+            margs["right_context"] = right_context
+        margs["load_pretrained_model_from"] = ""
+        sd = ckpt["model"]
+        for pre in cls._CKPT_PREFIXES:
+            if any(k.startswith(pre) for k in sd):
+                sd = {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
+                break
+        model = cls(margs)
+        res = model.load_state_dict(sd, strict=strict)
+        return model, list(res.missing_keys), list(res.unexpected_keys)
+
     def load_state_dict(self, state_dict, strict=True, **kw):
         sd = {k: v for k, v in state_dict.items() if not k.startswith(_PRETRAIN_PREFIXES)}
         out = super().load_state_dict(sd, strict=strict, **kw)
