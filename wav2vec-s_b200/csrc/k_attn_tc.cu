@@ -328,7 +328,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc_commit_1sm(bar_sfull);
         return true;
       };
+      // The thread never waits for an MMA it has just issued.  The K slot of S(g+1) is refilled after PV(g) has been
+      // issued, the V slot of PV(g-1) at the start of tile g -- by then those MMAs have long retired, so the waits
+      // return at once.  (Waiting for S(g+1) and PV(g) right after issuing them, as this loop first did, made the
+      // thread's own chain 2570 cycles per tile -- longer than the softmax chain it feeds; clock64 trace.)  A wait
+      // may lag its barrier by one phase at most (parity waits), which this order guarantees.
       int gt = 0, wi = 0;
+      bool pending_v = false;            // PV(g-1) has been issued and its V slot is not refilled yet
       for (; wk.w < n_items && ok; wk.next(sh), wnext.next(sh), ++wi) {
         const Item im = item_of(sh, wk);
         const int n = im.ts.n_kt;
@@ -354,10 +360,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             TRACE(1, g, 1);
             if (!(ok = issue_s(g + 1))) break;
             TRACE(1, g, 2);
-            if (!(ok = MMA_WAIT(bar_sfull, (g + 1) & 1))) break;    // S(g+1) retired (idle time: P(g) is not ready yet)
-            load_kv(ck, bar_kfull, sK, D);                             // K(g+1+NS)
-            if (it + 2 == n) load_q(wnext);                            // it was the item's last S: Q is free
-            TRACE(1, g, 6);
+          }
+          if (pending_v) {
+            if (!(ok = MMA_WAIT(bar_pvdone, (g - 1) & 1))) break;     // PV(g-1) retired a tile ago: V's slot is free
+            load_kv(cv, bar_vfull, sV, 2 * D);                         // V(g+1)
+            pending_v = false;
           }
           const int sl = g % NS;
           if (!(ok = MMA_WAIT(bar_vfull + 8 * sl, (g / NS) & 1))) break;
@@ -370,9 +377,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           for (int k = 0; k < KT / 16; ++k)
             umma_ss(tmem_base + O_COL, dP + 2 * k, dv + (2048 >> 4) * k, idesc_pv, (it > 0 || k > 0) ? 1u : 0u);
           tc_commit_1sm(bar_pvdone);
+          pending_v = true;
           TRACE(1, g, 5);
-          if (!(ok = MMA_WAIT(bar_pvdone, g & 1))) break;           // PV(g) retired: V's slot is free
-          load_kv(cv, bar_vfull, sV, 2 * D);                           // V(g+NS)
+          if (it + 1 < n) {
+            if (!(ok = MMA_WAIT(bar_sfull, (g + 1) & 1))) break;    // S(g+1), issued before PV(g), has retired
+            load_kv(ck, bar_kfull, sK, D);                             // K(g+1+NS)
+            if (it + 2 == n) load_q(wnext);                            // it was the item's last S: Q is free
+            TRACE(1, g, 6);
+          }
           TRACE(1, g, 7);
         }
         gt += n;
