@@ -48,15 +48,20 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// 64 rows x 128 B from a strided global matrix into a swizzled tile; rows >= n_rows are zero-filled
+// 64 rows x 128 B from a strided global matrix into a swizzled tile; rows >= n_rows are zero-filled.  Rows at or past
+// `split` come from a second matrix (step mode: keys of this step's own tokens are read from the qkv buffer, earlier
+// keys from the K/V cache).
 __device__ __forceinline__ void load_tile_async(bf16* tile, const bf16* src, int64_t row_stride, int first_row,
-                                                int n_rows, int tid) {
+                                                int n_rows, int tid, const bf16* src2 = nullptr,
+                                                int64_t row_stride2 = 0, int split = INT_MAX) {
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int c = tid + 128 * r;
     const int row = c >> 3, chunk = c & 7;
     const bool ok = row < n_rows;
-    const bf16* g = src + (size_t)(first_row + (ok ? row : 0)) * row_stride + chunk * 8;
+    const int ar = first_row + (ok ? row : 0);
+    const bf16* g = ar < split ? src + (size_t)ar * row_stride + chunk * 8
+                               : src2 + (size_t)(ar - split) * row_stride2 + chunk * 8;
     cp_async16(smem_addr(tile + sw(row, chunk)), g, ok);
   }
 }
@@ -85,6 +90,18 @@ attn_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ keypad
   const bf16* kbase = step ? kv_cache + (size_t)b * kv_rows * krs + (size_t)h * HD : qbase + D;
   const bf16* vbase = kbase + D;
   const uint8_t* kp = step ? nullptr : keypad + (size_t)b * M;
+  // step mode: the M query tokens of this step are the last M of the T2 keys.  Their K / V are read from the qkv
+  // buffer, and the first query tile's CTA of each (head, stream) also appends them to the cache for later steps
+  // (what a separate kv_append launch used to do: one kernel less per layer in a latency-bound chain).
+  const int f0 = step ? T2 - M : INT_MAX;
+  if (step && blockIdx.x == 0) {
+    bf16* cache = const_cast<bf16*>(kv_cache) + (size_t)b * kv_rows * krs + (size_t)h * HD;
+    for (int i = tid; i < M * 16; i += 128) {          // 8 chunks of K + 8 chunks of V per token
+      const int row = i >> 4, part = (i >> 3) & 1, chunk = i & 7;
+      const uint4 v = *reinterpret_cast<const uint4*>(qbase + (size_t)row * rs + (1 + part) * D + chunk * 8);
+      *reinterpret_cast<uint4*>(cache + (size_t)(f0 + row) * krs + part * D + chunk * 8) = v;
+    }
+  }
 
   int q_first, q_count;
   if (step) { q_first = tile_id * QT; q_count = min(QT, M - q_first); }
@@ -103,8 +120,8 @@ attn_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ keypad
     const bool s1 = it >= n0;
     const int k0 = s1 ? seg1_begin + (it - n0) * KT : it * KT;
     const int cnt = min(KT, (s1 ? seg1_end : seg0_end) - k0);
-    load_tile_async(Ks[buf], kbase, krs, k0, cnt, tid);
-    load_tile_async(Vs[buf], vbase, krs, k0, cnt, tid);
+    load_tile_async(Ks[buf], kbase, krs, k0, cnt, tid, qbase + D, rs, f0);
+    load_tile_async(Vs[buf], vbase, krs, k0, cnt, tid, qbase + 2 * D, rs, f0);
     if (tid < KT) {
       int info;
       if (step) info = tid < cnt ? 0 : INT_MAX;

@@ -170,7 +170,8 @@ w2vs_status_t block_step(const w2vs_config* cfg, const WeightLayout& wl, const S
     void* cache = at<void>(d_state, L.kv + (size_t)l * L.kv_layer_bytes);
     if (pre_ln) W2VS_TRY(layer_norm(lw.ln1_w, lw.ln1_b, false));
     W2VS_TRY(gemm(Xa, D, lw.wqkv, lw.bqkv, nullptr, qkv, 3 * D, adt, 0));
-    W2VS_TRY(launch_kv_append(qkv, cache, L.kv_rows, f0, ntok, D, (int)as, B, st));
+    // (bf16: the step attention kernel appends this step's K / V to the cache itself)
+    if (adt != W2VS_BF16) W2VS_TRY(launch_kv_append(qkv, cache, L.kv_rows, f0, ntok, D, (int)as, B, st));
     {
       AttnArgs aa{};
       aa.qkv = qkv; aa.ctx = ctx; aa.dtype = adt; aa.B = B; aa.heads = cfg->heads; aa.D = D;
