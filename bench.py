@@ -269,6 +269,43 @@ def stream_bench(a, kind, B, seconds):
     print(json.dumps(line))
 
 
+def incremental_probe(model, cfg, dev, seconds=30):
+    """p50 / p90 device latency of a decision step (first chunk 24 frames, then 16 frames = 5120 samples per step) of
+    one stream through BlockWiseWav2Vec2Model.open_stream -> w2vs_stream_step, on the bench's own weights."""
+    import torch
+    import wav2vec_s_b200 as W
+    from wav2vec_s_b200.model import EncoderStream
+    sm = W.BlockWiseWav2Vec2Model(cfg)
+    sm.load_state_dict(model.state_dict(), strict=False)
+    sm = sm.to(dev, next(model.parameters()).dtype).eval()
+    L = seconds * SR
+    wav = torch.randn(1, L, generator=torch.Generator().manual_seed(4321)).to(dev)
+    bounds = [7760]
+    while bounds[-1] + 5120 < L:
+        bounds.append(bounds[-1] + 5120)
+    bounds.append(L)
+    lats = []
+    for rep in range(3):
+        st = sm.open_stream(B=1, max_seconds=seconds + 1, max_new_samples=7760 + 400)
+        pos, lat = 0, []
+        for n in bounds:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            st.step(wav[:, pos:n], EncoderStream.FINAL if n >= L else EncoderStream.NONE)
+            e1.record()
+            torch.cuda.synchronize()
+            lat.append(e0.elapsed_time(e1))
+            pos = n
+        if rep > 0:
+            lats += lat[1:-1]
+    lats.sort()
+    p50 = lats[len(lats) // 2]
+    return {"metric": "p50 per-chunk latency (wav2vec-S large incremental, 1 stream, 16 frames/step)",
+            "p50_ms": p50, "p90_ms": lats[int(0.9 * len(lats))], "unit": "ms", "steps": len(lats),
+            "realtime_factor": 0.32 / (p50 / 1e3)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -278,6 +315,7 @@ def main():
     ap.add_argument("--workload", default="large_64x20s", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-incremental", action="store_true", help="skip the incremental-mode latency probe")
     ap.add_argument("--kernel-detail", action="store_true", help="per-kernel (name, shape) device ms in the JSON line")
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
     ap.add_argument("--step-blocks", type=int, default=1, help="streaming workloads: blocks of 16 frames per decision step")
@@ -480,6 +518,13 @@ def main():
                                          if "[" in k or "_kernel" in k}
         else:
             line["roofline"] = None
+        if kind == "large" and world == 1 and not a.no_incremental:
+            # the other half of BASELINE.json's metric: p50 latency of one decision step (16 new frames) of the
+            # incremental path, one stream, same model; measured after the timed regions above
+            try:
+                line["incremental"] = incremental_probe(model, cfg, dev)
+            except Exception as ex:   # never lose the headline line to the secondary measurement
+                line["incremental"] = {"error": f"{type(ex).__name__}: {ex}"}
         if not a.no_cpu_baseline:
             r = cpu_reference_run(kind, a.cpu_sample_batch, seconds, 2, 1)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
