@@ -70,8 +70,10 @@ __device__ __forceinline__ void load_tile_async(bf16* tile, const bf16* src, int
 __global__ void __launch_bounds__(128)
 attn_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ keypad, bf16* __restrict__ ctx,
                 int T2, int M, int main_ctx, int rc, int D, int n_main_tiles, int n_tiles, float scale_log2,
-                const bf16* __restrict__ kv_cache, int64_t kv_rows) {
+                const bf16* __restrict__ kv_cache, int64_t kv_rows, int n_splits, float* __restrict__ partials,
+                unsigned* __restrict__ counters) {
   __shared__ __align__(128) bf16 Qs[TILE_ELEMS];
+  __shared__ int s_last;
   __shared__ __align__(128) bf16 Ks[2][TILE_ELEMS];
   __shared__ __align__(128) bf16 Vs[2][TILE_ELEMS];
   __shared__ int s_kinfo[2][KT];
@@ -80,7 +82,10 @@ attn_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ keypad
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const int h = blockIdx.y, b = blockIdx.z;
-  const int tile_id = n_tiles - 1 - (int)blockIdx.x;  // heaviest first
+  // step mode with n_splits > 1: blockIdx.x = query tile * n_splits + split; each split takes a contiguous range of
+  // key tiles and leaves (m, l, O) per row, the last CTA of a (stream, head, query tile) to finish combines them
+  const int tile_lin = (int)blockIdx.x / n_splits, split = (int)blockIdx.x % n_splits;
+  const int tile_id = n_tiles - 1 - tile_lin;  // heaviest first
   const int nb = T2 / main_ctx;
   const int rcd = rc > 0 ? rc : 1;
   const bool step = kv_cache != nullptr;
@@ -94,7 +99,7 @@ attn_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ keypad
   // buffer, and the first query tile's CTA of each (head, stream) also appends them to the cache for later steps
   // (what a separate kv_append launch used to do: one kernel less per layer in a latency-bound chain).
   const int f0 = step ? T2 - M : INT_MAX;
-  if (step && blockIdx.x == 0) {
+  if (step && blockIdx.x == 0) {      // (query tile 0, split 0)
     bf16* cache = const_cast<bf16*>(kv_cache) + (size_t)b * kv_rows * krs + (size_t)h * HD;
     for (int i = tid; i < M * 16; i += 128) {          // 8 chunks of K + 8 chunks of V per token
       const int row = i >> 4, part = (i >> 3) & 1, chunk = i & 7;
@@ -115,6 +120,12 @@ attn_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ keypad
   const int n0 = (seg0_end + KT - 1) / KT;
   const int n1 = (seg1_end - seg1_begin + KT - 1) / KT;
   const int n_kt = n0 + n1;
+  int it_begin = 0, it_end = n_kt;
+  if (n_splits > 1) {
+    const int per = (n_kt + n_splits - 1) / n_splits;
+    it_begin = min(split * per, n_kt);
+    it_end = min(it_begin + per, n_kt);
+  }
 
   auto issue_tile = [&](int it, int buf) {
     const bool s1 = it >= n0;
@@ -132,7 +143,7 @@ attn_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ keypad
   };
 
   load_tile_async(Qs, qbase, rs, q_first, q_count, tid);
-  issue_tile(0, 0);
+  if (it_begin < it_end) issue_tile(it_begin, 0);
   cp_async_commit();
 
   // this thread's two query rows: warp*16 + g and + 8
@@ -146,9 +157,9 @@ attn_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ keypad
   for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
-  for (int it = 0; it < n_kt; ++it) {
-    const int buf = it & 1;
-    if (it + 1 < n_kt) {
+  for (int it = it_begin; it < it_end; ++it) {
+    const int buf = (it - it_begin) & 1;
+    if (it + 1 < it_end) {
       issue_tile(it + 1, buf ^ 1);
       cp_async_commit();
       cp_async_wait<1>();
@@ -156,7 +167,7 @@ attn_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ keypad
       cp_async_wait<0>();
     }
     __syncthreads();
-    if (it == 0) {
+    if (it == it_begin) {
       const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) ldsm_x4(smem_addr(Qs + sw(row, kk * 2 + (lane >> 4))), qf[kk]);
@@ -236,11 +247,60 @@ attn_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ keypad
     __syncthreads();  // tile `buf` fully consumed before the next iteration's prefetch overwrites it
   }
 
+  cp_async_wait<0>();   // an empty key range (a trailing split) never waited for its Q tile
   // ---- normalise, stage through this warp's 16 rows of Qs, 16-byte coalesced stores
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
   l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  if (n_splits > 1) {
+    // ---- partial state of this split: per row 64 un-normalised outputs, the running maximum (raw score units)
+    //      and the row sum; the last CTA of this (stream, head, query tile) merges the splits
+    const size_t grp = ((size_t)b * gridDim.y + h) * n_tiles + tile_lin;
+    float* P = partials + (grp * n_splits + split) * (size_t)(QT * 66);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      *reinterpret_cast<float2*>(P + r0 * 66 + j * 8 + 2 * t4) = make_float2(o[j][0], o[j][1]);
+      *reinterpret_cast<float2*>(P + r1 * 66 + j * 8 + 2 * t4) = make_float2(o[j][2], o[j][3]);
+    }
+    if (t4 == 0) {
+      *reinterpret_cast<float2*>(P + r0 * 66 + 64) = make_float2(m0, l0);
+      *reinterpret_cast<float2*>(P + r1 * 66 + 64) = make_float2(m1, l1);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(counters + grp, 1u) == (unsigned)n_splits - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const float* P0 = partials + grp * n_splits * (size_t)(QT * 66);
+    for (int idx = tid; idx < q_count * 8; idx += 128) {
+      const int row = idx >> 3, chunk = idx & 7;
+      float mx = -INFINITY;
+      for (int sp = 0; sp < n_splits; ++sp) mx = fmaxf(mx, __ldcg(P0 + (size_t)sp * QT * 66 + row * 66 + 64));
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, lsum = 0.f;
+      for (int sp = 0; sp < n_splits; ++sp) {
+        const float* pr = P0 + (size_t)sp * QT * 66 + row * 66;
+        const float2 ml = __ldcg(reinterpret_cast<const float2*>(pr + 64));
+        if (ml.x == -INFINITY) continue;
+        const float w = exp2f((ml.x - mx) * scale_log2);
+        lsum = fmaf(ml.y, w, lsum);
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          const float2 ov = __ldcg(reinterpret_cast<const float2*>(pr + chunk * 8 + e));
+          acc[e] = fmaf(ov.x, w, acc[e]);
+          acc[e + 1] = fmaf(ov.y, w, acc[e + 1]);
+        }
+      }
+      const float inv = lsum > 0.f ? 1.0f / lsum : 0.f;
+      uint4 v;
+      v.x = pack_bf16x2(acc[0] * inv, acc[1] * inv); v.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
+      v.z = pack_bf16x2(acc[4] * inv, acc[5] * inv); v.w = pack_bf16x2(acc[6] * inv, acc[7] * inv);
+      *reinterpret_cast<uint4*>(ctx + ((size_t)b * M + q_first + row) * D + (size_t)h * HD + chunk * 8) = v;
+    }
+    if (tid == 0) counters[grp] = 0u;            // ready for the next launch (stream order)
+    return;
+  }
   const float i0 = l0 > 0.f ? 1.0f / l0 : 0.f, i1 = l1 > 0.f ? 1.0f / l1 : 0.f;
   __syncwarp();
 #pragma unroll
@@ -268,9 +328,19 @@ w2vs_status_t launch_attention_mma(const AttnArgs& a, cudaStream_t st) {
   const float scale_log2 = (1.0f / sqrtf((float)HD)) * 1.4426950408889634f;
   if (a.n_step_q > 0) {
     const int nt = (a.n_step_q + QT - 1) / QT;
-    dim3 grid((unsigned)nt, (unsigned)a.heads, (unsigned)a.B);
+    // long left contexts: split the keys of a (stream, head) over up to 8 CTAs (two key tiles per split at least)
+    const int n_kt = (a.n_step_keys + KT - 1) / KT;
+    int splits = 1;
+    if (a.step_partials != nullptr && a.step_counters != nullptr) {
+      // ... as long as the streams and heads alone do not fill the GPU (measured: 16 streams are slower split)
+      const int fill = 296 / (a.B * a.heads * nt);
+      splits = n_kt / 2 < fill ? n_kt / 2 : fill;
+      splits = splits < 1 ? 1 : (splits > kAttnStepMaxSplits ? kAttnStepMaxSplits : splits);
+    }
+    dim3 grid((unsigned)(nt * splits), (unsigned)a.heads, (unsigned)a.B);
     launch_pdl(attn_mma_kernel, grid, dim3(128), 0, st, (const bf16*)a.qkv, (const uint8_t*)nullptr, (bf16*)a.ctx,
-               a.n_step_keys, a.n_step_q, 1, 0, a.D, nt, nt, scale_log2, (const bf16*)a.kv_cache, a.kv_rows);
+               a.n_step_keys, a.n_step_q, 1, 0, a.D, nt, nt, scale_log2, (const bf16*)a.kv_cache, a.kv_rows, splits,
+               a.step_partials, a.step_counters);
     W2VS_CHECK_LAUNCH("attn_mma_kernel");
     return W2VS_OK;
   }
@@ -278,7 +348,7 @@ w2vs_status_t launch_attention_mma(const AttnArgs& a, cudaStream_t st) {
   const int n_main = (a.T2 + QT - 1) / QT, n_rc = (M - a.T2 + QT - 1) / QT;
   dim3 grid((unsigned)(n_main + n_rc), (unsigned)a.heads, (unsigned)a.B);
   attn_mma_kernel<<<grid, 128, 0, st>>>((const bf16*)a.qkv, a.keypad, (bf16*)a.ctx, a.T2, M, a.main_ctx, a.rc,
-                                        a.D, n_main, n_main + n_rc, scale_log2, nullptr, 0);
+                                        a.D, n_main, n_main + n_rc, scale_log2, nullptr, 0, 1, nullptr, nullptr);
   W2VS_CHECK_LAUNCH("attn_mma_kernel");
   return W2VS_OK;
 }

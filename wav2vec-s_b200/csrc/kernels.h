@@ -91,7 +91,12 @@ struct AttnArgs {
   int B, T2, main_ctx, rc, heads, D;
   int n_step_q, n_step_keys; const void* kv_cache; int64_t kv_rows;
   const uint8_t* pad_blk;           // optional [B][ceil(M/128)] flags from prep_masks (block mode, tcgen05 kernel)
+  // step mode, optional: split the cached keys of a (stream, head) over several CTAs (partial softmax state per
+  // split, combined by the CTA that finishes last).  step_partials: fp32 [B][heads][q tiles][8][64][66];
+  // step_counters: zeroed unsigned [B][heads][q tiles] (the kernel resets them).
+  float* step_partials; unsigned* step_counters;
 };
+constexpr int kAttnStepMaxSplits = 8;
 w2vs_status_t launch_attention_simt(const AttnArgs& a, cudaStream_t st);
 w2vs_status_t launch_attention_mma(const AttnArgs& a, cudaStream_t st);   // mma.sync flash kernel (also step mode)
 w2vs_status_t launch_attention_tc(const AttnArgs& a, cudaStream_t st);    // tcgen05 / TMEM kernel (block mode)

@@ -44,9 +44,9 @@ struct StreamLayout {
   int new_max[W2VS_MAX_CONV];
   int fcap, kv_rows, ntok_max;
   // device state
-  size_t in[W2VS_MAX_CONV][2], fbuf, kv, kv_layer_bytes, dev_total;
+  size_t in[W2VS_MAX_CONV][2], fbuf, kv, kv_layer_bytes, sync, dev_total;
   // workspace
-  size_t out[2], normed, feats_tmp, x, xa, qkv, ctx, h, ws_total;
+  size_t out[2], normed, feats_tmp, x, xa, qkv, ctx, h, attn_part, ws_total;
 };
 
 inline bool conv_has_ln(const w2vs_config* cfg, int i) {
@@ -104,6 +104,8 @@ w2vs_status_t make_stream_layout(const w2vs_config* cfg, int B, int max_frames, 
   L->fbuf = d.take((size_t)B * L->fcap * D * 4);
   L->kv_layer_bytes = align_up((size_t)B * L->kv_rows * 2 * D * as, 256);
   L->kv = d.take(L->kv_layer_bytes * cfg->layers);
+  // completion counters of the split-key step attention, one per (stream, head, query tile); zeroed by w2vs_stream_init
+  L->sync = d.take((size_t)B * cfg->heads * ((L->ntok_max + 63) / 64) * 4);
   L->dev_total = d.off;
 
   Bump w;
@@ -123,6 +125,7 @@ w2vs_status_t make_stream_layout(const w2vs_config* cfg, int B, int max_frames, 
   L->qkv = w.take(tok * 3 * D * as);
   L->ctx = w.take(tok * D * as);
   L->h = w.take(tok * F * as);
+  L->attn_part = w.take((size_t)B * cfg->heads * ((L->ntok_max + 63) / 64) * kAttnStepMaxSplits * 64 * 66 * 4);
   L->ws_total = w.off;
   return W2VS_OK;
 }
@@ -176,6 +179,7 @@ w2vs_status_t block_step(const w2vs_config* cfg, const WeightLayout& wl, const S
       AttnArgs aa{};
       aa.qkv = qkv; aa.ctx = ctx; aa.dtype = adt; aa.B = B; aa.heads = cfg->heads; aa.D = D;
       aa.n_step_q = ntok; aa.n_step_keys = f0 + ntok; aa.kv_cache = cache; aa.kv_rows = L.kv_rows;
+      aa.step_partials = at<float>(d_ws, L.attn_part); aa.step_counters = at<unsigned>(d_state, L.sync);
       W2VS_TRY(launch_attention(0, aa, st));
     }
     W2VS_TRY(gemm(ctx, D, lw.wo, lw.bo, X, X, D, W2VS_F32, 0));
@@ -227,7 +231,10 @@ w2vs_status_t w2vs_stream_init(const w2vs_config* cfg, int32_t B, int32_t max_fr
   memset(hs, 0, sizeof(*hs));
   hs->magic = kMagic;
   hs->B = B; hs->max_frames = max_frames; hs->max_new = max_new; hs->main_ctx = main_ctx; hs->rc = rc;
-  (void)stream;  // nothing to clear on the device: every row is written before it is read
+  // every data row is written before it is read; only the attention kernel's completion counters need zeroing
+  cudaError_t e = cudaMemsetAsync(at<uint8_t>(d_state, L.sync), 0, (size_t)B * cfg->heads * ((L.ntok_max + 63) / 64) * 4,
+                                  (cudaStream_t)stream);
+  if (e != cudaSuccess) { set_error("stream init memset: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
   return W2VS_OK;
 }
 
