@@ -33,6 +33,7 @@ conv0_kernel(const TIn* __restrict__ wav, int64_t wav_ld, const float* __restric
              int stride, float* __restrict__ gn_stats, int frames_per_cta, const float* __restrict__ wav_stats,
              const int32_t* __restrict__ wav_lengths) {
   constexpr int C = NI * 64;
+  pdl_prologue();
   extern __shared__ __align__(16) float smem[];
   float* s_w = smem;                       // [KW][C]  tap-major: a lane's channel pairs are 8-byte contiguous
   float* s_bias = s_w + KW * C;            // [C]
@@ -216,9 +217,9 @@ static w2vs_status_t launch_one(const Conv0Args& a, cudaStream_t st) {
     attr_done = true;
   }
   dim3 grid((unsigned)ceil_div64(a.T0, frames_per_cta), (unsigned)a.B);
-  conv0_kernel<TIn, TOut, NI, KW, MODE><<<grid, 256, smem, st>>>(
-      (const TIn*)a.wav, a.wav_ld, a.w, a.bias, a.gamma, a.beta, (TOut*)a.out, a.rows_per_utt, a.T0,
-      a.stride, a.gn_stats, frames_per_cta, a.wav_stats, a.wav_lengths);
+  launch_pdl(conv0_kernel<TIn, TOut, NI, KW, MODE>, grid, dim3(256), smem, st,
+             (const TIn*)a.wav, a.wav_ld, a.w, a.bias, a.gamma, a.beta, (TOut*)a.out, a.rows_per_utt, a.T0,
+             a.stride, a.gn_stats, frames_per_cta, a.wav_stats, a.wav_lengths);
   W2VS_CHECK_LAUNCH("conv0_kernel");
   return W2VS_OK;
 }

@@ -334,6 +334,7 @@ embed_tokens_kernel(const float* __restrict__ feats, int feat_rows, const uint8_
                     const float* __restrict__ posconv, const float* __restrict__ gamma,
                     const float* __restrict__ beta, float* __restrict__ X, TAct* __restrict__ Xa,
                     int B, int T, int T2, int M, int main_ctx, int rc, int D) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t tok = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (tok >= (int64_t)B * M) return;
@@ -384,9 +385,9 @@ static w2vs_status_t embed_dispatch(const EmbedArgs& a, cudaStream_t st) {
   const int wpb = 8;
   dim3 grid((unsigned)ceil_div64((int64_t)a.B * a.M, wpb));
 #define W2VS_EMB_CASE(NCH)                                                                        \
-  embed_tokens_kernel<TAct, NCH><<<grid, wpb * 32, 0, st>>>(                                      \
-      a.feats, a.feat_rows, a.frame_pad, a.pos, a.pos_offset, a.sin_table, a.posconv, a.gamma,    \
-      a.beta, a.X, (TAct*)a.Xa, a.B, a.T, a.T2, a.M, a.main_ctx, a.rc, a.D)
+  launch_pdl(embed_tokens_kernel<TAct, NCH>, grid, dim3(wpb * 32), 0, st,                         \
+             a.feats, a.feat_rows, a.frame_pad, a.pos, a.pos_offset, a.sin_table, a.posconv, a.gamma, \
+             a.beta, a.X, (TAct*)a.Xa, a.B, a.T, a.T2, a.M, a.main_ctx, a.rc, a.D)
   if (a.D <= 256) W2VS_EMB_CASE(1);
   else if (a.D <= 512) W2VS_EMB_CASE(2);
   else if (a.D <= 1024) W2VS_EMB_CASE(4);
@@ -407,6 +408,7 @@ __global__ void __launch_bounds__(256)
 finalize_rows_kernel(const float* __restrict__ X, const float* __restrict__ gamma,
                      const float* __restrict__ beta, TOut* __restrict__ out, int B, int T_out,
                      int64_t in_rows_per_utt, int D, int tbd) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= (int64_t)B * T_out) return;
@@ -432,8 +434,8 @@ static w2vs_status_t finalize_dispatch(const FinalizeArgs& a, cudaStream_t st) {
   const int wpb = 8;
   dim3 grid((unsigned)ceil_div64((int64_t)a.B * a.T_out, wpb));
 #define W2VS_FIN_CASE(NCH)                                                            \
-  finalize_rows_kernel<TOut, NCH><<<grid, wpb * 32, 0, st>>>(                         \
-      a.X, a.gamma, a.beta, (TOut*)a.out, a.B, a.T_out, a.in_rows_per_utt, a.D, a.tbd)
+  launch_pdl(finalize_rows_kernel<TOut, NCH>, grid, dim3(wpb * 32), 0, st,             \
+             a.X, a.gamma, a.beta, (TOut*)a.out, a.B, a.T_out, a.in_rows_per_utt, a.D, a.tbd)
   if (a.D <= 256) W2VS_FIN_CASE(1);
   else if (a.D <= 512) W2VS_FIN_CASE(2);
   else if (a.D <= 1024) W2VS_FIN_CASE(4);

@@ -10,6 +10,7 @@ namespace {
 __global__ void concat_rows_kernel(uint4* __restrict__ dst, int64_t dst_bs, const uint4* __restrict__ srcA,
                                    int64_t a_bs, int offA, int cA, const uint4* __restrict__ srcB, int64_t b_bs,
                                    int nB, int row_vecs, int B) {
+  pdl_prologue();
   const int64_t per_b = (int64_t)(cA + nB) * row_vecs;
   const int64_t total = per_b * B;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -27,6 +28,7 @@ template <typename TIn>
 __global__ void concat_wav_kernel(float* __restrict__ dst, int64_t dst_bs, const float* __restrict__ srcA,
                                   int64_t a_bs, int offA, int cA, const TIn* __restrict__ src_new, int64_t new_bs,
                                   int n, int B) {
+  pdl_prologue();
   const int64_t per_b = (int64_t)cA + n;
   const int64_t total = per_b * B;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -64,9 +66,8 @@ w2vs_status_t launch_concat_rows(void* dst, int64_t dst_bs_bytes, const void* sr
                "concat_rows alignment");
   const int64_t total = (int64_t)(cA + nB) * (row_bytes / 16) * B;
   if (total <= 0) return W2VS_OK;
-  concat_rows_kernel<<<grid_for(total), 256, 0, st>>>((uint4*)dst, dst_bs_bytes / 16, (const uint4*)srcA,
-                                                      a_bs_bytes / 16, offA, cA, (const uint4*)srcB,
-                                                      b_bs_bytes / 16, nB, row_bytes / 16, B);
+  launch_pdl(concat_rows_kernel, dim3(grid_for(total)), dim3(256), 0, st, (uint4*)dst, dst_bs_bytes / 16,
+             (const uint4*)srcA, a_bs_bytes / 16, offA, cA, (const uint4*)srcB, b_bs_bytes / 16, nB, row_bytes / 16, B);
   W2VS_CHECK_LAUNCH("concat_rows_kernel");
   return W2VS_OK;
 }
@@ -76,11 +77,11 @@ w2vs_status_t launch_concat_wav(float* dst, int64_t dst_bs, const float* srcA, i
   const int64_t total = ((int64_t)cA + n) * B;
   if (total <= 0) return W2VS_OK;
   if (new_dtype == W2VS_F32)
-    concat_wav_kernel<float><<<grid_for(total), 256, 0, st>>>(dst, dst_bs, srcA, a_bs, offA, cA, (const float*)src_new, new_bs, n, B);
+    launch_pdl(concat_wav_kernel<float>, dim3(grid_for(total)), dim3(256), 0, st, dst, dst_bs, srcA, a_bs, offA, cA, (const float*)src_new, new_bs, n, B);
   else if (new_dtype == W2VS_I16)   // 16-bit PCM chunks straight from the audio source (x / 32768)
-    concat_wav_kernel<int16_t><<<grid_for(total), 256, 0, st>>>(dst, dst_bs, srcA, a_bs, offA, cA, (const int16_t*)src_new, new_bs, n, B);
+    launch_pdl(concat_wav_kernel<int16_t>, dim3(grid_for(total)), dim3(256), 0, st, dst, dst_bs, srcA, a_bs, offA, cA, (const int16_t*)src_new, new_bs, n, B);
   else
-    concat_wav_kernel<bf16><<<grid_for(total), 256, 0, st>>>(dst, dst_bs, srcA, a_bs, offA, cA, (const bf16*)src_new, new_bs, n, B);
+    launch_pdl(concat_wav_kernel<bf16>, dim3(grid_for(total)), dim3(256), 0, st, dst, dst_bs, srcA, a_bs, offA, cA, (const bf16*)src_new, new_bs, n, B);
   W2VS_CHECK_LAUNCH("concat_wav_kernel");
   return W2VS_OK;
 }
