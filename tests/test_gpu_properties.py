@@ -85,3 +85,12 @@ def test_incremental_equals_full_utterance_at_30s(model):
     assert tuple(y.shape) == tuple(ref.shape)
     err = (y.float() - ref.float()).abs().max() / ref.float().abs().max()
     assert err < 2e-2, float(err)
+    # a second stream over the same audio gives the same bits (split-key attention merges its partial states in
+    # a fixed order; the completion counters only elect the CTA that does it)
+    st2 = model.open_stream(B=1, max_seconds=31, max_new_samples=7760 + 400)
+    outs2, pos = [], 0
+    while pos < L:
+        n = min(7760 if pos == 0 else 5120, L - pos)
+        outs2.append(st2.step(wav[:, pos:pos + n], EncoderStream.FINAL if pos + n >= L else EncoderStream.NONE))
+        pos += n
+    assert torch.equal(torch.cat(outs2, 0), y)
