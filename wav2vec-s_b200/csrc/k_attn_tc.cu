@@ -20,9 +20,11 @@
 //                          more than 2^8), exp2 (ex2.approx, part of it emulated on the FMA pipe), row sum, bf16 P
 //                          -> smem in the K-major 128B-swizzled operand layout; per item: O / l -> bf16 -> staged
 //                          in the P buffer -> TMA store.
-//   1 warp     MMA issuer  (one thread; it also issues the TMA loads, at the points where it has just observed that a
-//                          ring slot is free: S(g) retired -> K(g+2); PV(g) retired -> V(g+2); last S of an item
-//                          -> next Q -- no loader warp, no "empty" barriers)
+//   1 warp     MMA issuer  (one thread; it also issues the TMA loads -- no loader warp, no "empty" barriers: it
+//                          commits the MMAs that read a ring slot, so it knows when the slot is free.  The refills
+//                          are deferred by one step -- K's slot of S(g+1) after PV(g) has been issued, V's slot of
+//                          PV(g-1) at the start of tile g, the next Q after the item's last S -- so the thread never
+//                          waits for an MMA it has just issued)
 //                          S = Q K^T  (tcgen05.mma M=128,N=64,K=64: A,B K-major from smem -> TMEM cols 0..63)
 //                          O += P V   (M=128,N=64,K=64: A = bf16 P K-major from smem, B = V MN-major from smem
 //                          -> TMEM cols 64..127); owns the TMEM allocation.
