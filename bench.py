@@ -525,7 +525,7 @@ def main():
                 line["incremental"] = incremental_probe(model, cfg, dev)
             except Exception as ex:   # never lose the headline line to the secondary measurement
                 line["incremental"] = {"error": f"{type(ex).__name__}: {ex}"}
-        if not a.no_cpu_baseline:
+        if not a.no_cpu_baseline and world == 1:      # reported on rank 0 at N=1 only
             r = cpu_reference_run(kind, a.cpu_sample_batch, seconds, 2, 1)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
