@@ -52,11 +52,14 @@ constexpr int CHUNK = 32;                  // columns per epilogue chunk
 constexpr bool kTmaReduce = W2VS_GEMM_TMA_REDUCE != 0;
 constexpr int SMEM_LIMIT = 232448;
 
-template <int BN, typename TC> struct Cfg2 {
+// SLOTS: staging slots per epilogue warp.  Two let the residual chunk c+1 be loaded while chunk c is processed; one
+// frees 32 KB (fp32) for a fifth TMA ring stage -- used for the long-K in-place product (fc2, K = 4096), whose
+// epilogue has 4x the MMA time of a K = 1024 tile to hide in and whose mainloop streams its A operand from HBM.
+template <int BN, typename TC, int SLOTS = 2> struct Cfg2 {
   static constexpr int kBStageBytes = (BN / 2) * BK * 2;
   static constexpr int kStageBytes = A_STAGE_BYTES + kBStageBytes;
   static constexpr int kSlotBytes = 32 * CHUNK * (int)sizeof(TC);          // 4 KB fp32 / 2 KB bf16
-  static constexpr int kStagingBytes = N_EPI_WARPS * 2 * kSlotBytes;
+  static constexpr int kStagingBytes = N_EPI_WARPS * SLOTS * kSlotBytes;
   static constexpr int kMiscBytes = N_EPI_WARPS * (BN / 2) * 4 /*bias*/ + 512 /*barriers*/ + 1024 /*align*/;
   static constexpr int kStagesFit = (SMEM_LIMIT - kStagingBytes - kMiscBytes) / kStageBytes;
 #ifndef W2VS_GEMM_MAX_STAGES
@@ -72,12 +75,12 @@ template <int BN, typename TC> struct Cfg2 {
 
 using namespace tc;
 
-template <int BN, typename TC>
+template <int BN, typename TC, int SLOTS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int has_residual,
                 int M, int N, int K, int a_row_len, int gelu) {
-  using C2 = Cfg2<BN, TC>;
+  using C2 = Cfg2<BN, TC, SLOTS>;
   constexpr int S = C2::kStages;
   constexpr bool kF32 = sizeof(TC) == 4;
   extern __shared__ uint8_t smem_raw[];
@@ -176,7 +179,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int e = warp;                      // 0..7
     const int quarter = warp & 3;            // TMEM lanes this warp may touch: 32*quarter ..
     const int half = e >> 2;                 // column half of the tile
-    const uint32_t slot0 = sStage + (uint32_t)e * 2 * C2::kSlotBytes;
+    const uint32_t slot0 = sStage + (uint32_t)e * SLOTS * C2::kSlotBytes;
     const uint32_t my_res_bar = bar_res + 16 * e;
     const uint32_t tempty_leader = mapa(bar_tempty, 0);
     uint32_t res_phase = 0;                  // bit s = parity of residual slot s
@@ -194,7 +197,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
       for (int i = lane; i < BN / 2; i += 32) bs[i] = (bias != nullptr && colw + i < N) ? bias[colw + i] : 0.f;
       // residual chunk 0 prefetch (overlaps the wait for the accumulator)
-      if (!kTmaReduce && has_residual && lane == 0) {
+      if (SLOTS == 2 && !kTmaReduce && has_residual && lane == 0) {
         bulk_wait_read<0>();                           // earlier stores from slot 0/1 have been read out
         mbar_expect_tx(my_res_bar, C2::kSlotBytes);
         tma_load_2d(slot0, &tmC, my_res_bar, colw, row0);
@@ -207,9 +210,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * (BN / 2));
 #pragma unroll 1
       for (int c = 0; c < C2::kChunksPerWarp; ++c) {
-        const int sl = c & 1;
+        const int sl = c & (SLOTS - 1);
         const uint32_t slot = slot0 + sl * C2::kSlotBytes;
-        if (!kTmaReduce && has_residual) {
+        if (SLOTS == 1) {
+          // single slot: wait until the previous store has read it, then fetch this chunk's residual into it (the
+          // accumulator load and the bias arithmetic below run while it is in flight)
+          if (lane == 0) {
+            bulk_wait_read<0>();
+            if (!kTmaReduce && has_residual) {
+              mbar_expect_tx(my_res_bar, C2::kSlotBytes);
+              tma_load_2d(slot, &tmC, my_res_bar, colw + c * CHUNK, row0);
+            }
+          }
+        } else if (!kTmaReduce && has_residual) {
           if (c + 1 < C2::kChunksPerWarp && lane == 0) {
             bulk_wait_read<0>();                       // the store that used the other slot has drained it
             mbar_expect_tx(my_res_bar + 8 * (sl ^ 1), C2::kSlotBytes);
@@ -284,9 +297,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-template <int BN, typename TC>
+template <int BN, typename TC, int SLOTS = 2>
 w2vs_status_t launch_bn(const GemmArgs& g, cudaStream_t st) {
-  using C2 = Cfg2<BN, TC>;
+  using C2 = Cfg2<BN, TC, SLOTS>;
   alignas(64) CUtensorMap tmA, tmB, tmC;
   const int64_t a_row_len = g.lda;
   const uint64_t a_inner = (uint64_t)(g.K <= a_row_len ? g.K : a_row_len);
@@ -302,7 +315,7 @@ w2vs_status_t launch_bn(const GemmArgs& g, cudaStream_t st) {
                       CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_64B));
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, TC, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C2::kSmemBytes);
     if (e != cudaSuccess) { set_error("gemm_tc2 smem attribute: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
     attr_done = true;
@@ -312,7 +325,7 @@ w2vs_status_t launch_bn(const GemmArgs& g, cudaStream_t st) {
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   // plain stream launch: as a programmatic dependent (PDL) this kernel's 200 KB CTAs cannot become resident early
   // anyway, and 16-stream incremental steps measured 7 % slower with it
-  gemm_tc2_kernel<BN, TC><<<2 * clusters, N_THREADS, C2::kSmemBytes, st>>>(
+  gemm_tc2_kernel<BN, TC, SLOTS><<<2 * clusters, N_THREADS, C2::kSmemBytes, st>>>(
       tmA, tmB, tmC, g.bias, g.residual != nullptr ? 1 : 0, g.M, g.N, g.K, (int)a_row_len,
       (g.flags & W2VS_EPI_GELU) ? 1 : 0);
   if (g_prof_on) {
@@ -332,6 +345,11 @@ w2vs_status_t launch_typed(const GemmArgs& g, cudaStream_t st) {
   // streams) 256-wide tiles would leave most of the GPU idle while a handful of clusters stream all of W.
   const int64_t m_tiles = ceil_div64(g.M, 2 * BM);
   const int clusters = num_sms() / 2;
+#ifndef W2VS_GEMM_LONGK_SINGLE_SLOT
+#define W2VS_GEMM_LONGK_SINGLE_SLOT 1
+#endif
+  if (W2VS_GEMM_LONGK_SINGLE_SLOT && sizeof(TC) == 4 && g.K >= 2048 && g.N % 256 == 0 && m_tiles * (g.N / 256) >= clusters)
+    return launch_bn<256, TC, 1>(g, st);          // fp32 output, long K: five ring stages instead of four
   if (g.N % 256 == 0 && (m_tiles * (g.N / 256) >= clusters || g.N % 128 != 0)) return launch_bn<256, TC>(g, st);
   if (g.N % 128 == 0 && (m_tiles * (g.N / 128) >= clusters || g.N % 64 != 0)) return launch_bn<128, TC>(g, st);
   if (g.N % 64 == 0) return launch_bn<64, TC>(g, st);
