@@ -40,7 +40,14 @@ constexpr int N_THREADS = 64 + 32 * N_EPI_WARPS;
 // Warp roles.  The SMSP arbiter favours the highest warp id, and the TMA-producer / MMA-issuer threads sit on
 // the critical path of every stage, so they take the two highest ids; the epilogue warps are 0..7.
 constexpr int PRODUCER_WARP = N_EPI_WARPS, MMA_WARP = N_EPI_WARPS + 1;
-constexpr int CHUNK = 32;                  // columns per epilogue chunk
+// Columns per epilogue chunk: 32 for bf16 outputs; W2VS_GEMM_F32_CHUNK for fp32 outputs.  With 32 fp32 columns a
+// staging slot is 4 KB and only four TMA ring stages fit next to two slots per warp; 16 columns (2 KB slots, five
+// stages, still double buffered) was measured: the K = 4096 product gains what the single-slot variant below gains
+// (16.8 -> 14.8 ms per step), but the K = 1024 product loses to the doubled per-chunk overhead (5.4 -> 6.1 ms), so
+// the default is 32 plus W2VS_GEMM_LONGK_SINGLE_SLOT.
+#ifndef W2VS_GEMM_F32_CHUNK
+#define W2VS_GEMM_F32_CHUNK 32
+#endif
 // In-place residual (C += A.W^T + bias): true = the staged tile is added to C by the TMA reduction path
 // (cp.reduce.async.bulk.tensor .add, fp32 adds in L2) -- no residual load, no second pass through smem;
 // false = the residual chunk is TMA-loaded into the staging slot and added by the epilogue threads.
@@ -58,7 +65,8 @@ constexpr int SMEM_LIMIT = 232448;
 template <int BN, typename TC, int SLOTS = 2> struct Cfg2 {
   static constexpr int kBStageBytes = (BN / 2) * BK * 2;
   static constexpr int kStageBytes = A_STAGE_BYTES + kBStageBytes;
-  static constexpr int kSlotBytes = 32 * CHUNK * (int)sizeof(TC);          // 4 KB fp32 / 2 KB bf16
+  static constexpr int kChunk = sizeof(TC) == 4 ? W2VS_GEMM_F32_CHUNK : 32;
+  static constexpr int kSlotBytes = 32 * kChunk * (int)sizeof(TC);
   static constexpr int kStagingBytes = N_EPI_WARPS * SLOTS * kSlotBytes;
   static constexpr int kMiscBytes = N_EPI_WARPS * (BN / 2) * 4 /*bias*/ + 512 /*barriers*/ + 1024 /*align*/;
   static constexpr int kStagesFit = (SMEM_LIMIT - kStagingBytes - kMiscBytes) / kStageBytes;
@@ -68,7 +76,7 @@ template <int BN, typename TC, int SLOTS = 2> struct Cfg2 {
   static constexpr int kStages = kStagesFit > W2VS_GEMM_MAX_STAGES ? W2VS_GEMM_MAX_STAGES : kStagesFit;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kMiscBytes;
-  static constexpr int kChunksPerWarp = BN / 2 / CHUNK;
+  static constexpr int kChunksPerWarp = BN / 2 / kChunk;
   static_assert(BN == 64 || BN == 128 || BN == 256, "BN");
   static_assert(kStages >= 3, "pipeline too shallow");
 };
@@ -83,6 +91,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   using C2 = Cfg2<BN, TC, SLOTS>;
   constexpr int S = C2::kStages;
   constexpr bool kF32 = sizeof(TC) == 4;
+  constexpr int CHUNK = C2::kChunk;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
@@ -231,12 +240,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         } else if (lane == 0) {
           bulk_wait_read<1>();                         // the store issued two chunks ago (same slot) is done
         }
-        uint32_t r[32];
-        tmem_ld32(taddr + c * CHUNK, r);
+        uint32_t r[CHUNK];
+        tmem_ld_chunk<CHUNK>(taddr + c * CHUNK, r);
         tmem_ld_wait();
-        float v[32];
+        float v[CHUNK];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
+        for (int j = 0; j < CHUNK; j += 2) {
           const float2 bb = *reinterpret_cast<const float2*>(bs + c * CHUNK + j);   // smem broadcast
           unpack2(fadd2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), pack2(bb.x, bb.y)), v[j], v[j + 1]);
           if (gelu) gelu2<TC>(v[j], v[j + 1]);
@@ -247,11 +256,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         __syncwarp();                                  // lane 0's wait_group / everyone's mbarrier wait done
         if (kF32) {
-          // 128-byte rows, SWIZZLE_128B: 16-byte chunk j of row `lane` lives at chunk j ^ (lane & 7)
-          const uint32_t rowaddr = slot + lane * 128;
+          // CHUNK 32: 128-byte rows, SWIZZLE_128B: 16-byte chunk j of row `lane` lives at chunk j ^ (lane & 7)
+          // CHUNK 16:  64-byte rows, SWIZZLE_64B:  ... at chunk j ^ ((lane >> 1) & 3)
+          const uint32_t rowaddr = slot + lane * (CHUNK * 4);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t a = rowaddr + ((uint32_t)(j ^ (lane & 7)) << 4);
+          for (int j = 0; j < CHUNK / 4; ++j) {
+            const uint32_t a = rowaddr + ((uint32_t)(j ^ (CHUNK == 32 ? (lane & 7) : ((lane >> 1) & 3))) << 4);
             float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             if (!kTmaReduce && has_residual) {
               const uint4 rr = lds128(a);
@@ -264,7 +274,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           // 64-byte rows, SWIZZLE_64B: 16-byte chunk j of row `lane` lives at chunk j ^ ((lane >> 1) & 3)
           const uint32_t rowaddr = slot + lane * 64;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < CHUNK / 8; ++j) {
             const uint32_t a = rowaddr + ((uint32_t)(j ^ ((lane >> 1) & 3)) << 4);
             sts128(a, make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                                  pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7])));
@@ -309,10 +319,10 @@ w2vs_status_t launch_bn(const GemmArgs& g, cudaStream_t st) {
                     BN / 2, CU_TENSOR_MAP_SWIZZLE_128B));
   if (sizeof(TC) == 4)
     W2VS_TRY(make_map(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.C, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc,
-                      CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+                      C2::kChunk, 32, C2::kChunk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B));
   else
     W2VS_TRY(make_map(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.C, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc,
-                      CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+                      C2::kChunk, 32, CU_TENSOR_MAP_SWIZZLE_64B));
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, TC, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
