@@ -186,3 +186,31 @@ def test_sample_mask_and_lengths_agree_with_arbitrary_mask():
     yo, fmo = O.extract_features(sd, cfg, wav, pm)
     assert torch.equal(fm.cpu(), fmo)
     assert valid_rel_err(y.cpu(), yo, fmo.numpy()) < FP32_TOL
+
+
+@pytest.mark.parametrize("use_proj", [False, True])
+def test_online_encoder_wrapper_vs_oracle(use_proj):
+    """OnlineW2V2TransformerEncoder (unidirect_w2v2_encoder.py:534-607): checkpoint -> model, length-based masks,
+    optional encoder_proj, the rain output dict -- what the CAAT / SimulEval pipelines call."""
+    import argparse
+    from oracle import synth
+    cfg = cases.tiny(layer_norm_first=True, conv_bias=True)
+    sd = synth.make_state_dict(cfg, 31)
+    args = argparse.Namespace(main_context=8, right_context=4, encoder_embed_dim=96 if use_proj else 128,
+                              use_linear_layer=use_proj)
+    enc = W.OnlineW2V2TransformerEncoder(args, wav2vec_ckpt={"args": None, "cfg": {"model": dict(cfg)}, "model": sd})
+    enc = enc.cuda().eval()
+    B, L = 3, 9000
+    wav = synth.make_waveform(B, L, 32)
+    lens = synth.make_lengths(B, L, 33)
+    pm = O.lengths_to_padding_mask(lens)
+    wav = wav.masked_fill(pm, 0.0)
+    out = enc(wav.cuda(), lens.cuda())
+    y, fm = out["encoder_out"][0], out["encoder_padding_mask"][0]
+    ocfg = dict(cfg, main_context=8, right_context=4)
+    yo, fmo = O.rain_forward(sd, ocfg, wav, pm)
+    if use_proj:
+        yo = torch.nn.functional.linear(yo, enc.encoder_proj.weight.detach().cpu(), enc.encoder_proj.bias.detach().cpu())
+    assert torch.equal(fm.cpu(), fmo)
+    assert tuple(y.shape) == tuple(yo.shape)
+    assert valid_rel_err(y.detach().cpu(), yo, fmo.numpy(), time_first=True) < FP32_TOL
