@@ -684,8 +684,16 @@ class OnlineW2V2TransformerEncoder(nn.Module):
         output = self.w2v2_model(src_tokens, None, incremental_state, finished, is_infer,
                                  src_lengths=src_lengths, mask_len=mask_len)
         if self.use_linear_layer and self.encoder_proj is not None:
+            # unidirect_w2v2_encoder.py:590-594, through this library's GEMM (the step
+            # right after the path stays on the same kernels and the same stream)
+            from . import ops
+            x = output["encoder_out"][0]
+            T_, B_, D_ = x.shape
+            w = self.encoder_proj.weight.detach().to(x.dtype).contiguous()
+            y = ops.gemm(x.reshape(T_ * B_, D_), w, self.encoder_proj.bias.detach().float().contiguous(),
+                         out_dtype=x.dtype) if T_ * B_ > 0 else x.new_zeros((0, w.size(0)))
             output = dict(output)
-            output["encoder_out"] = [self.encoder_proj(output["encoder_out"][0])]
+            output["encoder_out"] = [y.view(T_, B_, w.size(0))]
         return output
 
     def forward_torchscript(self, net_input: Dict[str, torch.Tensor]):
