@@ -58,7 +58,7 @@ constexpr int NS = 2;                        // K ring and V ring depth
 constexpr int N_SOFTMAX_WARPS = 4;
 constexpr int N_THREADS = 160;               // warps 0-3 softmax, warp 4 MMA
 constexpr int CTAS_PER_SM = 3;
-constexpr int SMEM_BYTES = Q_BYTES + 2 * NS * KV_BYTES + P_BYTES + 256 /*barriers*/ + 1024 /*align*/;
+constexpr int SMEM_BYTES = Q_BYTES + 2 * NS * KV_BYTES + P_BYTES + 256 /*barriers*/ + 256 /*item ring*/ + 1024 /*align*/;
 constexpr uint32_t TMEM_COLS = 128, S_COL = 0, O_COL = 64;
 // barrier waits per role: parked (suspend-time hint) or spinning, see tc_common.cuh
 #ifndef W2VS_ATTN_MMA_PARK
@@ -248,6 +248,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t bar_qfull = bars, bar_kfull = bars + 8, bar_vfull = bar_kfull + 8 * NS, bar_sfull = bar_vfull + 8 * NS,
                  bar_sfree = bar_sfull + 8, bar_pfull = bar_sfree + 8, bar_pvdone = bar_pfull + 8;
   const uint32_t tmem_slot = bars + 96;
+  const uint32_t item_ring = bars + 256;                    // 8 x 32 bytes, used by the MMA thread only
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
   const int D = sh.D;
@@ -287,37 +288,55 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const uint64_t dQ = umma_desc_sw128(sQ), dK = umma_desc_sw128(sK), dV = umma_desc_mn_sw128(sV), dP = umma_desc_sw128(sP);
       bool ok = true;
       // ---- load cursor: (work item, tile in item, global tile index) of the next K tile and of the next V tile
-      struct Cur { Walker wk; int it, g, n_kt, n0, seg1, hcol, row; };
-      auto cur_item = [&](Cur& c) {
+      // One item_of() per work item: the K cursor runs ahead of everything else this thread does, so it computes
+      // the item's facts when it enters it and leaves them in a small shared-memory ring, keyed by the item's
+      // ordinal; the V cursor, the Q loads and the main loop look them up (this thread used to evaluate item_of
+      // four times per item, ~500 cycles each on a single lane).
+      struct ItemLite { int n_kt, n0, seg1, hcol, row, q_first, pad0, pad1; };
+      ItemLite* ring = reinterpret_cast<ItemLite*>(gen_base + (item_ring - smem_base));
+      struct Cur { Walker wk; int it, g, ord; ItemLite f; };
+      auto enter_k = [&](Cur& c) {                      // K cursor only: compute and publish
         if (c.wk.w < n_items) {
           const Item ci = item_of(sh, c.wk);
-          c.n_kt = ci.ts.n_kt; c.n0 = ci.ts.n0; c.seg1 = ci.ts.seg1_begin; c.hcol = ci.h * HD; c.row = ci.row_base;
+          c.f.n_kt = ci.ts.n_kt; c.f.n0 = ci.ts.n0; c.f.seg1 = ci.ts.seg1_begin; c.f.hcol = ci.h * HD;
+          c.f.row = ci.row_base; c.f.q_first = ci.q_first; c.f.pad0 = c.f.pad1 = 0;
+          ring[c.ord & 7] = c.f;
         }
       };
-      auto load_kv = [&](Cur& c, uint32_t bar0, uint32_t smem0, int col0) {   // tile c.g -> ring slot c.g % NS
+      auto enter_v = [&](Cur& c) { if (c.wk.w < n_items) c.f = ring[c.ord & 7]; };
+      auto load_k = [&](Cur& c) {                       // tile c.g -> ring slot c.g % NS
         if (c.wk.w >= n_items) return;
-        const int k0 = c.it < c.n0 ? c.it * KT : c.seg1 + (c.it - c.n0) * KT;
+        const int k0 = c.it < c.f.n0 ? c.it * KT : c.f.seg1 + (c.it - c.f.n0) * KT;
         const int sl = c.g % NS;
-        mbar_expect_tx(bar0 + 8 * sl, KV_BYTES);
-        tma_load_2d(smem0 + sl * KV_BYTES, &tmKV, bar0 + 8 * sl, col0 + c.hcol, c.row + k0);
+        mbar_expect_tx(bar_kfull + 8 * sl, KV_BYTES);
+        tma_load_2d(sK + sl * KV_BYTES, &tmKV, bar_kfull + 8 * sl, D + c.f.hcol, c.f.row + k0);
         ++c.g;
-        if (++c.it == c.n_kt) { c.it = 0; c.wk.next(sh); cur_item(c); }
+        if (++c.it == c.f.n_kt) { c.it = 0; c.wk.next(sh); ++c.ord; enter_k(c); }
       };
-      auto load_q = [&](const Walker& wq) {
+      auto load_v = [&](Cur& c) {
+        if (c.wk.w >= n_items) return;
+        const int k0 = c.it < c.f.n0 ? c.it * KT : c.f.seg1 + (c.it - c.f.n0) * KT;
+        const int sl = c.g % NS;
+        mbar_expect_tx(bar_vfull + 8 * sl, KV_BYTES);
+        tma_load_2d(sV + sl * KV_BYTES, &tmKV, bar_vfull + 8 * sl, 2 * D + c.f.hcol, c.f.row + k0);
+        ++c.g;
+        if (++c.it == c.f.n_kt) { c.it = 0; c.wk.next(sh); ++c.ord; enter_v(c); }
+      };
+      auto load_q = [&](const Walker& wq, int ord) {    // the K cursor has entered this item already
         if (wq.w >= n_items) return;
-        const Item q = item_of(sh, wq);
+        const ItemLite q = ring[ord & 7];
         mbar_expect_tx(bar_qfull, Q_BYTES);
-        tma_load_2d(sQ, &tmQ, bar_qfull, q.h * HD, q.row_base + q.q_first);
+        tma_load_2d(sQ, &tmQ, bar_qfull, q.hcol, q.row + q.q_first);
       };
       Cur ck, cv;
-      ck.wk.init(sh, vcta); ck.it = 0; ck.g = 0; cur_item(ck);
+      ck.wk.init(sh, vcta); ck.it = 0; ck.g = 0; ck.ord = 0; enter_k(ck);
       cv = ck;
       Walker wk, wnext;                  // this item / the next one (whose Q is loaded ahead)
       wk.init(sh, vcta);
       wnext = wk;
-      load_q(wnext);
+      load_q(wnext, 0);
       wnext.next(sh);
-      for (int i = 0; i < NS; ++i) { load_kv(ck, bar_kfull, sK, D); load_kv(cv, bar_vfull, sV, 2 * D); }
+      for (int i = 0; i < NS; ++i) { load_k(ck); load_v(cv); }
 
       auto issue_s = [&](int g) {     // S(g) = Q K(g)^T
         const int sl = g % NS;
@@ -338,23 +357,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       int gt = 0, wi = 0;
       bool pending_v = false;            // PV(g-1) has been issued and its V slot is not refilled yet
       for (; wk.w < n_items && ok; wk.next(sh), wnext.next(sh), ++wi) {
-        const Item im = item_of(sh, wk);
-        const int n = im.ts.n_kt;
+        const int n = ring[wi & 7].n_kt;
         if (!(ok = MMA_WAIT(bar_qfull, wi & 1))) break;
         if (gt > 0 && !(ok = MMA_WAIT(bar_sfree, (gt - 1) & 1))) break;   // softmax has read the previous item's last S
         tc_fence_after();
         if (!(ok = issue_s(gt))) break;
         if (n == 1) {     // the item's only S: once it has retired, K's slot and Q are free
           if (!(ok = MMA_WAIT(bar_sfull, gt & 1))) break;
-          load_kv(ck, bar_kfull, sK, D);
-          load_q(wnext);
+          load_k(ck);
+          load_q(wnext, wi + 1);
         }
         for (int it = 0; it < n && ok; ++it) {
           const int g = gt + it;
           TRACE(1, g, 0);
           if (it == 0 && n > 1) {   // S(g) of the item's first tile was issued above: free its K slot when it retires
             if (!(ok = MMA_WAIT(bar_sfull, g & 1))) break;
-            load_kv(ck, bar_kfull, sK, D);
+            load_k(ck);
           }
           if (it + 1 < n) {
             if (!(ok = MMA_WAIT(bar_sfree, g & 1))) break;          // softmax holds S(g) in registers
@@ -365,7 +383,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
           if (pending_v) {
             if (!(ok = MMA_WAIT(bar_pvdone, (g - 1) & 1))) break;     // PV(g-1) retired a tile ago: V's slot is free
-            load_kv(cv, bar_vfull, sV, 2 * D);                         // V(g+1)
+            load_v(cv);                                                // V(g+1)
             pending_v = false;
           }
           const int sl = g % NS;
@@ -383,8 +401,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           TRACE(1, g, 5);
           if (it + 1 < n) {
             if (!(ok = MMA_WAIT(bar_sfull, (g + 1) & 1))) break;    // S(g+1), issued before PV(g), has retired
-            load_kv(ck, bar_kfull, sK, D);                             // K(g+1+NS)
-            if (it + 2 == n) load_q(wnext);                            // it was the item's last S: Q is free
+            load_k(ck);                                                // K(g+1+NS)
+            if (it + 2 == n) load_q(wnext, wi + 1);                    // it was the item's last S: Q is free
             TRACE(1, g, 6);
           }
           TRACE(1, g, 7);
