@@ -372,7 +372,7 @@ w2vs_status_t launch_typed(const GemmArgs& g, cudaStream_t st) {
   // bf16 output with GELU (fc1), full-width tiles: 16 epilogue warps (four per TMEM lane quarter) with one staging
   // slot each -- the accumulator drain (bias, GELU, pack, store) paces this product and more warps hide its
   // latencies: 16.7 -> 15.8 ms per step (same-box A/B); the bias-only QKV product is 2 % slower with 16, so it
-  // keeps 8.
+  // keeps 8, and so does the fp32 + residual K = 1024 product (5.5 -> 5.75 ms with 16 warps and one slot each).
   if (W2VS_GEMM_BF16_EPI_WARPS == 16 && sizeof(TC) == 2 && (g.flags & W2VS_EPI_GELU) && g.N % 256 == 0 &&
       m_tiles * (g.N / 256) >= clusters)
     return launch_bn<256, TC, 1, 16>(g, st);
