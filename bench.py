@@ -33,6 +33,7 @@ WORKLOADS = {
     # name: (model, B per GPU, seconds)
     "large_64x20s": ("large", 64, 20),
     "base_32x15s": ("base", 32, 15),
+    "base_posconv_32x15s": ("base_posconv", 32, 15),   # same model with the wav2vec 2.0 convolutional positions
     "large_64x30s": ("large", 64, 30),
     "large_8x20s": ("large", 8, 20),
     "tiny_4x2s": ("tiny", 4, 2),
@@ -49,6 +50,8 @@ def model_cfg(kind):
         return dict(extractor_mode="layer_norm", encoder_layers=24, encoder_embed_dim=1024,
                     encoder_ffn_embed_dim=4096, encoder_attention_heads=16, layer_norm_first=True,
                     conv_bias=True, pos_type="sin", main_context=16, right_context=8)
+    if kind == "base_posconv":
+        return dict(model_cfg("base"), pos_type="conv", conv_pos=128, conv_pos_groups=16)
     if kind == "base":
         return dict(extractor_mode="layer_norm", encoder_layers=12, encoder_embed_dim=768,
                     encoder_ffn_embed_dim=3072, encoder_attention_heads=12, layer_norm_first=False,
@@ -90,9 +93,12 @@ def flops_per_utt(cfg, L):
     proj = 2.0 * cin * D * T if cin != D else 0.0
     linear = Ly * M * (8.0 * D * D + 4.0 * D * F)
     attn = Ly * 4.0 * D * P
-    gemm = (conv - 2.0 * spec[0][0] * spec[0][1] * lens[0]) + proj + linear   # what the GEMM kernel executes
-    return dict(total=conv + proj + linear + attn, conv=conv, proj=proj, linear=linear, attn=attn,
-                gemm=gemm, T=T, M=M)
+    posconv = 0.0
+    if cfg.get("pos_type") == "conv":   # grouped Conv1d(D, D, k, groups), SURVEY.md section 8(d)
+        posconv = 2.0 * D * (D // cfg["conv_pos_groups"]) * cfg["conv_pos"] * T
+    gemm = (conv - 2.0 * spec[0][0] * spec[0][1] * lens[0]) + proj + linear + posconv   # what the GEMM kernel executes
+    return dict(total=conv + proj + linear + attn + posconv, conv=conv, proj=proj, linear=linear, attn=attn,
+                posconv=posconv, gemm=gemm, T=T, M=M)
 
 
 class ClockSampler:

@@ -118,6 +118,9 @@ w2vs_status_t w2vs_weights_pack(const w2vs_config* cfg, const void* const* d_ref
     const float* g = next();
     const float* v = next();
     W2VS_TRY(launch_pack_posconv(g, v, at<float>(d_packed, wl.posconv_w), D, cfg->conv_pos_groups, cfg->conv_pos, st));
+    if (posconv_tc(cfg))
+      W2VS_TRY(launch_pack_posconv_tc(at<float>(d_packed, wl.posconv_w), at<void>(d_packed, wl.posconv_wg), D,
+                                      cfg->conv_pos_groups, cfg->conv_pos, posconv_dgp(cfg), st));
   }
   const size_t as = act_size(cfg);
   for (int n = 0; n < cfg->layers; ++n) {
@@ -292,7 +295,27 @@ w2vs_status_t w2vs_encode(const w2vs_config* cfg, const void* d_packed, const w2
   void* Xa = at<void>(d_ws, ws.xa);
   {
     const float* posconv = nullptr;
-    if (cfg->pos_type == W2VS_POS_CONV) {
+    int posconv_rows = 0;
+    if (posconv_tc(cfg)) {
+      // grouped Conv1d(D, D, k, groups) + SamePad + GELU (wav2vec2.py:791-804) as one implicit GEMM per group on the
+      // tcgen05 kernel: bias and GELU in its epilogue, fp32 result rows b*Tp + t read by embed_tokens below
+      const int k = cfg->conv_pos, groups = cfg->conv_pos_groups, Dg = D / groups, Dgp = posconv_dgp(cfg);
+      const int Tp = g.T + k;
+      const int64_t rows_tot = (int64_t)B * Tp + k;
+      bf16* xg = at<bf16>(d_ws, ws.posconv_xg);
+      float* out = at<float>(d_ws, ws.posconv_tmp);
+      W2VS_TRY(launch_posconv_pack_x(feats, rows_last, frame_pad, xg, B, g.T, D, k, groups, Dgp, st));
+      for (int grp = 0; grp < groups; ++grp) {
+        GemmArgs ga{};
+        ga.A = xg + (size_t)grp * rows_tot * Dgp; ga.lda = Dgp; ga.a_rows = rows_tot;
+        ga.W = at<bf16>(W, wl.posconv_wg) + (size_t)grp * Dg * k * Dgp;
+        ga.bias = at<float>(W, wl.posconv_b) + grp * Dg; ga.residual = nullptr;
+        ga.C = out + grp * Dg; ga.ldc = D; ga.M = (B - 1) * Tp + g.T; ga.N = Dg; ga.K = k * Dgp;
+        ga.dtype_ab = W2VS_BF16; ga.dtype_c = W2VS_F32; ga.flags = W2VS_EPI_GELU;
+        W2VS_TRY(launch_gemm(W2VS_GEMM_TCGEN05_2CTA, ga, st));
+      }
+      posconv = out; posconv_rows = Tp;
+    } else if (cfg->pos_type == W2VS_POS_CONV) {
       PosConvArgs pc{};
       pc.feats = feats; pc.feat_rows = rows_last; pc.frame_pad = frame_pad;
       pc.w = at<float>(W, wl.posconv_w); pc.bias = at<float>(W, wl.posconv_b);
@@ -303,7 +326,7 @@ w2vs_status_t w2vs_encode(const w2vs_config* cfg, const void* d_packed, const w2
     }
     EmbedArgs e{};
     e.feats = feats; e.feat_rows = rows_last; e.frame_pad = frame_pad; e.pos = pos; e.pos_offset = 0;
-    e.sin_table = at<float>(W, wl.sin_table); e.posconv = posconv;
+    e.sin_table = at<float>(W, wl.sin_table); e.posconv = posconv; e.posconv_rows = posconv_rows;
     e.gamma = cfg->layer_norm_first ? nullptr : at<float>(W, wl.enc_ln_w);
     e.beta = cfg->layer_norm_first ? nullptr : at<float>(W, wl.enc_ln_b);
     e.X = X; e.Xa = Xa; e.act_dtype = adt;

@@ -376,6 +376,7 @@ w2vs_status_t launch_typed(const GemmArgs& g, cudaStream_t st) {
   if (W2VS_GEMM_BF16_EPI_WARPS == 16 && sizeof(TC) == 2 && (g.flags & W2VS_EPI_GELU) && g.N % 256 == 0 &&
       m_tiles * (g.N / 256) >= clusters)
     return launch_bn<256, TC, 1, 16>(g, st);
+  if (g.N <= 64) return launch_bn<64, TC>(g, st);   // one group of the positional conv (N = D / groups = 48 or 64)
   if (g.N % 256 == 0 && (m_tiles * (g.N / 256) >= clusters || g.N % 128 != 0)) return launch_bn<256, TC>(g, st);
   if (g.N % 128 == 0 && (m_tiles * (g.N / 128) >= clusters || g.N % 64 != 0)) return launch_bn<128, TC>(g, st);
   if (g.N % 64 == 0) return launch_bn<64, TC>(g, st);

@@ -75,6 +75,45 @@ posconv_kernel(const float* __restrict__ feats, int feat_rows, const uint8_t* __
     out[((size_t)b * T + t) * D + grp * Dg + cog] = gelu_erf(acc);
   }
 }
+
+// ---- tensor-core path of the positional conv (bf16 models) --------------------------------------------------------
+// Group g is the implicit GEMM  out[b*Tp + t, g*Dg + o] = sum_{j<k, i<Dgp} xg[g][b*Tp + t + j][i] * wg[g][o][j*Dgp + i]:
+// with the group's channels stored contiguously per frame, row m of the A operand is the k*Dgp contiguous elements
+// starting at frame m (the wrapped-row view the conv stack uses, lda = Dgp < K = k*Dgp), and the k/2 zero frames in
+// front of every utterance are SamePad's padding.
+//
+// folded fp32 weights [grp][j][ci][cog] -> bf16 [grp][cog][j*Dgp + ci], zero for ci >= Dg
+__global__ void pack_posconv_tc_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int Dg, int Dgp,
+                                       int groups, int k) {
+  const int64_t n = (int64_t)groups * Dg * k * Dgp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Dgp);
+    const int j = (int)((i / Dgp) % k);
+    const int cog = (int)((i / ((int64_t)Dgp * k)) % Dg);
+    const int grp = (int)(i / ((int64_t)Dgp * k * Dg));
+    dst[i] = ci < Dg ? from_f32<bf16>(w[(((size_t)grp * k + j) * Dg + ci) * Dg + cog]) : from_f32<bf16>(0.f);
+  }
+}
+
+// xg[grp][b*Tp + u][c] = x[b, u - k/2, grp*Dg + c] for a real, unpadded frame and c < Dg, else 0; 8 channels per thread
+__global__ void posconv_pack_x_kernel(const float* __restrict__ feats, int feat_rows,
+                                      const uint8_t* __restrict__ frame_pad, uint4* __restrict__ xg, int B, int T,
+                                      int Tp, int D, int Dg, int Dgp, int k, int64_t rows_tot, int64_t total) {
+  const int v_per_row = Dgp / 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % v_per_row) * 8;
+    const int64_t row = (i / v_per_row) % rows_tot;
+    const int grp = (int)(i / ((int64_t)v_per_row * rows_tot));
+    const int b = (int)(row / Tp), t = (int)(row % Tp) - k / 2;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (b < B && t >= 0 && t < T && c < Dg && !(frame_pad != nullptr && frame_pad[(size_t)b * T + t])) {
+      const float4* src = reinterpret_cast<const float4*>(feats + ((size_t)b * feat_rows + t) * D + grp * Dg + c);
+      const float4 lo = src[0], hi = src[1];
+      o = make_uint4(pack_bf16x2(lo.x, lo.y), pack_bf16x2(lo.z, lo.w), pack_bf16x2(hi.x, hi.y), pack_bf16x2(hi.z, hi.w));
+    }
+    xg[i] = o;
+  }
+}
 }  // namespace
 
 static int grid_for(int64_t n) {
@@ -103,6 +142,26 @@ w2vs_status_t launch_pack_posconv(const float* g, const float* v, float* dst, in
                                   cudaStream_t st) {
   pack_posconv_kernel<<<k, 256, 0, st>>>(g, v, dst, D, groups, k);
   W2VS_CHECK_LAUNCH("pack_posconv_kernel");
+  return W2VS_OK;
+}
+
+w2vs_status_t launch_pack_posconv_tc(const float* w_folded, void* dst, int D, int groups, int k, int Dgp,
+                                     cudaStream_t st) {
+  const int Dg = D / groups;
+  pack_posconv_tc_kernel<<<grid_for((int64_t)groups * Dg * k * Dgp), 256, 0, st>>>(w_folded, (bf16*)dst, Dg, Dgp, groups, k);
+  W2VS_CHECK_LAUNCH("pack_posconv_tc_kernel");
+  return W2VS_OK;
+}
+
+w2vs_status_t launch_posconv_pack_x(const float* feats, int feat_rows, const uint8_t* frame_pad, void* xg, int B,
+                                    int T, int D, int k, int groups, int Dgp, cudaStream_t st) {
+  const int Dg = D / groups, Tp = T + k;
+  W2VS_REQUIRE(Dg % 8 == 0 && Dgp % 64 == 0 && Dgp >= Dg, "positional conv group width");
+  const int64_t rows_tot = (int64_t)B * Tp + k;
+  const int64_t total = (int64_t)groups * rows_tot * (Dgp / 8);
+  posconv_pack_x_kernel<<<grid_for(total), 256, 0, st>>>(feats, feat_rows, frame_pad, (uint4*)xg, B, T, Tp, D, Dg, Dgp, k,
+                                                        rows_tot, total);
+  W2VS_CHECK_LAUNCH("posconv_pack_x_kernel");
   return W2VS_OK;
 }
 

@@ -331,7 +331,7 @@ template <typename TAct, int NCH>
 __global__ void __launch_bounds__(256)
 embed_tokens_kernel(const float* __restrict__ feats, int feat_rows, const uint8_t* __restrict__ frame_pad,
                     const int32_t* __restrict__ pos, int pos_offset, const float* __restrict__ sin_table,
-                    const float* __restrict__ posconv, const float* __restrict__ gamma,
+                    const float* __restrict__ posconv, int posconv_rows, const float* __restrict__ gamma,
                     const float* __restrict__ beta, float* __restrict__ X, TAct* __restrict__ Xa,
                     int B, int T, int T2, int M, int main_ctx, int rc, int D) {
   pdl_prologue();
@@ -357,7 +357,7 @@ embed_tokens_kernel(const float* __restrict__ feats, int feat_rows, const uint8_
         if (!pad) load8(feats + ((size_t)b * feat_rows + t) * D + c0, v[j]);
         float p[8];
         if (posconv) {
-          load8(posconv + ((size_t)b * T + t) * D + c0, p);
+          load8(posconv + ((size_t)b * posconv_rows + t) * D + c0, p);
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[j][e] += p[e];
         } else if (!pad) {
@@ -386,7 +386,7 @@ static w2vs_status_t embed_dispatch(const EmbedArgs& a, cudaStream_t st) {
   dim3 grid((unsigned)ceil_div64((int64_t)a.B * a.M, wpb));
 #define W2VS_EMB_CASE(NCH)                                                                        \
   launch_pdl(embed_tokens_kernel<TAct, NCH>, grid, dim3(wpb * 32), 0, st,                         \
-             a.feats, a.feat_rows, a.frame_pad, a.pos, a.pos_offset, a.sin_table, a.posconv, a.gamma, \
+             a.feats, a.feat_rows, a.frame_pad, a.pos, a.pos_offset, a.sin_table, a.posconv, a.posconv_rows > 0 ? a.posconv_rows : a.T, a.gamma, \
              a.beta, a.X, (TAct*)a.Xa, a.B, a.T, a.T2, a.M, a.main_ctx, a.rc, a.D)
   if (a.D <= 256) W2VS_EMB_CASE(1);
   else if (a.D <= 512) W2VS_EMB_CASE(2);

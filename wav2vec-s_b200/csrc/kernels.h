@@ -44,6 +44,7 @@ struct EmbedArgs {
   const float* feats; int feat_rows;          // [B*feat_rows, D]
   const uint8_t* frame_pad; const int32_t* pos; int pos_offset;
   const float* sin_table; const float* posconv;
+  int posconv_rows;                           // rows per utterance of `posconv` (0: T)
   const float *gamma, *beta;                  // encoder.layer_norm when post-LN, else NULL
   float* X; void* Xa; int act_dtype;
   int B, T, T2, M, main_ctx, rc, D;
@@ -119,6 +120,12 @@ struct PosConvArgs {
   int B, T, D, k, groups;
 };
 w2vs_status_t launch_posconv(const PosConvArgs& a, cudaStream_t st);
+// tensor-core path: group-major bf16 copy of the (padding-zeroed) frames, one [rows_tot][Dgp] matrix per group with
+// k/2 zero rows in front of every utterance (Tp = T + k rows per utterance), and the matching weight operand
+w2vs_status_t launch_posconv_pack_x(const float* feats, int feat_rows, const uint8_t* frame_pad, void* xg, int B,
+                                    int T, int D, int k, int groups, int Dgp, cudaStream_t st);
+w2vs_status_t launch_pack_posconv_tc(const float* w_folded, void* dst, int D, int groups, int k, int Dgp,
+                                     cudaStream_t st);
 
 w2vs_status_t launch_pack_copy(const float* src, void* dst, int dst_dtype, int64_t n, cudaStream_t st);
 w2vs_status_t launch_pack_conv(const float* src, void* dst, int dst_dtype, int C_out, int C_in, int k,

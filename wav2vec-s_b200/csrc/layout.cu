@@ -191,12 +191,13 @@ void make_weight_layout(const w2vs_config* cfg, WeightLayout* wl) {
   } else {
     wl->proj_w = wl->proj_b = kNone;
   }
-  wl->sin_table = wl->posconv_w = wl->posconv_b = kNone;
+  wl->sin_table = wl->posconv_w = wl->posconv_b = wl->posconv_wg = kNone;
   if (cfg->pos_type == W2VS_POS_SIN) {
     wl->sin_table = b.take((size_t)cfg->sin_rows * D * 4);
   } else {
     wl->posconv_w = b.take((size_t)D * (D / cfg->conv_pos_groups) * cfg->conv_pos * 4);
     wl->posconv_b = b.take((size_t)D * 4);
+    if (posconv_tc(cfg)) wl->posconv_wg = b.take((size_t)D * cfg->conv_pos * posconv_dgp(cfg) * 2);
   }
   wl->enc_ln_w = b.take((size_t)D * 4);
   wl->enc_ln_b = b.take((size_t)D * 4);
@@ -248,7 +249,14 @@ void make_workspace(const w2vs_config* cfg, const Geometry& g, int B, Workspace*
   ws->qkv = b.take(tok * 3 * D * as);
   ws->ctx = b.take(tok * D * as);
   ws->h = b.take(tok * F * as);
-  ws->posconv_tmp = cfg->pos_type == W2VS_POS_CONV ? b.take((size_t)B * g.T * D * 4) : kNone;
+  ws->posconv_tmp = ws->posconv_xg = kNone;
+  if (posconv_tc(cfg)) {
+    const size_t tp = (size_t)g.T + cfg->conv_pos;
+    ws->posconv_tmp = b.take(B * tp * D * 4);
+    ws->posconv_xg = b.take((size_t)cfg->conv_pos_groups * (B * tp + cfg->conv_pos) * posconv_dgp(cfg) * 2);
+  } else if (cfg->pos_type == W2VS_POS_CONV) {
+    ws->posconv_tmp = b.take((size_t)B * g.T * D * 4);
+  }
   ws->total = b.off;
 }
 

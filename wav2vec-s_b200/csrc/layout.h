@@ -43,7 +43,8 @@ struct WeightLayout {
   size_t feat_ln_w, feat_ln_b;     // layer_norm [C_last]
   size_t proj_w, proj_b;           // act [D][C_last], fp32 [D]; SIZE_MAX if C_last == D
   size_t sin_table;                // fp32 [sin_rows][D]
-  size_t posconv_w, posconv_b;     // fp32 [groups][k][Dg_out][Dg_in] folded weight-norm, fp32 [D]
+  size_t posconv_w, posconv_b;     // fp32 [groups][k][Dg_in][Dg_out] folded weight-norm, fp32 [D]
+  size_t posconv_wg;               // bf16 [groups][Dg_out][k * Dgp] tensor-core operand (posconv_tc() only), else SIZE_MAX
   size_t enc_ln_w, enc_ln_b;       // encoder.layer_norm
   size_t layers_begin;             // LayerW table is computed by layer_at()
   size_t layer_stride;
@@ -75,11 +76,19 @@ struct Workspace {
   size_t qkv;                  // act [B*M][3D]
   size_t ctx;                  // act [B*M][D]
   size_t h;                    // act [B*M][F]
-  size_t posconv_tmp;          // fp32 [B][T][D]  (pos_type=conv only)
+  size_t posconv_tmp;          // fp32 [B][T][D], or [B * (T + k)][D] on the tensor-core path  (pos_type=conv only)
+  size_t posconv_xg;           // bf16 [groups][B * (T + k) + k][Dgp] group-major, zero-padded conv input (posconv_tc())
   size_t total;
 };
 void make_workspace(const w2vs_config* cfg, const Geometry& g, int B, Workspace* ws);
 
 inline size_t act_size(const w2vs_config* cfg) { return cfg->dtype == W2VS_BF16 ? 2 : 4; }
+
+// Positional conv (pos_type = conv) on the tensor cores: bf16 models whose group width is a multiple of 8.
+// Each group is an implicit GEMM over a group-major copy of the frames, channels padded to Dgp (multiple of 64).
+inline bool posconv_tc(const w2vs_config* cfg) {
+  return cfg->pos_type == W2VS_POS_CONV && cfg->dtype == W2VS_BF16 && (cfg->embed_dim / cfg->conv_pos_groups) % 8 == 0;
+}
+inline int posconv_dgp(const w2vs_config* cfg) { return (cfg->embed_dim / cfg->conv_pos_groups + 63) / 64 * 64; }
 
 }  // namespace w2vs
