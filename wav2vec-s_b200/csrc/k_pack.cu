@@ -1,6 +1,7 @@
 // Weight repacking (run once per load_state_dict) and the optional convolutional positional
-// embedding (pos_type="conv": wav2vec2.py:791-804; not used by the released wav2vec-S models, kept for
-// API completeness as a straightforward direct kernel).
+// embedding (pos_type="conv": wav2vec2.py:791-804; not used by the released wav2vec-S models): a direct fp32
+// kernel for the fp32 parity mode, and the operand packing of the tensor-core path (bf16 models), where every
+// group is an implicit GEMM on the tcgen05 kernel (api.cu).
 #include "common.cuh"
 #include "kernels.h"
 
