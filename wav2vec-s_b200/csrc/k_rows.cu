@@ -84,54 +84,72 @@ layernorm_rows_kernel(const TIn* x, int64_t ldx, const float* __restrict__ gamma
 // bf16 -> LayerNorm -> GELU -> bf16 (the conv blocks' Fp32LayerNorm + GELU, in place over the GEMM output): same
 // arithmetic as the generic kernel (fp32, mean first, then centred squares) on packed f32x2 pairs -- 8.5 issued
 // instructions per element instead of 14; the generic kernel was issue bound at 79 % on these passes (ncu).
+// Each warp normalises LG_ROWS rows at once: all of their loads are issued before the first reduction, which doubles
+// the bytes in flight per SM (one 1 KB row per warp kept these passes at 5 of 6.5 TB/s, latency bound).
+#ifndef W2VS_LN_GELU_ROWS
+#define W2VS_LN_GELU_ROWS 2
+#endif
+constexpr int LG_ROWS = W2VS_LN_GELU_ROWS;
 template <int NCH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NCH <= 2 ? 4 : 2)
 ln_gelu_bf16_kernel(const bf16* x, int64_t ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
                     bf16* out, int64_t ldo, int rows) {
   pdl_prologue();
   constexpr int N = NCH * 256;
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  uint64_t p[NCH][4];
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * LG_ROWS;
+  if (row0 >= rows) return;
+  uint64_t p[LG_ROWS][NCH][4];
 #pragma unroll
-  for (int j = 0; j < NCH; ++j) {
-    const uint4 u = *reinterpret_cast<const uint4*>(x + (size_t)row * ldx + (lane + 32 * j) * 8);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  for (int r = 0; r < LG_ROWS; ++r) {
+    const int row = min(row0 + r, rows - 1);          // a tail warp recomputes the last row and drops the result
 #pragma unroll
-    for (int e = 0; e < 4; ++e) p[j][e] = pack2(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));
+    for (int j = 0; j < NCH; ++j) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + (size_t)row * ldx + (lane + 32 * j) * 8);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) p[r][j][e] = pack2(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));
+    }
   }
-  uint64_t s2 = pack2(0.f, 0.f);
+  uint64_t rs2[LG_ROWS];
 #pragma unroll
-  for (int j = 0; j < NCH; ++j)
+  for (int r = 0; r < LG_ROWS; ++r) {
+    uint64_t s2 = pack2(0.f, 0.f);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) s2 = fadd2(s2, p[j][e]);
-  float sa, sb;
-  unpack2(s2, sa, sb);
-  const float mean = warp_sum(sa + sb) * (1.0f / N);
-  const uint64_t nm2 = pack2(-mean, -mean);
-  uint64_t q2 = pack2(0.f, 0.f);
+    for (int j = 0; j < NCH; ++j)
 #pragma unroll
-  for (int j = 0; j < NCH; ++j)
+      for (int e = 0; e < 4; ++e) s2 = fadd2(s2, p[r][j][e]);
+    float sa, sb;
+    unpack2(s2, sa, sb);
+    const float mean = warp_sum(sa + sb) * (1.0f / N);
+    const uint64_t nm2 = pack2(-mean, -mean);
+    uint64_t q2 = pack2(0.f, 0.f);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { p[j][e] = fadd2(p[j][e], nm2); q2 = ffma2(p[j][e], p[j][e], q2); }
-  unpack2(q2, sa, sb);
-  const float rstd = 1.0f / sqrtf(warp_sum(sa + sb) * (1.0f / N) + 1e-5f);
-  const uint64_t rs2 = pack2(rstd, rstd);
+    for (int j = 0; j < NCH; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { p[r][j][e] = fadd2(p[r][j][e], nm2); q2 = ffma2(p[r][j][e], p[r][j][e], q2); }
+    unpack2(q2, sa, sb);
+    const float rstd = 1.0f / sqrtf(warp_sum(sa + sb) * (1.0f / N) + 1e-5f);
+    rs2[r] = pack2(rstd, rstd);
+  }
 #pragma unroll
   for (int j = 0; j < NCH; ++j) {
     const int c0 = (lane + 32 * j) * 8;
     const ulonglong2 g01 = *reinterpret_cast<const ulonglong2*>(gamma + c0), g23 = *reinterpret_cast<const ulonglong2*>(gamma + c0 + 4);
     const ulonglong2 b01 = *reinterpret_cast<const ulonglong2*>(beta + c0), b23 = *reinterpret_cast<const ulonglong2*>(beta + c0 + 4);
     const uint64_t g[4] = {g01.x, g01.y, g23.x, g23.y}, bt[4] = {b01.x, b01.y, b23.x, b23.y};
-    uint32_t o[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float y0, y1;
-      unpack2(gelu_tanh2p(ffma2(p[j][e], fmul2(rs2, g[e]), bt[e])), y0, y1);
-      o[e] = pack_bf16x2(y0, y1);
+    for (int r = 0; r < LG_ROWS; ++r) {
+      if (row0 + r >= rows) break;
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float y0, y1;
+        unpack2(gelu_tanh2p(ffma2(p[r][j][e], fmul2(rs2[r], g[e]), bt[e])), y0, y1);
+        o[e] = pack_bf16x2(y0, y1);
+      }
+      *reinterpret_cast<uint4*>(out + (size_t)(row0 + r) * ldo + c0) = make_uint4(o[0], o[1], o[2], o[3]);
     }
-    *reinterpret_cast<uint4*>(out + (size_t)row * ldo + c0) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -237,7 +255,7 @@ w2vs_status_t launch_layernorm(const LayerNormArgs& a, cudaStream_t st) {
   }
   if (a.act_dtype == W2VS_BF16 && a.gelu && a.out_f32 == nullptr && a.out_act != nullptr && a.N % 256 == 0 && a.N <= 1024 &&
       a.N != 768) {
-    const dim3 grid((unsigned)ceil_div64(a.rows, 8));
+    const dim3 grid((unsigned)ceil_div64(a.rows, 8 * LG_ROWS));
     switch (a.N / 256) {
       case 1: launch_pdl(ln_gelu_bf16_kernel<1>, grid, dim3(256), 0, st, (const bf16*)a.x, a.ldx, a.gamma, a.beta, (bf16*)a.out_act, a.ldo, a.rows); break;
       case 2: launch_pdl(ln_gelu_bf16_kernel<2>, grid, dim3(256), 0, st, (const bf16*)a.x, a.ldx, a.gamma, a.beta, (bf16*)a.out_act, a.ldo, a.rows); break;
