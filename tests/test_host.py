@@ -124,6 +124,32 @@ def test_invalid_config_is_rejected_before_any_launch():
     assert e.value.status == cabi.UNSUPPORTED
 
 
+def test_posconv_layout_sizes():
+    """pos_type="conv": the bf16 model carries the extra tensor-core operand of the positional conv
+    ([groups][D/groups][k * 64] bf16) and its workspace the group-major frame copy; integer layout arithmetic only."""
+    cfg = O.default_cfg(extractor_mode="layer_norm", pos_type="conv")            # D = 768, 16 groups of 48, k = 128
+    m = W.Wav2VecSModel(cfg)
+    D, groups, k, Dgp = 768, 16, 128, 64
+    def sizes(dtype):
+        c = m._c_config(dtype, 0)
+        pw, ws = C.c_size_t(), C.c_size_t()
+        cabi.check(cabi.lib().w2vs_packed_weights_size(C.byref(c), C.byref(pw)), "packed")
+        cabi.check(cabi.lib().w2vs_get_workspace_size(C.byref(c), 2, 16000, 16, 8, C.byref(ws)), "workspace")
+        return pw.value, ws.value
+    m_sin = W.Wav2VecSModel(dict(cfg, pos_type="sin"))
+    def sizes_sin(dtype):
+        c = m_sin._c_config(dtype, 64)
+        pw = C.c_size_t()
+        cabi.check(cabi.lib().w2vs_packed_weights_size(C.byref(c), C.byref(pw)), "packed")
+        return pw.value
+    folded = D * (D // groups) * k * 4 + D * 4                                    # fp32 folded weights + bias
+    sin_tab = 64 * D * 4
+    assert sizes(torch.float32)[0] - (sizes_sin(torch.float32) - sin_tab) == folded
+    assert sizes(torch.bfloat16)[0] - (sizes_sin(torch.bfloat16) - sin_tab) == folded + D * k * Dgp * 2
+    T = m.geometry(16000, 16, 8).frames
+    assert sizes(torch.bfloat16)[1] > 2 * (T + k) * D * 4 + groups * (2 * (T + k) + k) * Dgp * 2
+
+
 def test_from_checkpoint_formats():
     """Checkpoint ingestion: hydra-era {"cfg": {"model": ..}}, argparse-era {"args": ..},
     and a composite fine-tuned checkpoint with the encoder under a prefix and foreign keys next to it."""
