@@ -120,7 +120,9 @@ def _attention_ref(qkv, keypad, T2, main, rc, heads):
 
 
 @pytest.mark.parametrize("T2,main,rc", [(500, 16, 8), (18, 16, 8), (12, 16, 8), (38, 16, 8), (250, 8, 4),
-                                        (200, 32, 16), (100, 16, 0), (2, 16, 8), (1000, 16, 8)])
+                                        (200, 32, 16), (100, 16, 0), (2, 16, 8), (1000, 16, 8),
+                                        # context_type="sampling" block sizes (wav2vec_S.py:392-395): not powers of two
+                                        (300, 20, 10), (310, 12, 6), (500, 30, 14), (260, 10, 4), (400, 24, 12)])
 @pytest.mark.parametrize("dtype,impl", [(torch.float32, 1), (torch.bfloat16, 1), (torch.bfloat16, 2), (torch.bfloat16, 3)])
 def test_attention(T2, main, rc, dtype, impl):
     B, heads, D = 2, 3, 192

@@ -120,6 +120,27 @@ def test_all_layers_vs_oracle_fp32(name):
     assert valid_rel_err(y.cpu(), yo, None if fmo is None else fmo.numpy()) < FP32_TOL
 
 
+@pytest.mark.parametrize("main,rc,L", [(20, 10, 16000), (12, 6, 9000), (30, 14, 24000), (10, 4, 7000), (26, 12, 40000)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_sampling_range_contexts_vs_oracle(main, rc, L, dtype):
+    """Block sizes the reference draws with context_type="sampling" (wav2vec_S.py:392-395: even main context in
+    8..32, even right context <= main / 2) -- not powers of two, so block boundaries fall inside the kernels' 64- and
+    128-token tiles.  Ragged batch, against the oracle (itself checked against the live reference on these sizes in
+    tests/test_oracle_vs_reference.py)."""
+    from oracle import synth
+    cfg = cases.tiny(main_context=main, right_context=rc, layer_norm_first=(main % 4 == 0))
+    B = 3
+    sd = synth.make_state_dict(cfg, cases.WSEED + main)
+    wav = synth.make_waveform(B, L, cases.XSEED + main)
+    pm = O.lengths_to_padding_mask(synth.make_lengths(B, L, cases.LSEED + main))
+    wav = wav.masked_fill(pm, 0.0)
+    yo, fmo = O.extract_features(sd, cfg, wav, pm)
+    m = build(W.Wav2VecSModel, cfg, sd, dtype)
+    y, fm = m.extract_features(wav.cuda(), pm.cuda())
+    assert torch.equal(fm.cpu(), fmo)
+    assert valid_rel_err(y.cpu(), yo, fmo.numpy()) < (FP32_TOL if dtype == torch.float32 else BF16_TOL)
+
+
 @pytest.mark.parametrize("embed_dim,heads", [(768, 12), (1024, 16)], ids=["Dg48", "Dg64"])
 def test_posconv_tensor_core_path_vs_oracle(embed_dim, heads):
     """pos_type="conv" at the real widths (Conv1d(D, D, 128, groups=16), group width 48 / 64): in bf16 mode every

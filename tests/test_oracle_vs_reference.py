@@ -19,6 +19,12 @@ VARIANTS = {
     "groupnorm_posconv": dict(cfg=cases.tiny(extractor_mode="default", pos_type="conv", encoder_layers=2), B=2, L=6400, ragged=True),
     "ctx_8_4": dict(cfg=cases.tiny(main_context=8, right_context=4), B=2, L=8000, ragged=False),
     "rc0": dict(cfg=cases.tiny(right_context=0, layer_norm_first=True), B=1, L=5000, ragged=False),
+    # block sizes the reference draws with context_type="sampling" (wav2vec_S.py:392-395): even main in 8..32,
+    # even right context <= main / 2 -- not powers of two
+    "ctx_20_10": dict(cfg=cases.tiny(main_context=20, right_context=10, layer_norm_first=True), B=2, L=16000, ragged=True),
+    "ctx_12_6": dict(cfg=cases.tiny(main_context=12, right_context=6), B=2, L=9000, ragged=False),
+    "ctx_30_14": dict(cfg=cases.tiny(main_context=30, right_context=14, layer_norm_first=True), B=1, L=24000, ragged=False),
+    "ctx_10_4": dict(cfg=cases.tiny(main_context=10, right_context=4), B=3, L=7000, ragged=True),
 }
 
 
