@@ -141,6 +141,25 @@ def test_sampling_range_contexts_vs_oracle(main, rc, L, dtype):
     assert valid_rel_err(y.cpu(), yo, fmo.numpy()) < (FP32_TOL if dtype == torch.float32 else BF16_TOL)
 
 
+def test_context_type_sampling_draws_like_reference():
+    """context_type="sampling": the host draws (main, right) per call with Python's `random`, exactly as
+    wav2vec_S.py:392-395 does, and the encoder runs with the drawn block sizes."""
+    import random
+    from oracle import synth
+    cfg = cases.tiny(context_type="sampling", layer_norm_first=True)
+    sd = synth.make_state_dict(cfg, cases.WSEED)
+    wav = synth.make_waveform(2, 20000, cases.XSEED)
+    m = build(W.Wav2VecSModel, cfg, sd, torch.float32)
+    for seed in (3, 11, 12345):
+        random.seed(seed)
+        y, _ = m.extract_features(wav.cuda(), None)
+        random.seed(seed)
+        main = random.randint(4, 16) * 2
+        rc = min(random.randint(2, 8) * 2, main // 2)
+        yo, _ = O.extract_features(sd, dict(cfg, context_type="constant", main_context=main, right_context=rc), wav, None)
+        assert valid_rel_err(y.cpu(), yo) < FP32_TOL, (seed, main, rc)
+
+
 @pytest.mark.parametrize("embed_dim,heads", [(768, 12), (1024, 16)], ids=["Dg48", "Dg64"])
 def test_posconv_tensor_core_path_vs_oracle(embed_dim, heads):
     """pos_type="conv" at the real widths (Conv1d(D, D, 128, groups=16), group width 48 / 64): in bf16 mode every

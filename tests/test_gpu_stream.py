@@ -61,6 +61,30 @@ def test_stream_irregular_chunks_equal_offline(name):
     assert valid_rel_err(y, ref) < 1e-4
 
 
+@pytest.mark.parametrize("main,rc", [(8, 4), (32, 16), (20, 10), (12, 6), (16, 0)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_stream_other_block_sizes_equal_offline(main, rc, dtype):
+    """Incremental mode with block sizes other than 16 / 8 (the reference's sampling range, wav2vec_S.py:392-395,
+    and no look-ahead): irregular chunks, FINAL flush == the offline rain forward on the whole utterance."""
+    from oracle import synth
+    cfg = cases.tiny(layer_norm_first=True, conv_bias=True, main_context=main, right_context=rc)
+    sd = synth.make_state_dict(cfg, 21 + main)
+    wav = synth.make_waveform(1, 30000, 77 + main)
+    m = build(cfg, sd, dtype)
+    ref, _ = O.rain_forward(sd, cfg, wav, None, finished=True, is_infer=True)
+    rs = np.random.RandomState(main)
+    st = m.open_stream(B=1, max_seconds=3.0, max_new_samples=9000)
+    src = wav.cuda()
+    outs, pos, L = [], 0, src.size(1)
+    while pos < L:
+        n = min(int(rs.choice([37, 400, 1600, 5120, 8999])), L - pos)
+        outs.append(st.step(src[:, pos:pos + n], EncoderStream.FINAL if pos + n >= L else EncoderStream.NONE))
+        pos += n
+    y = torch.cat(outs, 0).cpu()
+    assert tuple(y.shape) == tuple(ref.shape)
+    assert valid_rel_err(y, ref) < TOL[dtype]
+
+
 def test_stream_batch_lockstep():
     cfg = cases.tiny(layer_norm_first=True, conv_bias=True)
     from oracle import synth

@@ -53,9 +53,10 @@ def test_fairseq_extract_features(name):
     assert O.max_abs_rel(y, y_ref) < 2e-5
 
 
+@pytest.mark.parametrize("main,rc", [(16, 8), (8, 4), (32, 16), (20, 10), (12, 6), (16, 0)])
 @pytest.mark.parametrize("finished", [False, True])
-def test_rain_forward_infer(finished):
-    cfg = cases.tiny(layer_norm_first=True)
+def test_rain_forward_infer(finished, main, rc):
+    cfg = cases.tiny(layer_norm_first=True, main_context=main, right_context=rc)
     sd, wav, _ = _inputs(dict(cfg=cfg, B=1, L=12880 + 320 * 5, ragged=False), 200)
     with torch.no_grad():
         m = ref_shim.build_rain_model(cfg)
