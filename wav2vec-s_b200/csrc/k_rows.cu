@@ -84,8 +84,9 @@ layernorm_rows_kernel(const TIn* x, int64_t ldx, const float* __restrict__ gamma
 // bf16 -> LayerNorm -> GELU -> bf16 (the conv blocks' Fp32LayerNorm + GELU, in place over the GEMM output): same
 // arithmetic as the generic kernel (fp32, mean first, then centred squares) on packed f32x2 pairs -- 8.5 issued
 // instructions per element instead of 14; the generic kernel was issue bound at 79 % on these passes (ncu).
-// Each warp normalises LG_ROWS rows at once: all of their loads are issued before the first reduction, which doubles
-// the bytes in flight per SM (one 1 KB row per warp kept these passes at 5 of 6.5 TB/s, latency bound).
+// Each warp normalises LG_ROWS rows at once, all of their loads issued before the first reduction.  Measured: alone
+// (ncu) the pass stays at 5.0 of 6.5 TB/s either way; inside the power-capped step the row kernels take 7.25 instead
+// of 7.5 ms (same-box A/B), so two rows it is.
 #ifndef W2VS_LN_GELU_ROWS
 #define W2VS_LN_GELU_ROWS 2
 #endif
