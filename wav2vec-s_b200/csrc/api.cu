@@ -297,21 +297,23 @@ w2vs_status_t w2vs_encode(const w2vs_config* cfg, const void* d_packed, const w2
     const float* posconv = nullptr;
     int posconv_rows = 0;
     if (posconv_tc(cfg)) {
-      // grouped Conv1d(D, D, k, groups) + SamePad + GELU (wav2vec2.py:791-804) as one implicit GEMM per group on the
-      // tcgen05 kernel: bias and GELU in its epilogue, fp32 result rows b*Tp + t read by embed_tokens below
+      // grouped Conv1d(D, D, k, groups) + SamePad + GELU (wav2vec2.py:791-804) as one implicit GEMM per group, all in
+      // one launch of the tcgen05 kernel: bias and GELU in its epilogue, fp32 result rows b*Tp + t read by embed_tokens below
       const int k = cfg->conv_pos, groups = cfg->conv_pos_groups, Dg = D / groups, Dgp = posconv_dgp(cfg);
       const int Tp = g.T + k;
       const int64_t rows_tot = (int64_t)B * Tp + k;
       bf16* xg = at<bf16>(d_ws, ws.posconv_xg);
       float* out = at<float>(d_ws, ws.posconv_tmp);
       W2VS_TRY(launch_posconv_pack_x(feats, rows_last, frame_pad, xg, B, g.T, D, k, groups, Dgp, st));
-      for (int grp = 0; grp < groups; ++grp) {
+      {
+        // all groups in one launch: product grp reads the rows_tot frames of its group, Dg rows of W, and writes
+        // the column block grp * Dg of the result
         GemmArgs ga{};
-        ga.A = xg + (size_t)grp * rows_tot * Dgp; ga.lda = Dgp; ga.a_rows = rows_tot;
-        ga.W = at<bf16>(W, wl.posconv_wg) + (size_t)grp * Dg * k * Dgp;
-        ga.bias = at<float>(W, wl.posconv_b) + grp * Dg; ga.residual = nullptr;
-        ga.C = out + grp * Dg; ga.ldc = D; ga.M = (B - 1) * Tp + g.T; ga.N = Dg; ga.K = k * Dgp;
+        ga.A = xg; ga.lda = Dgp; ga.a_rows = (int64_t)groups * rows_tot;
+        ga.W = at<bf16>(W, wl.posconv_wg); ga.bias = at<float>(W, wl.posconv_b); ga.residual = nullptr;
+        ga.C = out; ga.ldc = D; ga.M = (B - 1) * Tp + g.T; ga.N = Dg; ga.K = k * Dgp;
         ga.dtype_ab = W2VS_BF16; ga.dtype_c = W2VS_F32; ga.flags = W2VS_EPI_GELU;
+        ga.batch = groups; ga.a_batch_rows = rows_tot; ga.w_batch_rows = Dg; ga.c_batch_stride = Dg;
         W2VS_TRY(launch_gemm(W2VS_GEMM_TCGEN05_2CTA, ga, st));
       }
       posconv = out; posconv_rows = Tp;

@@ -89,7 +89,7 @@ template <int BN, typename TC, int SLOTS, int EW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * EW + 64, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int has_residual,
-                int M, int N, int K, int a_row_len, int gelu) {
+                int M, int N, int K, int a_row_len, int gelu, int n_batch, int a_batch_rows, int w_batch_rows) {
   using C2 = Cfg2<BN, TC, SLOTS, EW>;
   constexpr int S = C2::kStages;
   constexpr bool kF32 = sizeof(TC) == 4;
@@ -114,7 +114,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
   const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + 2 * BM - 1) / (2 * BM);
-  const int n_tiles = tiles_m * tiles_n;
+  const int tiles_pb = tiles_m * tiles_n;          // tiles per product; n_batch > 1: the tile index also walks the batch
+  const int n_tiles = tiles_pb * n_batch;
   const int num_kb = (K + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
@@ -145,8 +146,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t phase = 0;
       bool ok = true;
       for (int tile = cluster_id; tile < n_tiles && ok; tile += n_clusters) {
-        const int m0 = (tile / tiles_n) * (2 * BM) + (int)rank * BM;
-        const int n0 = (tile % tiles_n) * BN + (int)rank * (BN / 2);
+        const int bt = tile / tiles_pb, rem = tile - bt * tiles_pb;
+        const int m0 = (rem / tiles_n) * (2 * BM) + (int)rank * BM + bt * a_batch_rows;
+        const int n0 = (rem % tiles_n) * BN + (int)rank * (BN / 2) + bt * w_batch_rows;
         for (int kb = 0; kb < num_kb; ++kb) {
           if (!(ok = mbar_wait(bar_empty + 8 * stage, phase ^ 1))) break;
           if (leader) mbar_expect_tx(bar_full + 8 * stage, 2 * C2::kStageBytes);
@@ -199,15 +201,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t aphase = 0;
     bool ok = true;
     for (int tile = cluster_id; tile < n_tiles && ok; tile += n_clusters) {
-      const int m0 = (tile / tiles_n) * (2 * BM) + (int)rank * BM;
-      const int n0 = (tile % tiles_n) * BN;
+      const int bt = tile / tiles_pb, rem = tile - bt * tiles_pb;
+      const int m0 = (rem / tiles_n) * (2 * BM) + (int)rank * BM;
+      const int n0 = (rem % tiles_n) * BN;
       const int row0 = m0 + quarter * 32;
       const int colw = n0 + half * CPW;                // first column of this warp
       // bias of this warp's columns -> its private smem strip
       float* bs = bias_s + e * CPW;
       __syncwarp();
 #pragma unroll
-      for (int i = lane; i < CPW; i += 32) bs[i] = (bias != nullptr && colw + i < N) ? bias[colw + i] : 0.f;
+      for (int i = lane; i < CPW; i += 32) bs[i] = (bias != nullptr && colw + i < N) ? bias[bt * N + colw + i] : 0.f;
       // residual chunk 0 prefetch (overlaps the wait for the accumulator)
       if (SLOTS == 2 && !kTmaReduce && has_residual && lane == 0) {
         bulk_wait_read<0>();                           // earlier stores from slot 0/1 have been read out
@@ -287,6 +290,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __syncwarp();
         if (lane == 0) {
           if (kTmaReduce && has_residual) tma_reduce_add_2d(&tmC, slot, colw + c * CHUNK, row0);
+          else if (n_batch > 1) tma_store_3d(&tmC, slot, colw + c * CHUNK, bt, row0);   // {column, product, row}: clipped at N
           else tma_store_2d(&tmC, slot, colw + c * CHUNK, row0);
           bulk_commit();
         }
@@ -318,9 +322,20 @@ w2vs_status_t launch_bn(const GemmArgs& g, cudaStream_t st) {
   const uint64_t a_inner = (uint64_t)(g.K <= a_row_len ? g.K : a_row_len);
   W2VS_TRY(make_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.A, a_inner, (uint64_t)g.a_rows, (uint64_t)a_row_len,
                     BK, BM, CU_TENSOR_MAP_SWIZZLE_128B));
-  W2VS_TRY(make_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.W, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.K, BK,
-                    BN / 2, CU_TENSOR_MAP_SWIZZLE_128B));
-  if (sizeof(TC) == 4)
+  const int n_batch = g.batch > 1 ? g.batch : 1;
+  W2VS_TRY(make_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.W, (uint64_t)g.K,
+                    (uint64_t)((n_batch - 1) * g.w_batch_rows + g.N), (uint64_t)g.K, BK, BN / 2,
+                    CU_TENSOR_MAP_SWIZZLE_128B));
+  if (n_batch > 1) {
+    // one product per batch index: the third map dimension clips every store at the product's own N columns
+    if (sizeof(TC) == 4)
+      W2VS_TRY(make_map3(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.C, (uint64_t)g.N, (uint64_t)n_batch, (uint64_t)g.M,
+                         (uint64_t)g.c_batch_stride, (uint64_t)g.ldc, C2::kChunk, 32,
+                         C2::kChunk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B));
+    else
+      W2VS_TRY(make_map3(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.C, (uint64_t)g.N, (uint64_t)n_batch, (uint64_t)g.M,
+                         (uint64_t)g.c_batch_stride, (uint64_t)g.ldc, C2::kChunk, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+  } else if (sizeof(TC) == 4)
     W2VS_TRY(make_map(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.C, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc,
                       C2::kChunk, 32, C2::kChunk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B));
   else
@@ -333,18 +348,20 @@ w2vs_status_t launch_bn(const GemmArgs& g, cudaStream_t st) {
     if (e != cudaSuccess) { set_error("gemm_tc2 smem attribute: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
     attr_done = true;
   }
-  const int tiles = (int)(ceil_div64(g.M, 2 * BM) * ceil_div64(g.N, BN));
+  const int tiles = (int)(ceil_div64(g.M, 2 * BM) * ceil_div64(g.N, BN)) * n_batch;
   const int max_clusters = num_sms() / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   // plain stream launch: as a programmatic dependent (PDL) this kernel's 200 KB CTAs cannot become resident early
   // anyway, and 16-stream incremental steps measured 7 % slower with it
   gemm_tc2_kernel<BN, TC, SLOTS, EW><<<2 * clusters, 32 * EW + 64, C2::kSmemBytes, st>>>(
       tmA, tmB, tmC, g.bias, g.residual != nullptr ? 1 : 0, g.M, g.N, g.K, (int)a_row_len,
-      (g.flags & W2VS_EPI_GELU) ? 1 : 0);
+      (g.flags & W2VS_EPI_GELU) ? 1 : 0, n_batch, (int)g.a_batch_rows, (int)g.w_batch_rows);
   if (g_prof_on) {
     char name[96];
-    snprintf(name, sizeof(name), "gemm_tc2_kernel[M=%d,N=%d,K=%d,lda=%lld,%s%s%s]", g.M, g.N, g.K, (long long)g.lda,
-             sizeof(TC) == 4 ? "f32" : "bf16", g.residual ? ",res" : "", (g.flags & W2VS_EPI_GELU) ? ",gelu" : "");
+    char bat[24] = "";
+    if (n_batch > 1) snprintf(bat, sizeof(bat), ",batch=%d", n_batch);
+    snprintf(name, sizeof(name), "gemm_tc2_kernel[M=%d,N=%d,K=%d,lda=%lld,%s%s%s%s]", g.M, g.N, g.K, (long long)g.lda,
+             sizeof(TC) == 4 ? "f32" : "bf16", g.residual ? ",res" : "", (g.flags & W2VS_EPI_GELU) ? ",gelu" : "", bat);
     W2VS_CHECK_LAUNCH(name);
   } else {
     W2VS_CHECK_LAUNCH("gemm_tc2_kernel");
@@ -394,6 +411,11 @@ w2vs_status_t launch_gemm_tc2(const GemmArgs& g, cudaStream_t st) {
                "GEMM operands must be 16-byte aligned");
   W2VS_REQUIRE(g.residual == nullptr || (g.dtype_c == W2VS_F32 && g.residual == (const float*)g.C),
                "tcgen05 GEMM adds the residual in place (residual == C, fp32)");
+  if (g.batch > 1)
+    W2VS_REQUIRE(g.residual == nullptr && g.c_batch_stride * (g.dtype_c == W2VS_F32 ? 4 : 2) % 16 == 0 &&
+                     g.c_batch_stride >= g.N && g.c_batch_stride <= g.ldc && g.w_batch_rows >= g.N &&
+                     (int64_t)g.batch * g.a_batch_rows < (1ll << 31),
+                 "batched GEMM: no residual, products are 16-byte aligned column blocks of C");
   if (g.M <= 0) return W2VS_OK;
   return g.dtype_c == W2VS_F32 ? launch_typed<float>(g, st) : launch_typed<bf16>(g, st);
 }

@@ -70,6 +70,10 @@ struct GemmArgs {
   const float* bias; const float* residual;     // residual fp32 [M, ldc] (may alias C)
   void* C; int64_t ldc;
   int M, N, K; int dtype_ab, dtype_c; int flags;
+  // batch > 1 (CTA-pair tcgen05 kernel only): `batch` independent products in one launch -- A of product b starts
+  // a_batch_rows rows (of lda) after A of b - 1, W w_batch_rows rows after, C c_batch_stride elements after, bias N
+  // floats after; no residual.  The groups of the positional conv.
+  int batch; int64_t a_batch_rows, w_batch_rows, c_batch_stride;
 };
 w2vs_status_t launch_gemm_simt(const GemmArgs& g, cudaStream_t st);
 w2vs_status_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st);    // 1-CTA tcgen05 (first version)

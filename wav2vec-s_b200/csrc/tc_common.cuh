@@ -126,6 +126,10 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"((uint64_t)map), "r"(src), "r"(x), "r"(y) : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int x, int y, int z) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"((uint64_t)map), "r"(src), "r"(x), "r"(y), "r"(z) : "memory");
+}
 // out[tile] += smem tile, the fp32 additions done by the L2 reduction units (in-place residual update)
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int x, int y) {
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
@@ -224,6 +228,29 @@ inline w2vs_status_t make_map(CUtensorMap* map, CUtensorMapDataType dt, int elem
     set_error("cuTensorMapEncodeTiled failed: %d (inner=%llu rows=%llu stride=%llu box=%ux%u)", (int)r,
               (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)row_stride_elems, box_inner,
               box_rows);
+    return W2VS_CUDA_ERROR;
+  }
+  return W2VS_OK;
+}
+
+// 3-D map over column blocks of one row-major matrix: dimensions {inner (columns of a block), block, rows} with
+// strides {block_stride, row_stride} -- ascending, as a column block is narrower than a row; boxes {box_inner, 1,
+// box_rows} land in shared memory exactly like a 2-D {box_inner, box_rows} box, and are clipped at `inner` columns.
+inline w2vs_status_t make_map3(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base,
+                               uint64_t inner, uint64_t blocks, uint64_t rows, uint64_t block_stride_elems,
+                               uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_rows,
+                               CUtensorMapSwizzle sw) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return W2VS_CUDA_ERROR; }
+  cuuint64_t dims[3] = {inner, blocks, rows};
+  cuuint64_t strides[2] = {block_stride_elems * (uint64_t)elem_bytes, row_stride_elems * (uint64_t)elem_bytes};
+  cuuint32_t box[3] = {box_inner, 1, box_rows};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3-D) failed: %d (inner=%llu blocks=%llu rows=%llu)", (int)r,
+              (unsigned long long)inner, (unsigned long long)blocks, (unsigned long long)rows);
     return W2VS_CUDA_ERROR;
   }
   return W2VS_OK;
