@@ -33,6 +33,10 @@ CASES = {
     "tiny_ctx8_4": dict(cfg=tiny(main_context=8, right_context=4, layer_norm_first=True), B=2, L=10000,
                         ragged=True),
     "tiny_ctx32_16": dict(cfg=tiny(main_context=32, right_context=16), B=1, L=24000),
+    # block sizes that are not powers of two (context_type="sampling" draws them, wav2vec_S.py:392-395)
+    "tiny_ctx20_10": dict(cfg=tiny(main_context=20, right_context=10, layer_norm_first=True), B=2, L=16000,
+                          ragged=True),
+    "tiny_ctx12_6": dict(cfg=tiny(main_context=12, right_context=6), B=2, L=9000),
     "tiny_short_T12": dict(cfg=tiny(), B=2, L=4000),                             # T=12 < main
     "tiny_T1": dict(cfg=tiny(layer_norm_first=True), B=1, L=400),                # T=1
     "tiny_T17": dict(cfg=tiny(), B=1, L=5760),                                   # T=17 odd, rc overrun
