@@ -152,26 +152,47 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def cpu_reference_run(cfg_kind, B, seconds, steps, warmup):
-    """Time the oracle port (reference algorithm, PyTorch CPU, fp32) on the host cores."""
+def reference_cpu_encoder(cfg_kind):
+    """(encode(wav) callable, kind, description): the reference's OWN implementation on the host CPU -- its
+    unmodified modules through oracle/ref_shim.py (sources in the build container, oracle/_ref bytecode on the GPU
+    box; kind "reference") -- or, when neither is present, the oracle port (kind "port")."""
+    import warnings
     import torch
-    from oracle import synth
+    from oracle import ref_shim, synth
     from oracle import w2vs_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    warnings.filterwarnings("ignore")
     cfg = O.default_cfg(**model_cfg(cfg_kind))
     sd = synth.make_state_dict(cfg, 0)
+    if ref_shim.available():
+        m = ref_shim.build_fairseq_model(cfg)
+        m.load_state_dict(sd, strict=False)
+
+        def encode(wav):
+            with torch.no_grad():
+                return m.extract_features(wav, None)[0]
+        return encode, "reference", f"unmodified reference modules ({ref_shim.kind()}) on torch CPU"
+    return (lambda wav: O.extract_features(sd, cfg, wav, None)[0]), "port", "oracle port on torch CPU"
+
+
+def cpu_reference_run(cfg_kind, B, seconds, steps, warmup):
+    """Time the reference's CPU implementation (fp32, all host threads) on a bounded sample of the workload."""
+    import torch
+    from oracle import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    encode, kind, what = reference_cpu_encoder(cfg_kind)
     wav = synth.make_waveform(B, seconds * SR, 1234)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.extract_features(sd, cfg, wav, None)
+        encode(wav)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     t = statistics.median(times)
-    return dict(value=B * seconds / t, unit="audio-s/s", cores=cores, kind="port",
-                sample=f"{cfg_kind} fp32, {B} x {seconds} s, oracle port on torch CPU, median of {steps} after {warmup} warm-up",
+    return dict(value=B * seconds / t, unit="audio-s/s", cores=cores, kind=kind,
+                sample=f"{cfg_kind} fp32, {B} x {seconds} s per step (a sample of the workload's batch), {what}, "
+                       f"median of {steps} after {warmup} warm-up",
                 ms_per_step=t * 1e3)
 
 

@@ -14,9 +14,12 @@
  *
  * Conventions follow the reference's own native precedent (warp_transducer/include/rnnt.h):
  * extern "C", an int status enum, the CUDA stream passed by the caller, caller-owned workspace
- * sized by *_size() queries, and no device allocation, no host synchronisation and no global
- * state inside the library.  All pointers named `d_*` are device pointers; everything else is
- * host memory.  The library is re-entrant per (stream, workspace, state).
+ * sized by *_size() queries, and no device allocation and no host synchronisation inside the
+ * library.  All pointers named `d_*` are device pointers; everything else is host memory.  The
+ * library is re-entrant per (stream, workspace, state) and works on whichever CUDA device is
+ * current on the calling thread: the only process-wide state are idempotent per-device caches
+ * (SM count, "dynamic shared memory opted in" flags) and thread-local diagnostics (last error,
+ * launch counter).
  */
 #ifndef W2VS_H_
 #define W2VS_H_
@@ -181,7 +184,7 @@ w2vs_status_t w2vs_stream_info(const void* host_state, int64_t* samples, int32_t
 typedef enum {
   W2VS_GEMM_AUTO = 0,
   W2VS_GEMM_SIMT = 1,          /* fp32-accurate CUDA-core kernel */
-  W2VS_GEMM_TCGEN05 = 2,       /* tcgen05, one CTA per tile */
+  /* 2 was the first one-CTA tcgen05 kernel, retired in ABI version 2 */
   W2VS_GEMM_TCGEN05_2CTA = 3,  /* tcgen05 cta_group::2 CTA pairs, TMA-store epilogue (default for bf16) */
   W2VS_GEMM_SKINNY = 4         /* M <= 64: weight-streaming mma.sync kernel (default for incremental steps) */
 } w2vs_gemm_impl_t;

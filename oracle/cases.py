@@ -50,7 +50,14 @@ CASES = {
     "tiny_stream_postln": dict(cfg=tiny(encoder_layers=12), B=1, L=25000, api="stream"),
     "base_1s": dict(cfg=base_cfg(), B=2, L=16000, ragged=True),
     "large_1s": dict(cfg=large_cfg(), B=1, L=20000),
+    # BASELINE.json shapes.  `compact=k`: the golden file keeps the final output only, every k-th frame (k = 3 is
+    # coprime with the 16-frame blocks, so every position inside a block and every block is sampled) -- the full
+    # tensors would put tens of MB into the repository.
+    "cfg1_base_10s": dict(cfg=base_cfg(), B=1, L=160000, compact=1),            # configs[0] exactly: T=499, M=748
+    "large_20s": dict(cfg=large_cfg(), B=1, L=320000, compact=3),               # configs[2] utterance: T=999, M=1496
 }
+# golden cases small enough for the stage-by-stage tests (the compact ones have their own tests)
+SMALL = [n for n, c in CASES.items() if not c.get("compact")]
 
 WSEED = 7
 XSEED = 1234

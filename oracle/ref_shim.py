@@ -1,14 +1,17 @@
 """TEST INFRASTRUCTURE ONLY -- loader for the *unmodified* reference sources.
 
-Executes the reference's own hot-path files from ``/root/reference`` under a stub
-``fairseq`` namespace (``import fairseq`` itself fails here: no omegaconf/hydra, py3.12).
-Nothing from the reference is copied into this repository; the files are loaded where
-they lie.  This module only works in the build container (``/root/reference`` does not
-exist on the GPU box) and is used for exactly two things:
+Executes the reference's own hot-path files under a stub ``fairseq`` namespace (``import
+fairseq`` itself fails here: no omegaconf/hydra, py3.12).  No reference source is copied into
+this repository: in the build container the files are loaded where they lie under
+``/root/reference``; on the GPU box (where that path does not exist) the same modules are loaded
+from ``oracle/_ref/`` -- bytecode of the unmodified files, produced by ``oracle/build_ref.py``,
+git-ignored, shipped with the snapshot like a built ``.so``.  Used for:
 
   * ``tests/golden/make_golden.py``  -- generate golden input/output vectors,
-  * ``tests/test_oracle_vs_reference.py`` -- pin ``oracle/w2vs_oracle.py`` (the restatement
-    that does travel) against the real reference, skipped when the reference is absent.
+  * ``tests/test_oracle_vs_reference.py`` -- pin ``oracle/w2vs_oracle.py`` against the real
+    reference (skipped when neither form of the reference is present),
+  * ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` -- time the reference's own code on
+    the host cores (``kind: "reference"``).
 
 Loaded verbatim (reference paths relative to /root/reference):
   fairseq/fairseq/incremental_decoding_utils.py
@@ -33,13 +36,34 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+import importlib.machinery
+
 REF_ROOT = os.environ.get("W2VS_REFERENCE_ROOT", "/root/reference")
-_FS = os.path.join(REF_ROOT, "fairseq", "fairseq")
+PYC_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+_KEY = os.path.join("fairseq", "fairseq", "models", "wav2vec", "wav2vec_S.py")
 _loaded = {}
 
 
+def source_available() -> bool:
+    return os.path.isfile(os.path.join(REF_ROOT, _KEY))
+
+
+def compiled_available() -> bool:
+    return os.path.isfile(os.path.join(PYC_ROOT, _KEY + "c"))
+
+
 def available() -> bool:
-    return os.path.isfile(os.path.join(_FS, "models", "wav2vec", "wav2vec_S.py"))
+    return source_available() or compiled_available()
+
+
+def kind() -> str:
+    """Where the reference modules come from: "source" (/root/reference), "compiled" (oracle/_ref) or "absent"."""
+    return "source" if source_available() else ("compiled" if compiled_available() else "absent")
+
+
+_ROOT = REF_ROOT if source_available() else PYC_ROOT
+_EXT = ".py" if source_available() else ".pyc"
+_FS = os.path.join(_ROOT, "fairseq", "fairseq")
 
 
 def _mod(name, is_pkg=False):
@@ -51,7 +75,11 @@ def _mod(name, is_pkg=False):
 
 
 def _load(name, path):
-    spec = importlib.util.spec_from_file_location(name, path)
+    if _EXT == ".pyc":
+        path = path + "c"
+        spec = importlib.util.spec_from_file_location(name, path, loader=importlib.machinery.SourcelessFileLoader(name, path))
+    else:
+        spec = importlib.util.spec_from_file_location(name, path)
     m = importlib.util.module_from_spec(spec)
     sys.modules[name] = m
     spec.loader.exec_module(m)
@@ -62,7 +90,7 @@ def _install():
     if _loaded:
         return _loaded
     if not available():
-        raise RuntimeError(f"reference sources not found under {REF_ROOT}")
+        raise RuntimeError(f"reference not found: neither sources under {REF_ROOT} nor oracle/_ref (oracle/build_ref.py)")
     if "fairseq" in sys.modules and not getattr(sys.modules["fairseq"], "_w2vs_shim", False):
         raise RuntimeError("a real fairseq is already imported; shim refuses to shadow it")
 
@@ -210,7 +238,7 @@ def _install():
         setattr(w2v, k, getattr(w2, k))
     ws = _load("fairseq.models.wav2vec.wav2vec_S", os.path.join(wdir, "wav2vec_S.py"))
     rain = _load("w2vs_ref_rain_unidirect_w2v2_encoder",
-                 os.path.join(REF_ROOT, "rain", "layers", "unidirect_w2v2_encoder.py"))
+                 os.path.join(_ROOT, "rain", "layers", "unidirect_w2v2_encoder.py"))
     _loaded.update(wav2vec2=w2, wav2vec_S=ws, rain=rain, modules=modules)
     return _loaded
 

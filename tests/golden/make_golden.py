@@ -57,12 +57,17 @@ def run_case(name):
                 m.post_extract_proj.register_forward_hook(lambda mod, i, o: taps.__setitem__("post_proj", o))
             m.encoder.layers[0].register_forward_hook(lambda mod, i, o: taps.__setitem__("layer0", o[0]))
             y, fm = m.extract_features(wav.clone(), pm)
-            out["y"] = y.numpy()
             out["fmask"] = fm.numpy() if fm is not None else np.zeros((0,), dtype=bool)
-            out["conv_out"] = taps["conv_out"].numpy()
-            if "post_proj" in taps:
-                out["post_proj"] = taps["post_proj"].numpy()
-            out["layer0"] = taps["layer0"].numpy()
+            if c.get("compact"):
+                # BASELINE-size case: the output only, every `compact`-th frame (see oracle/cases.py)
+                out["y"] = y[:, ::c["compact"]].contiguous().numpy()
+                out["y_shape"] = np.array(y.shape, dtype=np.int64)
+            else:
+                out["y"] = y.numpy()
+                out["conv_out"] = taps["conv_out"].numpy()
+                if "post_proj" in taps:
+                    out["post_proj"] = taps["post_proj"].numpy()
+                out["layer0"] = taps["layer0"].numpy()
         elif api == "rain":
             m = ref_shim.build_rain_model(cfg)
             missing, unexpected = m.load_state_dict(sd, strict=False)

@@ -20,7 +20,8 @@ BF16_TOL = 2e-2
 # output on these cases), so they get 1.5x the output bound.
 BF16_STAGE_TOL = 3e-2
 
-FAIRSEQ = [n for n, c in cases.CASES.items() if c.get("api", "fairseq") == "fairseq"]
+FAIRSEQ = [n for n, c in cases.CASES.items() if c.get("api", "fairseq") == "fairseq" and not c.get("compact")]
+COMPACT = [n for n, c in cases.CASES.items() if c.get("compact")]
 RAIN = [n for n, c in cases.CASES.items() if c.get("api") == "rain"]
 
 

@@ -10,7 +10,8 @@ from helpers import load_golden, case_inputs, valid_rel_err
 
 FP32_TOL = 2e-5  # oracle and reference run the same torch ops; only op ordering may differ
 
-FAIRSEQ = [n for n, c in cases.CASES.items() if c.get("api", "fairseq") == "fairseq"]
+FAIRSEQ = [n for n, c in cases.CASES.items() if c.get("api", "fairseq") == "fairseq" and not c.get("compact")]
+COMPACT = [n for n, c in cases.CASES.items() if c.get("compact")]
 RAIN = [n for n, c in cases.CASES.items() if c.get("api") == "rain"]
 STREAM = [n for n, c in cases.CASES.items() if c.get("api") == "stream"]
 
@@ -94,3 +95,16 @@ def test_waveform_frontend_restatement():
         ref = F.layer_norm(x[b, :n], x[b, :n].shape)                                       # raw_audio_dataset.py:69-72
         assert torch.equal(y[b, :n], ref)
         assert torch.equal(y[b, n:], x[b, n:])
+
+
+@pytest.mark.parametrize("name", COMPACT)
+def test_baseline_shapes_compact(name):
+    """BASELINE.json shapes (cfg1 base 1 x 10 s exactly; one large 20 s utterance of configs[2]): the oracle against
+    the unmodified reference's output, stored every k-th frame (oracle/cases.py)."""
+    g = load_golden(name)
+    cfg, sd, wav, pm, _ = case_inputs(name)
+    assert cfg == g["cfg"]
+    y, fm = O.extract_features(sd, cfg, wav, pm)
+    assert list(y.shape) == g["y_shape"].tolist() and fm is None and g["fmask"].size == 0
+    k = cases.CASES[name]["compact"]
+    assert valid_rel_err(y[:, ::k], g["y"]) < FP32_TOL

@@ -17,7 +17,7 @@ F32, BF16, I16 = 0, 1, 2
 EXTRACTOR_DEFAULT, EXTRACTOR_LAYER_NORM = 0, 1
 POS_SIN, POS_CONV = 0, 1
 LAYOUT_BTD, LAYOUT_TBD = 0, 1
-GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, GEMM_TCGEN05_2CTA, GEMM_SKINNY = 0, 1, 2, 3, 4
+GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05_2CTA, GEMM_SKINNY = 0, 1, 3, 4
 EPI_GELU = 1
 
 

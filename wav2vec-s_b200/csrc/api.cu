@@ -439,12 +439,7 @@ w2vs_status_t launch_gemm(int impl, const GemmArgs& g, cudaStream_t st) {
   if (impl == W2VS_GEMM_AUTO)
     impl = g.dtype_ab != W2VS_BF16 ? W2VS_GEMM_SIMT : gemm_skinny_applicable(g) ? W2VS_GEMM_SKINNY : W2VS_GEMM_TCGEN05_2CTA;
   if (impl == W2VS_GEMM_SKINNY) return launch_gemm_skinny(g, st);
-  if (impl == W2VS_GEMM_TCGEN05) return launch_gemm_tc(g, st);
-  if (impl == W2VS_GEMM_TCGEN05_2CTA) {
-    // the pair kernel adds the residual in place; anything else goes through the 1-CTA kernel
-    if (g.residual != nullptr && (g.dtype_c != W2VS_F32 || g.residual != (const float*)g.C)) return launch_gemm_tc(g, st);
-    return launch_gemm_tc2(g, st);
-  }
+  if (impl == W2VS_GEMM_TCGEN05_2CTA) return launch_gemm_tc2(g, st);   // residual: in place (fp32, residual == C)
   if (impl == W2VS_GEMM_SIMT) return launch_gemm_simt(g, st);
   set_error("invalid value: gemm impl %d", impl);
   return W2VS_INVALID_VALUE;

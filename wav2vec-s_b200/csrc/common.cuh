@@ -67,6 +67,31 @@ static inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 #endif
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- per-device host-side caches ---------------------------------------------------------------------------------
+// cudaFuncSetAttribute and the SM count are properties of one device: everything the launchers remember is keyed
+// by the device that is current on the calling thread, so one process can drive several GPUs (one model replica
+// per device) through the same library.  Races between host threads are benign (idempotent values).
+constexpr int kMaxDevices = 64;
+static inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d >= 0 && d < kMaxDevices ? d : 0;
+}
+struct PerDeviceOnce {
+  bool done[kMaxDevices] = {};
+  bool& here() { return done[current_device()]; }
+};
+static inline int num_sms() {
+  static int n[kMaxDevices] = {};
+  const int d = current_device();
+  if (!n[d]) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d);
+    n[d] = v > 0 ? v : 148;
+  }
+  return n[d];
+}
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- dtype helpers ---------------------------------------------------------------------------

@@ -402,17 +402,31 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     bool ok = true;
     int gt = 0;
     // Key padding.  prep_masks leaves one "any padded key" flag per 128 tokens (pad_blk); the flags of an
-    // utterance (lane j holds block j) are fetched one work item ahead and folded into a bit mask, so the common
-    // case (no padding in a key tile) costs one or two bit tests.  Only flagged tiles (or callers without
-    // pad_blk, or utterances of more than 32 blocks) read their 64 padding bytes (2 per lane).
+    // utterance are fetched one work item ahead and folded into a 32-bit mask, so the common case (no padding in a
+    // key tile) costs one or two bit tests.  Bit j of the mask covers the tokens [j << flag_shift, (j + 1) <<
+    // flag_shift): 128 tokens while the utterance has at most 32 flag blocks (M <= 4096), and 2^fs flag blocks
+    // folded into one bit beyond that (lane j ORs its 2^fs flags), so that every token of an utterance of any
+    // length maps to a bit below 32.  Only flagged tiles (or callers without pad_blk) read their 64 padding bytes
+    // (2 per lane).
     const int pad_stride = (sh.M + 127) >> 7;
-    const bool flags_usable = pad_blk != nullptr && pad_stride <= 32;
-    auto fetch_flags = [&](int b_) -> uint32_t {      // this lane's flag of utterance b_ (raw load, consumed later)
+    const bool flags_usable = pad_blk != nullptr;
+    int fs = 0;
+    while (((pad_stride + (1 << fs) - 1) >> fs) > 32) ++fs;
+    const int flag_shift = 7 + fs;
+    auto fetch_flags = [&](int b_) -> uint32_t {      // this lane's flags of utterance b_ (raw loads, consumed later)
       uint32_t v = 0;
-      if (flags_usable && lane < pad_stride)
-        asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(pad_blk + (size_t)b_ * pad_stride + lane));
+      if (flags_usable) {
+        const int j0 = lane << fs, j1 = min(j0 + (1 << fs), pad_stride);
+        for (int j = j0; j < j1; ++j) {
+          uint32_t u;
+          asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(u) : "l"(pad_blk + (size_t)b_ * pad_stride + j));
+          v |= u;
+        }
+      }
       return v;
     };
+    // flag of the mask bit that covers token `tok` (callers without flags: always "may have padding")
+    auto flagged = [&](uint32_t mask, int tok) -> bool { return !flags_usable || ((mask >> (tok >> flag_shift)) & 1u) != 0; };
     Walker wk, wnext;
     wk.init(sh, vcta);
     wnext = wk;
@@ -445,10 +459,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         int lo = 0;
         uint32_t span = KT;
         bool all_vis[2] = {true, true}, none_vis[2] = {false, false};
-        if (!(it < n_fullvis && ((flag_mask >> (it >> 1)) & 1u) == 0)) {
+        if (!(it < n_fullvis && !flagged(flag_mask, it * KT))) {
           int k0, cnt; bool s1;
           im.ts.get(it, k0, cnt, s1);
-          if (((flag_mask >> (k0 >> 7)) | (flag_mask >> ((k0 + cnt - 1) >> 7))) & 1u) {
+          if (flagged(flag_mask, k0) || flagged(flag_mask, k0 + cnt - 1)) {
             const uint8_t* p_ = keypad + im.row_base + k0;
             const int last = cnt - 1, kr = cnt - 2 * lane;
 #pragma unroll
@@ -683,7 +697,8 @@ w2vs_status_t launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
                         (uint64_t)3 * a.D, HD, QT, CU_TENSOR_MAP_SWIZZLE_128B));
   W2VS_TRY(tc::make_map(&tmkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.qkv, (uint64_t)3 * a.D, (uint64_t)a.B * sh.M,
                         (uint64_t)3 * a.D, HD, KT, CU_TENSOR_MAP_SWIZZLE_128B));
-  static bool attr_done = false;
+  static PerDeviceOnce attr_once;   // the attribute belongs to the current device's copy of the kernel
+  bool& attr_done = attr_once.here();
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) { set_error("attn_tc smem attribute: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }

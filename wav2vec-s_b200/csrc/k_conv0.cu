@@ -209,7 +209,8 @@ static w2vs_status_t launch_one(const Conv0Args& a, cudaStream_t st) {
   W2VS_REQUIRE(a.stride >= 1 && a.stride <= 8, "first conv stride must be <= 8");
   size_t smem = (size_t)(KW * C + 3 * C + ((kFramesPerCta - 1) * 8 + KW + 3) / 4 * 4) * sizeof(float);
   if (MODE == C0_GN_STATS) smem += (size_t)8 * 2 * C * sizeof(float);
-  static bool attr_done = false;
+  static PerDeviceOnce attr_once;   // the attribute belongs to the current device's copy of the kernel
+  bool& attr_done = attr_once.here();
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv0_kernel<TIn, TOut, NI, KW, MODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

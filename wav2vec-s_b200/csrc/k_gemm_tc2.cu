@@ -341,7 +341,8 @@ w2vs_status_t launch_bn(const GemmArgs& g, cudaStream_t st) {
   else
     W2VS_TRY(make_map(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.C, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldc,
                       C2::kChunk, 32, CU_TENSOR_MAP_SWIZZLE_64B));
-  static bool attr_done = false;
+  static PerDeviceOnce attr_once;   // the attribute belongs to the current device's copy of the kernel
+  bool& attr_done = attr_once.here();
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, TC, SLOTS, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C2::kSmemBytes);

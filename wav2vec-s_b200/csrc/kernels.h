@@ -76,12 +76,10 @@ struct GemmArgs {
   int batch; int64_t a_batch_rows, w_batch_rows, c_batch_stride;
 };
 w2vs_status_t launch_gemm_simt(const GemmArgs& g, cudaStream_t st);
-w2vs_status_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st);    // 1-CTA tcgen05 (first version)
 w2vs_status_t launch_gemm_tc2(const GemmArgs& g, cudaStream_t st);   // CTA-pair tcgen05, TMA-store epilogue
 w2vs_status_t launch_gemm_skinny(const GemmArgs& g, cudaStream_t st); // M <= 64 weight-streaming kernel (mma.sync)
 bool gemm_skinny_applicable(const GemmArgs& g);
 w2vs_status_t launch_gemm(int impl, const GemmArgs& g, cudaStream_t st);  // impl: w2vs_gemm_impl_t
-w2vs_status_t debug_read_tc_fault(int* out);
 w2vs_status_t debug_read_tc2_fault(int* out);
 
 // ---- attention ------------------------------------------------------------------------------------

@@ -257,8 +257,14 @@ w2vs_status_t w2vs_stream_step(const w2vs_config* cfg, const void* d_packed, voi
   // a decision step is a chain of ~200 short kernels: launch the PDL-aware ones (common.cuh) as programmatic
   // dependents so that their launch latency hides under their predecessors
   struct PdlScope { PdlScope() { g_pdl_on = true; } ~PdlScope() { g_pdl_on = false; } } pdl_scope;
-  StreamHost* hs = reinterpret_cast<StreamHost*>(host_state);
-  W2VS_REQUIRE(hs->magic == kMagic, "host_state was not initialised by w2vs_stream_init");
+  // The step works on a copy of the host-side bookkeeping and commits it only after its last launch succeeded: a
+  // launch error in the middle of the chain leaves `host_state` describing the state before the call.  The device
+  // side tolerates that: conv carries are double buffered (the step writes the "next" buffers), frames and K/V rows
+  // are appended behind the committed counts, so repeating the call overwrites what the failed one left.
+  StreamHost* const hs_committed = reinterpret_cast<StreamHost*>(host_state);
+  W2VS_REQUIRE(hs_committed->magic == kMagic, "host_state was not initialised by w2vs_stream_init");
+  StreamHost hs_work = *hs_committed;
+  StreamHost* const hs = &hs_work;
   W2VS_REQUIRE(!hs->finished, "stream already finished");
   W2VS_REQUIRE(n_new >= 0 && n_new <= hs->max_new, "n_new exceeds max_new_samples");
   W2VS_REQUIRE(n_new == 0 || d_new != nullptr, "d_new_samples is NULL");
@@ -409,6 +415,7 @@ w2vs_status_t w2vs_stream_step(const w2vs_config* cfg, const void* d_packed, voi
     }
   }
   if (flush == W2VS_FLUSH_FINAL) hs->finished = 1;
+  *hs_committed = hs_work;
   *n_out = written;
   return W2VS_OK;
 }

@@ -256,16 +256,7 @@ inline w2vs_status_t make_map3(CUtensorMap* map, CUtensorMapDataType dt, int ele
   return W2VS_OK;
 }
 
-inline int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+using ::w2vs::num_sms;
 
 }  // namespace tc
 }  // namespace w2vs
