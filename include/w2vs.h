@@ -32,7 +32,7 @@ extern "C" {
 #endif
 
 #define W2VS_MAX_CONV 8
-#define W2VS_ABI_VERSION 1
+#define W2VS_ABI_VERSION 2
 
 typedef enum {
   W2VS_OK = 0,
@@ -72,7 +72,10 @@ typedef struct {
   int32_t conv_pos_groups;             /* 16 */
   int32_t seq_multiple;                /* required_seq_len_multiple (2) */
   int32_t sin_rows;                    /* rows of the sinusoidal table handed to pack (>= T+2) */
-  int32_t reserved[7];
+  int32_t stream_step_impl;            /* incremental mode: 0 = auto (one persistent cooperative kernel per decision
+                                          step where it applies: bf16, <= 32 tokens per step), 1 = always the
+                                          kernel-per-operator chain (the fp32 mode's path; A/B and cross-checks) */
+  int32_t reserved[6];
 } w2vs_config;
 
 /* ---- reference tensors handed to w2vs_weights_pack -------------------------------------

@@ -152,3 +152,38 @@ def test_stream_takes_pcm16_chunks():
     y = torch.cat(outs, 0).cpu()
     assert tuple(y.shape) == tuple(ref.shape)
     assert valid_rel_err(y, ref) < TOL[torch.float32]
+
+
+@pytest.mark.parametrize("pre_ln", [True, False], ids=["preln", "postln"])
+@pytest.mark.parametrize("B,main,rc", [(1, 16, 8), (2, 8, 4), (1, 20, 10), (3, 6, 2)])
+def test_fused_step_kernel_equals_operator_chain(pre_ln, B, main, rc):
+    """bf16 decision steps run as one persistent cooperative kernel (k_stream_fused.cu) when a step has at most 32
+    tokens; the kernel-per-operator chain (stream_step_impl = 1) computes the same rows with the same roundings, up
+    to summation order.  Irregular chunks, so that steps of every size (full blocks, the short blocks of the final
+    flush) and several blocks per call occur; both against each other and against the oracle's offline rows."""
+    from oracle import synth
+    cfg = cases.tiny(layer_norm_first=pre_ln, conv_bias=pre_ln, main_context=main, right_context=rc,
+                     encoder_layers=4)
+    sd = synth.make_state_dict(cfg, 40 + main)
+    L = 26000
+    wav = synth.make_waveform(B, L, 50 + main)
+    m = build(cfg, sd, torch.bfloat16)
+    ref, _ = O.rain_forward(sd, cfg, wav, None, finished=True, is_infer=True)
+    src = wav.cuda()
+    ys = []
+    for impl in (0, 1):
+        rs = np.random.RandomState(3)
+        st = m.open_stream(B=B, max_seconds=3.0, max_new_samples=9000, step_impl=impl)
+        W.cabi.launch_count(reset=True)
+        outs, pos = [], 0
+        while pos < L:
+            n = min(int(rs.choice([37, 400, 1600, 5120, 8999])), L - pos)
+            outs.append(st.step(src[:, pos:pos + n], EncoderStream.FINAL if pos + n >= L else EncoderStream.NONE))
+            pos += n
+        torch.cuda.synchronize()
+        ys.append((torch.cat(outs, 0).float().cpu(), W.cabi.launch_count(reset=True)))
+    (y_fused, n_fused), (y_chain, n_chain) = ys
+    assert n_fused < n_chain                      # the fused path really ran (far fewer launches)
+    assert tuple(y_fused.shape) == tuple(ref.shape)
+    assert valid_rel_err(y_fused, y_chain) < 1e-2
+    assert valid_rel_err(y_fused, ref) < TOL[torch.bfloat16] and valid_rel_err(y_chain, ref) < TOL[torch.bfloat16]

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("W2VS_LIBRARY") or os.path.join(HERE, "lib", "libw2vs.so")
 
 W2VS_MAX_CONV = 8
-W2VS_ABI_VERSION = 1
+W2VS_ABI_VERSION = 2
 OK, INVALID_VALUE, UNSUPPORTED, WORKSPACE_TOO_SMALL, CUDA_ERROR = range(5)
 F32, BF16, I16 = 0, 1, 2
 EXTRACTOR_DEFAULT, EXTRACTOR_LAYER_NORM = 0, 1
@@ -36,7 +36,7 @@ class Config(C.Structure):
         ("ffn_dim", C.c_int32), ("heads", C.c_int32), ("layers", C.c_int32),
         ("layer_norm_first", C.c_int32), ("pos_type", C.c_int32), ("conv_pos", C.c_int32),
         ("conv_pos_groups", C.c_int32), ("seq_multiple", C.c_int32), ("sin_rows", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("stream_step_impl", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -92,7 +92,7 @@ PROTOTYPES = {
 
 # kernel name -> class reported by bench.py
 KERNEL_CLASS = {"gemm_tc_kernel": "gemm", "gemm_tc2_kernel": "gemm", "gemm_simt_kernel": "gemm_simt", "attn_mma_kernel": "attention", "attn_tc_kernel": "attention",
-                "attn_simt_kernel": "attention", "conv0_kernel": "conv0"}
+                "attn_simt_kernel": "attention", "conv0_kernel": "conv0", "stream_fused_kernel": "stream_fused"}
 
 _lib = None
 

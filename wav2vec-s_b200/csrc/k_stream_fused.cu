@@ -1,0 +1,806 @@
+// One decision step of the incremental encoder as ONE persistent cooperative kernel (bf16 models).
+//
+// What it replaces: the chain embed -> 24 x [LN, QKV, attention, out_proj, LN, fc1, fc2] -> final LN of stream.cu's
+// block_step (the reference computes the same rows by re-encoding the whole prefix, rain/simul/transducer_agent.py:
+// 138-167; layer arithmetic wav2vec2.py:921-978, attention modules/multihead_attention.py:162-194).  A step is at
+// most 32 tokens, so its arithmetic is negligible; its cost as ~170 dependent launches was launch latency (7.5 us
+// per link) against an HBM floor of 0.1 ms for reading the 613 MB of weights once.  Here the whole step is one
+// grid of one CTA per SM:
+//   * phases separated by grid barriers (one 64-bit arrival counter in global memory, self-resetting):
+//       per layer  [LN + QKV -> q, K/V cache]  |  [attention over the cache, keys split over CTAs]  |
+//                  [out_proj + residual]  |  [LN + fc1 + GELU]  |  [fc2 + residual],   then the final LayerNorm;
+//   * every matrix product is split over the CTAs by output columns (units of 8 weight rows, CTA c owns units
+//     c, c + G, ...), so that each CTA streams a fixed, contiguous share of every weight matrix;
+//   * a producer cursor walks that share for ALL layers ahead of time: 8 x KC slabs of W go global -> shared with
+//     cp.async.bulk into a ring of stages (full/empty mbarriers).  Weights do not depend on activations, so the HBM
+//     stream never stops at a phase boundary.  The cursor belongs to thread 0 and is advanced without blocking
+//     ("pump") wherever that thread has nothing better to do: while it spins in a grid barrier, after every stage
+//     its warp has consumed, between attention items.  (A dedicated ninth producer warp would cap the kernel at
+//     168 registers per thread -- warps are allocated in fours -- and the product phases want more.);
+//   * 8 consumer warps split K eight ways (mma.sync.m16n8k16, bf16, fp32 accumulate; the k index inside a 16-step
+//     is permuted identically for A and W so that both are read with 8-byte accesses), partial sums are reduced
+//     through shared memory in a fixed order (deterministic), then bias / GELU / residual;
+//   * LayerNorm is computed by every CTA for all rows (fp32 statistics from the fp32 residual stream, bf16 operand
+//     rows in shared memory); post-LN models keep the un-normalised sum in the residual buffer and apply the
+//     pending LayerNorm when the value is next read (operand rows, residual term, final output);
+//   * attention: one (stream, head, key split) item per group of 4 warps, K/V tiles from the cache via cp.async,
+//     flash-style mma.sync, split results merged by the group that finishes a (stream, head) last.
+// Numerically the step matches the multi-kernel path up to summation order (same bf16 roundings: operand rows,
+// q/k/v, P, context, FFN hidden; fp32 residual stream and statistics).
+#include <cuda.h>
+#include <math.h>
+#include "common.cuh"
+#include "kernels.h"
+#include "layout.h"
+
+namespace w2vs {
+__device__ int g_fused_fault = 0;   // set when a barrier / pipeline wait timed out (diagnostics)
+}
+#define W2VS_TC_FAULT_FLAG (&::w2vs::g_fused_fault)
+#include "tc_common.cuh"
+
+namespace w2vs {
+namespace {
+using namespace tc;
+
+constexpr int FS_CW = 8;                        // warps: all of them consume; thread 0 also drives the weight ring
+constexpr int FS_THREADS = 32 * FS_CW;
+constexpr int FS_ROWS = 32;                     // token rows of a step (two m16 tiles)
+constexpr int FS_UMAX = 4;                      // 8-column units of one product a CTA may own
+constexpr int FS_MAX_STAGES = 12;
+constexpr int FS_KT = 64;                       // attention key tile
+constexpr int FS_ATT_GROUP_BYTES = 5 * 8192;    // Q + 2 K + 2 V tiles of 64 x 64 bf16
+constexpr int FS_MAX_SPLITS = 16;
+constexpr int FS_SMEM_LIMIT = 232448;
+constexpr unsigned long long FS_TIMEOUT_NS = 2000000000ull;
+
+__device__ __forceinline__ void named_bar(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                          uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// ---- attention tile helpers (64 x 64 bf16 tiles, 16-byte chunks XOR-swizzled by the row) ----
+__device__ __forceinline__ int sw(int row, int chunk) { return row * 64 + ((chunk ^ (row & 7)) << 3); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+struct FusedArgs {
+  const uint8_t* W;                    // packed weights
+  unsigned long long wqkv, bqkv, wo, bo, ln1_w, ln1_b, w1, b1, w2, b2, ln2_w, ln2_b;   // layer 0 offsets (bytes)
+  unsigned long long layer_stride, enc_ln_w, enc_ln_b, sin_table;
+  int layers, D, F, H, pre_ln;
+  int B, ntok, n_main, f0;             // tokens per stream in this step, frames emitted, first frame index
+  const float* feats; long long feat_rows;     // projected frames [B][feat_rows][D] fp32
+  float* R;                            // residual stream [B * ntok][D] fp32
+  bf16* q; bf16* ctx; bf16* h;         // [B * ntok][D], [.][D], [.][F]
+  bf16* kv; long long kv_layer_elems, kv_rows;   // cache [layers][B][kv_rows][2D]
+  float* partials; unsigned* counters; // attention split states [B*H][splits][32][66]; zeroed counters [B*H]
+  bf16* out;                           // [n_main][B][D]
+  unsigned long long* bar;             // [0] arrivals, [1] departures (both zero between launches)
+  int n_stages, n_splits;
+  float scale_log2;
+};
+
+struct Smem {
+  uint32_t ring, uni, stats, bars_full, bars_empty, flags;
+  int stage_bytes, pitch_w, pitch_a;
+};
+
+// One weight matrix of a phase: W [N][K] row-major bf16.
+struct Mat { const bf16* w; int N, K; };
+__device__ __forceinline__ Mat phase_mat(const FusedArgs& a, int layer, int p) {
+  const uint8_t* base = a.W + (size_t)layer * a.layer_stride;
+  Mat m;
+  if (p == 0) { m.w = reinterpret_cast<const bf16*>(base + a.wqkv); m.N = 3 * a.D; m.K = a.D; }
+  else if (p == 1) { m.w = reinterpret_cast<const bf16*>(base + a.wo); m.N = a.D; m.K = a.D; }
+  else if (p == 2) { m.w = reinterpret_cast<const bf16*>(base + a.w1); m.N = a.F; m.K = a.D; }
+  else { m.w = reinterpret_cast<const bf16*>(base + a.w2); m.N = a.D; m.K = a.F; }
+  return m;
+}
+__device__ __forceinline__ const float* lw(const FusedArgs& a, int layer, unsigned long long off) {
+  return reinterpret_cast<const float*>(a.W + (size_t)layer * a.layer_stride + off);
+}
+
+struct Ring { int stage; uint32_t phase; };
+
+// Producer cursor over this CTA's weight slabs in consumption order: layer, product, unit, K chunk.
+struct Prod { int l, p, u, j, stage; uint32_t phase; int done; };
+__device__ __forceinline__ void prod_skip_empty(const FusedArgs& a, Prod& pr, int G) {
+  // move to the next (layer, product) in which this CTA owns a unit
+  while (!pr.done) {
+    const Mat m = phase_mat(a, pr.l, pr.p);
+    if (pr.u < (m.N >> 3)) return;
+    pr.u = blockIdx.x; pr.j = 0;
+    if (++pr.p == 4) { pr.p = 0; if (++pr.l == a.layers) pr.done = 1; }
+  }
+  (void)G;
+}
+// Refill up to `budget` free stages; never blocks.  Thread 0 only.
+__device__ __noinline__ void pump(const FusedArgs& a, const Smem& sm, Prod& pr, int budget) {
+  const int KC = a.D, G = gridDim.x;
+  while (!pr.done && budget-- > 0) {
+    if (!mbar_try_wait(sm.bars_empty + 8 * pr.stage, pr.phase ^ 1)) return;    // not yet released by all 8 warps
+    const Mat m = phase_mat(a, pr.l, pr.p);
+    mbar_expect_tx(sm.bars_full + 8 * pr.stage, 8u * KC * 2u);
+    const bf16* src = m.w + (size_t)pr.u * 8 * m.K + (size_t)pr.j * KC;
+    const uint32_t dst = sm.ring + (uint32_t)pr.stage * sm.stage_bytes;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      bulk_g2s(dst + r * sm.pitch_w, src + (size_t)r * m.K, (uint32_t)KC * 2u, sm.bars_full + 8 * pr.stage);
+    if (++pr.stage == a.n_stages) { pr.stage = 0; pr.phase ^= 1; }
+    if (++pr.j == m.K / KC) { pr.j = 0; pr.u += G; }
+    prod_skip_empty(a, pr, G);
+  }
+}
+
+// Grid-wide barrier for the 256 consumer threads of every CTA.  Arrival counter in global memory, monotonically
+// increasing inside a launch (target = barriers so far x CTAs); the last CTA to leave the kernel resets it.
+__device__ __noinline__ bool grid_barrier(const FusedArgs& a, const Smem& sm, Prod& pr, unsigned long long target,
+                                          volatile int* s_abort) {
+  unsigned long long* bar = a.bar;
+  named_bar(1, 32 * FS_CW);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1ull);
+    pump(a, sm, pr, FS_MAX_STAGES);      // every stage consumed in the phase that just ended is free now
+    unsigned long long v;
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
+      if (v >= target) break;
+      if ((++spins & 0x3ff) == 0) {
+        const unsigned long long now = global_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > FS_TIMEOUT_NS) { atomicExch(&g_fused_fault, 1); *s_abort = 1; break; }
+      }
+    }
+    __threadfence();
+  }
+  named_bar(1, 32 * FS_CW);
+  return *s_abort == 0;
+}
+
+// LayerNorm of one fp32 row held as float4 v[NV] per lane (columns 4 lane + 128 j): returns mean / rstd.
+template <int NVMAX>
+__device__ __forceinline__ void row_stats(const float4 (&v)[NVMAX], int nv, int D, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NVMAX; ++j) if (j < nv) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NVMAX; ++j)
+    if (j < nv) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      q = fmaf(a, a, q); q = fmaf(b, b, q); q = fmaf(c, c, q); q = fmaf(d, d, q);
+    }
+  rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+}
+
+// ---- LN phase prologue: operand rows A = bf16(LN(R)) into shared memory, row statistics into `stats` ----
+__device__ __noinline__ void ln_rows_to_smem(const FusedArgs& a, const Smem& sm, uint8_t* smem_gen, int warp, int lane,
+                                                const float* gamma, const float* beta) {
+  const int Mt = a.B * a.ntok, D = a.D, nv = D >> 7;
+  float* stats = reinterpret_cast<float*>(smem_gen + (sm.stats - sm.ring));
+  for (int row = warp; row < FS_ROWS; row += FS_CW) {
+    uint8_t* dst = smem_gen + (sm.uni - sm.ring) + (size_t)row * sm.pitch_a;
+    if (row < Mt) {
+      float4 v[8];
+      const float* xr = a.R + (size_t)row * D + 4 * lane;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (j < nv) v[j] = __ldcg(reinterpret_cast<const float4*>(xr + 128 * j));
+      float mean, rstd;
+      row_stats<8>(v, nv, D, mean, rstd);
+      if (lane == 0) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nv) {
+          const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * lane + 128 * j);
+          const float4 bt = *reinterpret_cast<const float4*>(beta + 4 * lane + 128 * j);
+          uint2 u;
+          u.x = pack_bf16x2((v[j].x - mean) * rstd * g.x + bt.x, (v[j].y - mean) * rstd * g.y + bt.y);
+          u.y = pack_bf16x2((v[j].z - mean) * rstd * g.z + bt.z, (v[j].w - mean) * rstd * g.w + bt.w);
+          *reinterpret_cast<uint2*>(dst + (4 * lane + 128 * j) * 2) = u;
+        }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (j < nv) *reinterpret_cast<uint2*>(dst + (4 * lane + 128 * j) * 2) = make_uint2(0u, 0u);
+    }
+  }
+}
+
+enum { EPI_QKV = 0, EPI_RESID = 1, EPI_GELU = 2 };
+
+// One matrix product of a phase for this CTA's units.  A operand: shared-memory rows (a_glob == nullptr, LN phases)
+// or a global bf16 matrix [rows][lda] read through L2.
+template <int MT>
+__device__ __noinline__ bool gemm_phase(const FusedArgs& a, const Smem& sm, uint8_t* smem_gen, Ring& rs, Prod& pr, int layer,
+                                           int N, int K, const bf16* a_glob, int lda, int epi, const float* bias,
+                                           const float* res_gamma, const float* res_beta, int warp, int lane) {
+  const int G = gridDim.x, cta = blockIdx.x;
+  const int D = a.D, KC = D, Mt = a.B * a.ntok;
+  const int kw = KC / FS_CW, nsteps = kw >> 4, nch = K / KC;
+  const int g = lane >> 2, q = lane & 3;
+  const int units_total = N >> 3;
+  const int n_units = units_total > cta ? (units_total - 1 - cta) / G + 1 : 0;
+  float* part = reinterpret_cast<float*>(smem_gen + (sm.uni - sm.ring) + (size_t)FS_ROWS * sm.pitch_a);
+  const float* stats = reinterpret_cast<const float*>(smem_gen + (sm.stats - sm.ring));
+
+  float acc[FS_UMAX][MT][4];
+#pragma unroll
+  for (int i = 0; i < FS_UMAX; ++i)
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][mt][e] = 0.f;
+
+  uint2 af[MT][2][8];
+  auto load_a = [&](int j) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int row = mt * 16 + g + 8 * hf;
+        if (a_glob == nullptr) {
+          const uint32_t base = sm.uni + (uint32_t)row * sm.pitch_a + (uint32_t)(warp * kw + 4 * q) * 2;
+#pragma unroll
+          for (int s = 0; s < 8; ++s) if (s < nsteps) af[mt][hf][s] = lds64(base + s * 32);
+        } else {
+          const bf16* p = a_glob + (size_t)min(row, Mt - 1) * lda + (size_t)j * KC + warp * kw + 4 * q;
+#pragma unroll
+          for (int s = 0; s < 8; ++s) if (s < nsteps) af[mt][hf][s] = __ldcg(reinterpret_cast<const uint2*>(p + 16 * s));
+        }
+      }
+  };
+  if (n_units > 0 && nch == 1) load_a(0);
+
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < FS_UMAX; ++i) {
+    if (i < n_units) {
+      for (int j = 0; j < nch; ++j) {
+        if (nch > 1) load_a(j);
+        ok = mbar_wait(sm.bars_full + 8 * rs.stage, rs.phase) && ok;
+        const uint32_t wrow = sm.ring + (uint32_t)rs.stage * sm.stage_bytes + (uint32_t)g * sm.pitch_w +
+                              (uint32_t)(warp * kw + 4 * q) * 2;
+        uint2 bw[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) if (s < nsteps) bw[s] = lds64(wrow + s * 32);
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          if (s < nsteps) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+              mma_16816(acc[i][mt], af[mt][0][s].x, af[mt][1][s].x, af[mt][0][s].y, af[mt][1][s].y, bw[s].x, bw[s].y);
+          }
+        // the MMAs have consumed the registers, so every lane's loads from the stage have completed: hand the
+        // stage back to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sm.bars_empty + 8 * rs.stage);
+        if (++rs.stage == a.n_stages) { rs.stage = 0; rs.phase ^= 1; }
+        if (threadIdx.x == 0) pump(a, sm, pr, 2);
+      }
+    }
+  }
+  // ---- partial sums of the 8 K slices -> shared memory
+#pragma unroll
+  for (int i = 0; i < FS_UMAX; ++i)
+    if (i < n_units) {
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        float* p0 = part + (((size_t)warp * FS_UMAX + i) * FS_ROWS + mt * 16 + g) * 8 + 2 * q;
+        *reinterpret_cast<float2*>(p0) = make_float2(acc[i][mt][0], acc[i][mt][1]);
+        *reinterpret_cast<float2*>(p0 + 64) = make_float2(acc[i][mt][2], acc[i][mt][3]);
+      }
+    }
+  named_bar(1, 32 * FS_CW);
+  // ---- fixed-order reduction + epilogue: one thread per (unit, row), 8 consecutive columns
+  const int tid = threadIdx.x;
+  if (tid < n_units * Mt) {
+    const int i = tid / Mt, r = tid - i * Mt;
+    const int n0 = (cta + i * G) * 8;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+#pragma unroll
+    for (int w = 0; w < FS_CW; ++w) {
+      const float* p = part + (((size_t)w * FS_UMAX + i) * FS_ROWS + r) * 8;
+      const float4 x0 = *reinterpret_cast<const float4*>(p), x1 = *reinterpret_cast<const float4*>(p + 4);
+      v[0] += x0.x; v[1] += x0.y; v[2] += x0.z; v[3] += x0.w; v[4] += x1.x; v[5] += x1.y; v[6] += x1.z; v[7] += x1.w;
+    }
+    float bb[8];
+    load8(bias + n0, bb);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] += bb[e];
+    if (epi == EPI_QKV) {
+      bf16* dst;
+      if (n0 < D) dst = a.q + (size_t)r * D + n0;
+      else {
+        const int b = r / a.ntok, t = r - b * a.ntok;
+        dst = a.kv + (size_t)layer * a.kv_layer_elems + ((size_t)b * a.kv_rows + a.f0 + t) * (2 * D) + (n0 - D);
+      }
+      store8(dst, v);
+    } else if (epi == EPI_GELU) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = gelu_tanh(v[e]);
+      store8(a.h + (size_t)r * a.F + n0, v);
+    } else {
+      float* xr = a.R + (size_t)r * D + n0;
+      const float4 o0 = __ldcg(reinterpret_cast<const float4*>(xr)), o1 = __ldcg(reinterpret_cast<const float4*>(xr + 4));
+      float o[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+      if (res_gamma != nullptr) {     // post-LN: the residual term is the pending LayerNorm of the stored sum
+        const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+        float gg[8], bt[8];
+        load8(res_gamma + n0, gg);
+        load8(res_beta + n0, bt);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (o[e] - mean) * rstd * gg[e] + bt[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += o[e];
+      store8(xr, v);
+    }
+  }
+  return ok;
+}
+
+// ---- attention over the K/V cache: items (stream, head, key split) on groups of 4 warps ----
+__device__ __forceinline__ void load_tile(bf16* tile, const bf16* src, long long row_stride, int first_row, int n_rows,
+                                          int gtid) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int c = gtid + 128 * r;
+    const int row = c >> 3, chunk = c & 7;
+    const bool ok = row < n_rows;
+    const bf16* gp = src + (size_t)(first_row + (ok ? row : 0)) * row_stride + chunk * 8;
+    cp_async16(smem_u32(tile + sw(row, chunk)), gp, ok);
+  }
+}
+
+__device__ __noinline__ void attention_phase(const FusedArgs& a, const Smem& sm, uint8_t* smem_gen, Prod& pr, int layer,
+                                            int warp, int lane) {
+  const int G = gridDim.x, cta = blockIdx.x;
+  const int gi = warp >> 2, wi = warp & 3, gtid = threadIdx.x & 127;
+  const int mt = wi & 1, par = wi >> 1;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int D = a.D, H = a.H, S = a.n_splits, ntok = a.ntok;
+  const int n_keys = a.f0 + ntok, n_kt = (n_keys + FS_KT - 1) / FS_KT, per = (n_kt + S - 1) / S;
+  const long long krs = 2ll * D;
+  bf16* Qs = reinterpret_cast<bf16*>(smem_gen + (sm.uni - sm.ring) + (size_t)gi * FS_ATT_GROUP_BYTES);
+  bf16* Ks = Qs + 4096;          // [2][64 x 64]
+  bf16* Vs = Ks + 2 * 4096;      // [2][64 x 64]
+  int* s_last = reinterpret_cast<int*>(smem_gen + (sm.flags - sm.ring)) + 4 + gi;
+  const bf16* kv_l = a.kv + (size_t)layer * a.kv_layer_elems;
+  const float sl2 = a.scale_log2;
+  const bool active = mt * 16 < ntok;      // this warp's 16 query rows exist
+
+  for (int item = cta * 2 + gi; item < a.B * H * S; item += 2 * G) {
+    if (threadIdx.x == 0) pump(a, sm, pr, 2);
+    const int sp = item % S, bh = item / S, h = bh % H, b = bh / H;
+    const int t_begin = min(sp * per, n_kt), t_end = min(t_begin + per, n_kt);
+    const bf16* qbase = a.q + (size_t)b * ntok * D + (size_t)h * 64;
+    const bf16* kbase = kv_l + (size_t)b * a.kv_rows * krs + (size_t)h * 64;
+    const bf16* vbase = kbase + D;
+    uint32_t qf[4][4];
+    float o[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+    for (int t0 = t_begin; t0 < t_end; t0 += 2) {
+      if (t0 == t_begin) load_tile(Qs, qbase, D, 0, ntok, gtid);
+#pragma unroll
+      for (int p = 0; p < 2; ++p)
+        if (t0 + p < t_end) {
+          const int k0 = (t0 + p) * FS_KT, cnt = min(FS_KT, n_keys - k0);
+          load_tile(Ks + p * 4096, kbase, krs, k0, cnt, gtid);
+          load_tile(Vs + p * 4096, vbase, krs, k0, cnt, gtid);
+        }
+      cp_async_commit();
+      cp_async_wait_all();
+      named_bar(2 + gi, 128);
+      if (t0 == t_begin) {
+        const int row = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) ldsm_x4(smem_u32(Qs + sw(row, kk * 2 + (lane >> 4))), qf[kk]);
+      }
+      if (active && t0 + par < t_end) {
+        const bf16* Kt = Ks + par * 4096;
+        const bf16* Vt = Vs + par * 4096;
+        const int cnt = min(FS_KT, n_keys - (t0 + par) * FS_KT);
+        float s[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+          for (int jp = 0; jp < 4; ++jp) {
+            uint32_t kf[4];
+            const int mi = lane >> 3;
+            const int row = jp * 16 + (lane & 7) + (mi >> 1) * 8;
+            ldsm_x4(smem_u32(Kt + sw(row, kk * 2 + (mi & 1))), kf);
+            mma_16816(s[2 * jp], qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], kf[0], kf[1]);
+            mma_16816(s[2 * jp + 1], qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], kf[2], kf[3]);
+          }
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const bool vis = j * 8 + 2 * t4 + e < cnt;      // keys past the end of the cache (tile tail)
+            s[j][e] = vis ? s[j][e] : -INFINITY;
+            s[j][2 + e] = vis ? s[j][2 + e] : -INFINITY;
+            mx0 = fmaxf(mx0, s[j][e]);
+            mx1 = fmaxf(mx1, s[j][2 + e]);
+          }
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        const float ms0 = mn0 == -INFINITY ? 0.f : mn0 * sl2;
+        const float ms1 = mn1 == -INFINITY ? 0.f : mn1 * sl2;
+        const float a0 = exp2f(m0 * sl2 - ms0), a1 = exp2f(m1 * sl2 - ms1);
+        m0 = mn0; m1 = mn1;
+        float sum0 = 0.f, sum1 = 0.f;
+        uint32_t pf[8][2];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float p0 = exp2f(fmaf(s[j][0], sl2, -ms0)), p1 = exp2f(fmaf(s[j][1], sl2, -ms0));
+          const float p2 = exp2f(fmaf(s[j][2], sl2, -ms1)), p3 = exp2f(fmaf(s[j][3], sl2, -ms1));
+          sum0 += p0 + p1;
+          sum1 += p2 + p3;
+          pf[j][0] = pack_bf16x2(p0, p1);
+          pf[j][1] = pack_bf16x2(p2, p3);
+        }
+        l0 = l0 * a0 + sum0;
+        l1 = l1 * a1 + sum1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { o[j][0] *= a0; o[j][1] *= a0; o[j][2] *= a1; o[j][3] *= a1; }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+          for (int jp = 0; jp < 4; ++jp) {
+            uint32_t vf[4];
+            const int mi = lane >> 3;
+            const int row = kk * 16 + (lane & 7) + (mi & 1) * 8;
+            ldsm_x4_trans(smem_u32(Vt + sw(row, jp * 2 + (mi >> 1))), vf);
+            mma_16816(o[2 * jp], pf[2 * kk][0], pf[2 * kk][1], pf[2 * kk + 1][0], pf[2 * kk + 1][1], vf[0], vf[1]);
+            mma_16816(o[2 * jp + 1], pf[2 * kk][0], pf[2 * kk][1], pf[2 * kk + 1][0], pf[2 * kk + 1][1], vf[2], vf[3]);
+          }
+        }
+      }
+      named_bar(2 + gi, 128);       // both tiles consumed before the next pass (or the merge scratch) overwrites them
+    }
+    // ---- row sums across the quad, then the odd-tile warps hand their state to the even-tile warps
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    float* scr = reinterpret_cast<float*>(Ks) + (size_t)mt * 16 * 66;     // [2 m-tiles][16 rows][66]
+    if (par == 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        *reinterpret_cast<float2*>(scr + g * 66 + j * 8 + 2 * t4) = make_float2(o[j][0], o[j][1]);
+        *reinterpret_cast<float2*>(scr + (g + 8) * 66 + j * 8 + 2 * t4) = make_float2(o[j][2], o[j][3]);
+      }
+      if (t4 == 0) {
+        *reinterpret_cast<float2*>(scr + g * 66 + 64) = make_float2(m0, l0);
+        *reinterpret_cast<float2*>(scr + (g + 8) * 66 + 64) = make_float2(m1, l1);
+      }
+    }
+    named_bar(2 + gi, 128);
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+    if (par == 0) {
+      const float2 ml0 = *reinterpret_cast<const float2*>(scr + g * 66 + 64);
+      const float2 ml1 = *reinterpret_cast<const float2*>(scr + (g + 8) * 66 + 64);
+      const float M0 = fmaxf(m0, ml0.x), M1 = fmaxf(m1, ml1.x);
+      const float wa0 = m0 == -INFINITY ? 0.f : exp2f((m0 - M0) * sl2), wb0 = ml0.x == -INFINITY ? 0.f : exp2f((ml0.x - M0) * sl2);
+      const float wa1 = m1 == -INFINITY ? 0.f : exp2f((m1 - M1) * sl2), wb1 = ml1.x == -INFINITY ? 0.f : exp2f((ml1.x - M1) * sl2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 x0 = *reinterpret_cast<const float2*>(scr + g * 66 + j * 8 + 2 * t4);
+        const float2 x1 = *reinterpret_cast<const float2*>(scr + (g + 8) * 66 + j * 8 + 2 * t4);
+        o[j][0] = o[j][0] * wa0 + x0.x * wb0; o[j][1] = o[j][1] * wa0 + x0.y * wb0;
+        o[j][2] = o[j][2] * wa1 + x1.x * wb1; o[j][3] = o[j][3] * wa1 + x1.y * wb1;
+      }
+      l0 = l0 * wa0 + ml0.y * wb0; l1 = l1 * wa1 + ml1.y * wb1;
+      m0 = M0; m1 = M1;
+      if (S > 1) {
+        float* P = a.partials + ((size_t)bh * S + sp) * (size_t)(FS_ROWS * 66);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          *reinterpret_cast<float2*>(P + r0 * 66 + j * 8 + 2 * t4) = make_float2(o[j][0], o[j][1]);
+          *reinterpret_cast<float2*>(P + r1 * 66 + j * 8 + 2 * t4) = make_float2(o[j][2], o[j][3]);
+        }
+        if (t4 == 0) {
+          *reinterpret_cast<float2*>(P + r0 * 66 + 64) = make_float2(m0, l0);
+          *reinterpret_cast<float2*>(P + r1 * 66 + 64) = make_float2(m1, l1);
+        }
+        __threadfence();
+      } else {
+        const float i0 = l0 > 0.f ? 1.0f / l0 : 0.f, i1 = l1 > 0.f ? 1.0f / l1 : 0.f;
+        bf16* c0 = a.ctx + ((size_t)b * ntok + r0) * D + (size_t)h * 64 + 2 * t4;
+        bf16* c1 = a.ctx + ((size_t)b * ntok + r1) * D + (size_t)h * 64 + 2 * t4;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (r0 < ntok) *reinterpret_cast<uint32_t*>(c0 + j * 8) = pack_bf16x2(o[j][0] * i0, o[j][1] * i0);
+          if (r1 < ntok) *reinterpret_cast<uint32_t*>(c1 + j * 8) = pack_bf16x2(o[j][2] * i1, o[j][3] * i1);
+        }
+      }
+    }
+    if (S > 1) {
+      named_bar(2 + gi, 128);
+      if (gtid == 0) *s_last = atomicAdd(a.counters + bh, 1u) == (unsigned)S - 1;
+      named_bar(2 + gi, 128);
+      if (*s_last) {
+        __threadfence();
+        const float* P0 = a.partials + (size_t)bh * S * (size_t)(FS_ROWS * 66);
+        for (int idx = gtid; idx < ntok * 8; idx += 128) {
+          const int row = idx >> 3, chunk = idx & 7;
+          float mx = -INFINITY;
+          for (int s2 = 0; s2 < S; ++s2) mx = fmaxf(mx, __ldcg(P0 + (size_t)s2 * FS_ROWS * 66 + row * 66 + 64));
+          float accv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, lsum = 0.f;
+          for (int s2 = 0; s2 < S; ++s2) {
+            const float* pr = P0 + (size_t)s2 * FS_ROWS * 66 + row * 66;
+            const float2 ml = __ldcg(reinterpret_cast<const float2*>(pr + 64));
+            if (ml.x == -INFINITY) continue;
+            const float w = exp2f((ml.x - mx) * sl2);
+            lsum = fmaf(ml.y, w, lsum);
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+              const float2 ov = __ldcg(reinterpret_cast<const float2*>(pr + chunk * 8 + e));
+              accv[e] = fmaf(ov.x, w, accv[e]);
+              accv[e + 1] = fmaf(ov.y, w, accv[e + 1]);
+            }
+          }
+          const float inv = lsum > 0.f ? 1.0f / lsum : 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) accv[e] *= inv;
+          store8(a.ctx + ((size_t)b * ntok + row) * D + (size_t)h * 64 + chunk * 8, accv);
+        }
+        if (gtid == 0) a.counters[bh] = 0u;      // the next use is a grid barrier away
+      }
+      named_bar(2 + gi, 128);     // s_last and the scratch are reused by the group's next item
+    }
+  }
+}
+
+template <int MT>
+__global__ void __launch_bounds__(FS_THREADS, 1)
+stream_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ Smem sm) {
+  extern __shared__ uint8_t smem_raw[];
+  // `sm` holds offsets from a 1024-aligned base inside the dynamic shared memory (the ring sits at offset 0)
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));     // generic pointer to the ring
+  Smem s = sm;
+  s.ring += base; s.uni += base; s.stats += base; s.bars_full += base; s.bars_empty += base; s.flags += base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x, cta = blockIdx.x;
+  volatile int* s_abort = reinterpret_cast<volatile int*>(smem_gen + (s.flags - s.ring));
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < a.n_stages; ++i) { mbar_init(s.bars_full + 8 * i, 1); mbar_init(s.bars_empty + 8 * i, FS_CW); }
+    *s_abort = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+  }
+  __syncthreads();
+  Prod pr{0, 0, cta, 0, 0, 0u, 0};
+  if (threadIdx.x == 0) {
+    prod_skip_empty(a, pr, G);
+    pump(a, s, pr, FS_MAX_STAGES);       // the weight stream starts before anything else
+  }
+
+  const int D = a.D, Mt = a.B * a.ntok, nv = D >> 7;
+  unsigned long long nbar = 0;
+  Ring rs{0, 0};
+  bool ok = true;
+  // ---- embed: R = projected frame + sinusoidal position (absolute index frame + 2), one warp per row
+  for (int row = cta * FS_CW + warp; row < Mt; row += G * FS_CW) {
+    const int b = row / a.ntok, t = row - b * a.ntok;
+    const float* fr = a.feats + ((size_t)b * a.feat_rows + a.f0 + t) * D + 4 * lane;
+    const float* ps = reinterpret_cast<const float*>(a.W + a.sin_table) + (size_t)(a.f0 + t + 2) * D + 4 * lane;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < nv) {
+        const float4 x = __ldcg(reinterpret_cast<const float4*>(fr + 128 * j));
+        const float4 p = *reinterpret_cast<const float4*>(ps + 128 * j);
+        *reinterpret_cast<float4*>(a.R + (size_t)row * D + 4 * lane + 128 * j) = make_float4(x.x + p.x, x.y + p.y, x.z + p.z, x.w + p.w);
+      }
+  }
+  ok = grid_barrier(a, s, pr, ++nbar * G, s_abort);
+
+  for (int l = 0; l < a.layers && ok; ++l) {
+    // LayerNorm feeding the QKV product / the FFN, and (post-LN) the LayerNorm pending on the stored residual sum
+    const float *g_qkv, *b_qkv, *g_ffn, *b_ffn;
+    if (a.pre_ln) {
+      g_qkv = lw(a, l, a.ln1_w); b_qkv = lw(a, l, a.ln1_b); g_ffn = lw(a, l, a.ln2_w); b_ffn = lw(a, l, a.ln2_b);
+    } else {
+      g_qkv = l == 0 ? reinterpret_cast<const float*>(a.W + a.enc_ln_w) : lw(a, l - 1, a.ln2_w);
+      b_qkv = l == 0 ? reinterpret_cast<const float*>(a.W + a.enc_ln_b) : lw(a, l - 1, a.ln2_b);
+      g_ffn = lw(a, l, a.ln1_w); b_ffn = lw(a, l, a.ln1_b);
+    }
+    // ---- phase 1: LN + QKV
+    ln_rows_to_smem(a, s, smem_gen, warp, lane, g_qkv, b_qkv);
+    named_bar(1, 32 * FS_CW);
+    ok = gemm_phase<MT>(a, s, smem_gen, rs, pr, l, 3 * D, D, nullptr, 0, EPI_QKV, lw(a, l, a.bqkv), nullptr, nullptr, warp, lane) && ok;
+    ok = grid_barrier(a, s, pr, ++nbar * G, s_abort) && ok;
+    if (!ok) break;
+    // ---- phase 2: attention over the cache (this step's K/V rows were appended by phase 1)
+    attention_phase(a, s, smem_gen, pr, l, warp, lane);
+    ok = grid_barrier(a, s, pr, ++nbar * G, s_abort);
+    if (!ok) break;
+    // ---- phase 3: out_proj + residual
+    ok = gemm_phase<MT>(a, s, smem_gen, rs, pr, l, D, D, a.ctx, D, EPI_RESID, lw(a, l, a.bo), a.pre_ln ? nullptr : g_qkv,
+                        a.pre_ln ? nullptr : b_qkv, warp, lane) && ok;
+    ok = grid_barrier(a, s, pr, ++nbar * G, s_abort) && ok;
+    if (!ok) break;
+    // ---- phase 4: LN + fc1 + GELU
+    ln_rows_to_smem(a, s, smem_gen, warp, lane, g_ffn, b_ffn);
+    named_bar(1, 32 * FS_CW);
+    ok = gemm_phase<MT>(a, s, smem_gen, rs, pr, l, a.F, D, nullptr, 0, EPI_GELU, lw(a, l, a.b1), nullptr, nullptr, warp, lane) && ok;
+    ok = grid_barrier(a, s, pr, ++nbar * G, s_abort) && ok;
+    if (!ok) break;
+    // ---- phase 5: fc2 + residual
+    ok = gemm_phase<MT>(a, s, smem_gen, rs, pr, l, D, a.F, a.h, a.F, EPI_RESID, lw(a, l, a.b2), a.pre_ln ? nullptr : g_ffn,
+                        a.pre_ln ? nullptr : b_ffn, warp, lane) && ok;
+    ok = grid_barrier(a, s, pr, ++nbar * G, s_abort) && ok;
+  }
+  if (ok) {
+    // ---- final LayerNorm of the emitted frames: encoder.layer_norm (pre-LN) or the pending final_layer_norm
+    const float* gf = a.pre_ln ? reinterpret_cast<const float*>(a.W + a.enc_ln_w) : lw(a, a.layers - 1, a.ln2_w);
+    const float* bf = a.pre_ln ? reinterpret_cast<const float*>(a.W + a.enc_ln_b) : lw(a, a.layers - 1, a.ln2_b);
+    for (int o = cta * FS_CW + warp; o < a.B * a.n_main; o += G * FS_CW) {
+      const int b = o / a.n_main, t = o - b * a.n_main;
+      const float* xr = a.R + ((size_t)b * a.ntok + t) * D + 4 * lane;
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (j < nv) v[j] = __ldcg(reinterpret_cast<const float4*>(xr + 128 * j));
+      float mean, rstd;
+      row_stats<8>(v, nv, D, mean, rstd);
+      bf16* dst = a.out + ((size_t)t * a.B + b) * D + 4 * lane;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nv) {
+          const float4 gg = *reinterpret_cast<const float4*>(gf + 4 * lane + 128 * j);
+          const float4 bt = *reinterpret_cast<const float4*>(bf + 4 * lane + 128 * j);
+          uint2 u;
+          u.x = pack_bf16x2((v[j].x - mean) * rstd * gg.x + bt.x, (v[j].y - mean) * rstd * gg.y + bt.y);
+          u.y = pack_bf16x2((v[j].z - mean) * rstd * gg.z + bt.z, (v[j].w - mean) * rstd * gg.w + bt.w);
+          *reinterpret_cast<uint2*>(dst + 128 * j) = u;
+        }
+    }
+  }
+  // ---- leave: the last CTA out resets the barrier words for the next launch
+  named_bar(1, 32 * FS_CW);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(a.bar + 1, 1ull) == (unsigned long long)G - 1) {
+      a.bar[0] = 0ull;
+      a.bar[1] = 0ull;
+      __threadfence();
+    }
+  }
+}
+
+}  // namespace
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+bool stream_fused_applicable(const w2vs_config* cfg, int B, int ntok) {
+  const int D = cfg->embed_dim, F = cfg->ffn_dim, G = num_sms();
+  const int max_units = ((3 * D > F ? 3 * D : F) / 8 + G - 1) / G;
+  return cfg->dtype == W2VS_BF16 && D % 128 == 0 && D <= 1024 && F % D == 0 && cfg->heads * 64 == D && ntok >= 1 &&
+         B * ntok <= FS_ROWS && max_units <= FS_UMAX && cfg->pos_type == W2VS_POS_SIN;
+}
+
+w2vs_status_t launch_stream_fused(const StreamFusedArgs& h, cudaStream_t st) {
+  const w2vs_config* cfg = h.cfg;
+  W2VS_REQUIRE(stream_fused_applicable(cfg, h.B, h.ntok), "fused incremental step: configuration not supported");
+  const int D = cfg->embed_dim, F = cfg->ffn_dim, G = num_sms();
+  Smem sm;
+  sm.pitch_w = 2 * D + 32;
+  sm.pitch_a = 2 * D + 32;
+  sm.stage_bytes = 8 * sm.pitch_w;
+  const int a_bytes = FS_ROWS * sm.pitch_a + FS_CW * FS_UMAX * FS_ROWS * 8 * 4;
+  const int uni_bytes = (int)align_up((size_t)(a_bytes > 2 * FS_ATT_GROUP_BYTES ? a_bytes : 2 * FS_ATT_GROUP_BYTES), 1024);
+  const int tail_bytes = 1024;     // stats (256) + barriers (2 x 96) + flags
+  int n_stages = (FS_SMEM_LIMIT - 1024 - uni_bytes - tail_bytes) / sm.stage_bytes;
+  if (n_stages > FS_MAX_STAGES) n_stages = FS_MAX_STAGES;
+  // the ring is topped up at every grid barrier, so it has to hold what one product phase of a CTA consumes
+  const int u_qkv = (3 * D / 8 + G - 1) / G, u_fc1 = (F / 8 + G - 1) / G, u_fc2 = ((D / 8 + G - 1) / G) * (F / D);
+  const int need = u_qkv > u_fc1 ? (u_qkv > u_fc2 ? u_qkv : u_fc2) : (u_fc1 > u_fc2 ? u_fc1 : u_fc2);
+  W2VS_REQUIRE(n_stages >= need && n_stages >= 2, "fused incremental step: shared memory too small for the weight ring");
+  const int ring_bytes = (int)align_up((size_t)n_stages * sm.stage_bytes, 1024);
+  sm.ring = 0;
+  sm.uni = ring_bytes;
+  sm.stats = sm.uni + uni_bytes;
+  sm.bars_full = sm.stats + 256;
+  sm.bars_empty = sm.bars_full + 8 * FS_MAX_STAGES;
+  sm.flags = sm.bars_empty + 8 * FS_MAX_STAGES;
+  const size_t smem_bytes = (size_t)ring_bytes + uni_bytes + tail_bytes + 1024;
+
+  FusedArgs a{};
+  a.W = reinterpret_cast<const uint8_t*>(h.W);
+  const LayerW& l0 = h.wl->layer0;
+  a.wqkv = l0.wqkv; a.bqkv = l0.bqkv; a.wo = l0.wo; a.bo = l0.bo; a.ln1_w = l0.ln1_w; a.ln1_b = l0.ln1_b;
+  a.w1 = l0.w1; a.b1 = l0.b1; a.w2 = l0.w2; a.b2 = l0.b2; a.ln2_w = l0.ln2_w; a.ln2_b = l0.ln2_b;
+  a.layer_stride = h.wl->layer_stride; a.enc_ln_w = h.wl->enc_ln_w; a.enc_ln_b = h.wl->enc_ln_b; a.sin_table = h.wl->sin_table;
+  a.layers = cfg->layers; a.D = D; a.F = F; a.H = cfg->heads; a.pre_ln = cfg->layer_norm_first != 0;
+  a.B = h.B; a.ntok = h.ntok; a.n_main = h.n_main; a.f0 = h.f0;
+  a.feats = h.feats; a.feat_rows = h.feat_rows;
+  a.R = h.R; a.q = (bf16*)h.q; a.ctx = (bf16*)h.ctx; a.h = (bf16*)h.h;
+  a.kv = (bf16*)h.kv; a.kv_layer_elems = h.kv_layer_elems; a.kv_rows = h.kv_rows;
+  a.partials = h.partials; a.counters = h.counters; a.out = (bf16*)h.out; a.bar = h.bar;
+  a.n_stages = n_stages;
+  const int n_kt = (h.f0 + h.ntok + FS_KT - 1) / FS_KT;
+  int splits = (2 * G) / (h.B * cfg->heads);
+  if (splits > n_kt) splits = n_kt;
+  if (splits > FS_MAX_SPLITS) splits = FS_MAX_SPLITS;
+  if (splits > h.max_splits) splits = h.max_splits;
+  if (splits < 1) splits = 1;
+  a.n_splits = splits;
+  a.scale_log2 = 0.125f * 1.4426950408889634f;
+
+  const int mt = (h.B * h.ntok + 15) / 16;
+  void (*kern)(FusedArgs, Smem) = mt <= 1 ? stream_fused_kernel<1> : stream_fused_kernel<2>;
+  static PerDeviceOnce once[2];
+  bool& done = once[mt <= 1 ? 0 : 1].here();
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_LIMIT);
+    if (e != cudaSuccess) { set_error("stream_fused smem attribute: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
+    done = true;
+  }
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)G); lc.blockDim = dim3(FS_THREADS); lc.dynamicSmemBytes = smem_bytes; lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: the grid barriers cannot deadlock
+  attr[0].val.cooperative = 1;
+  lc.attrs = attr; lc.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&lc, kern, a, sm);
+  if (e != cudaSuccess) { set_error("stream_fused_kernel launch: %s", cudaGetErrorString(e)); cudaGetLastError(); return W2VS_CUDA_ERROR; }
+  W2VS_CHECK_LAUNCH("stream_fused_kernel");
+  return W2VS_OK;
+}
+
+w2vs_status_t debug_read_fused_fault(int* out) {
+  int v = 0;
+  cudaError_t e = cudaMemcpyFromSymbol(&v, g_fused_fault, sizeof(int));
+  if (e != cudaSuccess) { set_error("read g_fused_fault: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
+  *out = v;
+  return W2VS_OK;
+}
+
+}  // namespace w2vs

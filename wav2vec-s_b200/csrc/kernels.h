@@ -114,6 +114,23 @@ w2vs_status_t launch_concat_wav(float* dst, int64_t dst_bs, const float* srcA, i
 w2vs_status_t launch_kv_append(const void* qkv, void* cache, int64_t cache_rows, int row0, int n_tok, int D,
                                int elem_bytes, int B, cudaStream_t st);
 
+// ---- fused incremental step (k_stream_fused.cu): embed -> all layers -> final LayerNorm in one cooperative kernel ----
+struct WeightLayout;
+struct StreamFusedArgs {
+  const w2vs_config* cfg; const WeightLayout* wl; const void* W;
+  int B, ntok, n_main, f0;
+  const float* feats; int64_t feat_rows;     // projected frames [B][feat_rows][D]
+  float* R; void* q; void* ctx; void* h;     // workspace: residual stream fp32, q / context / FFN hidden (bf16)
+  void* kv; int64_t kv_layer_elems, kv_rows; // K/V cache [layers][B][kv_rows][2D]
+  float* partials; int max_splits;           // attention split states, room for max_splits x 32 rows x 66 per (stream, head)
+  unsigned* counters;                        // zeroed [B * heads]
+  void* out;                                 // [n_main][B][D] bf16
+  unsigned long long* bar;                   // two zeroed 64-bit words (grid barrier arrivals / departures)
+};
+bool stream_fused_applicable(const w2vs_config* cfg, int B, int ntok);
+w2vs_status_t launch_stream_fused(const StreamFusedArgs& a, cudaStream_t st);
+w2vs_status_t debug_read_fused_fault(int* out);
+
 // ---- positional conv + weight packing -----------------------------------------------------------------
 struct PosConvArgs {
   const float* feats; int feat_rows; const uint8_t* frame_pad;

@@ -44,7 +44,7 @@ struct StreamLayout {
   int new_max[W2VS_MAX_CONV];
   int fcap, kv_rows, ntok_max;
   // device state
-  size_t in[W2VS_MAX_CONV][2], fbuf, kv, kv_layer_bytes, sync, dev_total;
+  size_t in[W2VS_MAX_CONV][2], fbuf, kv, kv_layer_bytes, sync, sync_bytes, fused_bar, dev_total;
   // workspace
   size_t out[2], normed, feats_tmp, x, xa, qkv, ctx, h, attn_part, ws_total;
 };
@@ -105,7 +105,10 @@ w2vs_status_t make_stream_layout(const w2vs_config* cfg, int B, int max_frames, 
   L->kv_layer_bytes = align_up((size_t)B * L->kv_rows * 2 * D * as, 256);
   L->kv = d.take(L->kv_layer_bytes * cfg->layers);
   // completion counters of the split-key step attention, one per (stream, head, query tile); zeroed by w2vs_stream_init
-  L->sync = d.take((size_t)B * cfg->heads * ((L->ntok_max + 63) / 64) * 4);
+  L->sync_bytes = (size_t)B * cfg->heads * ((L->ntok_max + 63) / 64) * 4;
+  L->sync = d.take(L->sync_bytes);
+  // grid-barrier words of the fused step kernel (arrivals, departures): zero between launches
+  L->fused_bar = d.take(64);
   L->dev_total = d.off;
 
   Bump w;
@@ -143,6 +146,21 @@ w2vs_status_t block_step(const w2vs_config* cfg, const WeightLayout& wl, const S
   void* ctx = at<void>(d_ws, L.ctx);
   void* h = at<void>(d_ws, L.h);
   const bool pre_ln = cfg->layer_norm_first != 0;
+  if (cfg->stream_step_impl == 0 && stream_fused_applicable(cfg, B, ntok)) {
+    // bf16 models, at most 32 tokens per step: the whole step is one persistent cooperative kernel
+    StreamFusedArgs fa{};
+    fa.cfg = cfg; fa.wl = &wl; fa.W = W;
+    fa.B = B; fa.ntok = ntok; fa.n_main = n_main; fa.f0 = f0;
+    fa.feats = at<float>(d_state, L.fbuf); fa.feat_rows = L.fcap;
+    fa.R = X; fa.q = qkv; fa.ctx = ctx; fa.h = h;
+    fa.kv = at<void>(d_state, L.kv); fa.kv_layer_elems = (int64_t)(L.kv_layer_bytes / as); fa.kv_rows = L.kv_rows;
+    fa.partials = at<float>(d_ws, L.attn_part);
+    fa.max_splits = ((L.ntok_max + 63) / 64) * kAttnStepMaxSplits * 64 / 32;
+    fa.counters = at<unsigned>(d_state, L.sync);
+    fa.out = out_frames;
+    fa.bar = at<unsigned long long>(d_state, L.fused_bar);
+    return launch_stream_fused(fa, st);
+  }
   {
     EmbedArgs e{};
     e.feats = at<float>(d_state, L.fbuf) + (size_t)f0 * D; e.feat_rows = L.fcap;
@@ -232,8 +250,8 @@ w2vs_status_t w2vs_stream_init(const w2vs_config* cfg, int32_t B, int32_t max_fr
   hs->magic = kMagic;
   hs->B = B; hs->max_frames = max_frames; hs->max_new = max_new; hs->main_ctx = main_ctx; hs->rc = rc;
   // every data row is written before it is read; only the attention kernel's completion counters need zeroing
-  cudaError_t e = cudaMemsetAsync(at<uint8_t>(d_state, L.sync), 0, (size_t)B * cfg->heads * ((L.ntok_max + 63) / 64) * 4,
-                                  (cudaStream_t)stream);
+  // (L.sync and L.fused_bar are adjacent allocations: one memset covers both)
+  cudaError_t e = cudaMemsetAsync(at<uint8_t>(d_state, L.sync), 0, L.fused_bar + 64 - L.sync, (cudaStream_t)stream);
   if (e != cudaSuccess) { set_error("stream init memset: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
   return W2VS_OK;
 }

@@ -498,13 +498,17 @@ class EncoderStream:
 
     NONE, FINAL, PEEK = 0, 1, 2
 
-    def __init__(self, model, B, max_frames, max_new_samples, main_context=None, right_context=None):
+    def __init__(self, model, B, max_frames, max_new_samples, main_context=None, right_context=None, step_impl=0):
         device, dtype = model._device_dtype()
         self.model, self.B, self.device, self.dtype = model, B, device, dtype
         self.main = model.encoder.main_context if main_context is None else main_context
         self.rc = model.encoder.right_context if right_context is None else right_context
         self.max_frames, self.max_new = int(max_frames), int(max_new_samples)
-        self.ccfg, self.packed = model._ensure_packed(self.max_frames + 2)
+        ccfg, self.packed = model._ensure_packed(self.max_frames + 2)
+        # step_impl: 0 = one persistent cooperative kernel per decision step where it applies (bf16, <= 32 tokens per
+        # step), 1 = the kernel-per-operator chain (w2vs_config.stream_step_impl)
+        self.ccfg = cabi.Config.from_buffer_copy(ccfg)
+        self.ccfg.stream_step_impl = int(step_impl)
         lib = cabi.lib()
         hb, db, wb = C.c_size_t(), C.c_size_t(), C.c_size_t()
         cabi.check(lib.w2vs_stream_state_size(C.byref(self.ccfg), B, self.max_frames, self.max_new, self.main,
@@ -603,10 +607,10 @@ class BlockWiseWav2Vec2Model(Wav2VecSModel):
         return self._encode(source, padding_mask=padding_mask, layout=cabi.LAYOUT_BTD,
                             context=(self.encoder.main_context, self.encoder.right_context))
 
-    def open_stream(self, B=1, max_seconds=60.0, max_new_samples=4 * 5120 + 8000):
+    def open_stream(self, B=1, max_seconds=60.0, max_new_samples=4 * 5120 + 8000, step_impl=0):
         """Incremental encoder state for B lock-step live streams (see EncoderStream)."""
         max_frames = int(max_seconds * 16000) // 320 + 1
-        return EncoderStream(self, B, max_frames, max_new_samples)
+        return EncoderStream(self, B, max_frames, max_new_samples, step_impl=step_impl)
 
     def _forward_incremental(self, source, incremental_state, finished):
         st = incremental_state.get("w2vs_stream")
