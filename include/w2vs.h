@@ -72,9 +72,10 @@ typedef struct {
   int32_t conv_pos_groups;             /* 16 */
   int32_t seq_multiple;                /* required_seq_len_multiple (2) */
   int32_t sin_rows;                    /* rows of the sinusoidal table handed to pack (>= T+2) */
-  int32_t stream_step_impl;            /* incremental mode: 0 = auto (one persistent cooperative kernel per decision
-                                          step where it applies: bf16, <= 32 tokens per step), 1 = always the
-                                          kernel-per-operator chain (the fp32 mode's path; A/B and cross-checks) */
+  int32_t stream_step_impl;            /* incremental mode: 0 = default = 1 = the kernel-per-operator chain with
+                                          programmatic dependent launches; 2 = one persistent cooperative kernel per
+                                          decision step where it applies (bf16, <= 32 tokens per step; parity-tested,
+                                          measured slower than the chain so far: DESIGN.md section 5) */
   int32_t reserved[6];
 } w2vs_config;
 
@@ -224,6 +225,14 @@ int64_t w2vs_launch_count(int32_t reset);
  * waits for them and writes "kernel_name milliseconds launches" lines. */
 void w2vs_prof_enable(int32_t on, void* stream);
 int64_t w2vs_prof_collect(char* buf, int64_t capacity);
+
+/* Diagnostics of the persistent incremental-step kernel (synchronising; tools and tests only).
+ * w2vs_debug_fused_trace: globaltimer timestamps (ns) of the last launch on the current device,
+ *   [2 CTAs: first, last][64 layers][12 events]; n = number of 64-bit words to copy.
+ * w2vs_debug_fault_flags: bit 0 tcgen05 GEMM, bit 1 tcgen05 attention, bit 2 fused step kernel -- set when a
+ *   pipeline / barrier wait timed out inside a kernel (a bug; the kernels end instead of hanging). */
+w2vs_status_t w2vs_debug_fused_trace(uint64_t* out, int32_t n);
+w2vs_status_t w2vs_debug_fault_flags(int32_t* flags);
 
 #ifdef __cplusplus
 }

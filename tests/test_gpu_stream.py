@@ -157,9 +157,9 @@ def test_stream_takes_pcm16_chunks():
 @pytest.mark.parametrize("pre_ln", [True, False], ids=["preln", "postln"])
 @pytest.mark.parametrize("B,main,rc", [(1, 16, 8), (2, 8, 4), (1, 20, 10), (3, 6, 2)])
 def test_fused_step_kernel_equals_operator_chain(pre_ln, B, main, rc):
-    """bf16 decision steps run as one persistent cooperative kernel (k_stream_fused.cu) when a step has at most 32
-    tokens; the kernel-per-operator chain (stream_step_impl = 1) computes the same rows with the same roundings, up
-    to summation order.  Irregular chunks, so that steps of every size (full blocks, the short blocks of the final
+    """bf16 decision steps can run as one persistent cooperative kernel (k_stream_fused.cu, stream_step_impl = 2) when
+    a step has at most 32 tokens; the kernel-per-operator chain (the default) computes the same rows with the same
+    roundings, up to summation order.  Irregular chunks, so that steps of every size (full blocks, the short blocks of the final
     flush) and several blocks per call occur; both against each other and against the oracle's offline rows."""
     from oracle import synth
     cfg = cases.tiny(layer_norm_first=pre_ln, conv_bias=pre_ln, main_context=main, right_context=rc,
@@ -171,7 +171,7 @@ def test_fused_step_kernel_equals_operator_chain(pre_ln, B, main, rc):
     ref, _ = O.rain_forward(sd, cfg, wav, None, finished=True, is_infer=True)
     src = wav.cuda()
     ys = []
-    for impl in (0, 1):
+    for impl in (2, 0):
         rs = np.random.RandomState(3)
         st = m.open_stream(B=B, max_seconds=3.0, max_new_samples=9000, step_impl=impl)
         W.cabi.launch_count(reset=True)

@@ -88,6 +88,8 @@ PROTOTYPES = {
     "w2vs_launch_count": (C.c_int64, [C.c_int32]),
     "w2vs_prof_enable": (None, [C.c_int32, C.c_void_p]),
     "w2vs_prof_collect": (C.c_int64, [C.c_char_p, C.c_int64]),
+    "w2vs_debug_fused_trace": (C.c_int, [_P(C.c_uint64), C.c_int32]),
+    "w2vs_debug_fault_flags": (C.c_int, [_P(C.c_int32)]),
 }
 
 # kernel name -> class reported by bench.py

@@ -135,6 +135,7 @@ w2vs_status_t w2vs_weights_pack(const w2vs_config* cfg, const void* const* d_ref
     W2VS_TRY(copy_f32(l.ln1_b, D));
     W2VS_TRY(copy_act(l.w1, (int64_t)F * D));
     W2VS_TRY(copy_f32(l.b1, F));
+    if (l.w2s != kNone) W2VS_TRY(launch_pack_slabs(reinterpret_cast<const float*>(d_ref[t]), at<void>(d_packed, l.w2s), D, F, D, st));
     W2VS_TRY(copy_act(l.w2, (int64_t)D * F));
     W2VS_TRY(copy_f32(l.b2, D));
     W2VS_TRY(copy_f32(l.ln2_w, D));
@@ -427,6 +428,21 @@ w2vs_status_t w2vs_op_attention(int32_t impl, int32_t dtype, const void* d_qkv, 
   a.qkv = d_qkv; a.keypad = d_keypad; a.ctx = d_ctx; a.dtype = dtype;
   a.B = B; a.T2 = T_pad; a.main_ctx = main_ctx; a.rc = right_ctx; a.heads = heads; a.D = D;
   return launch_attention(impl, a, (cudaStream_t)stream);
+}
+
+w2vs_status_t w2vs_debug_fused_trace(uint64_t* out, int32_t n) {
+  W2VS_REQUIRE(out != nullptr && n >= 0, "out / n");
+  return debug_read_fused_trace(reinterpret_cast<unsigned long long*>(out), n);
+}
+
+w2vs_status_t w2vs_debug_fault_flags(int32_t* flags) {
+  W2VS_REQUIRE(flags != nullptr, "flags is NULL");
+  int a = 0, b = 0, c = 0;
+  W2VS_TRY(debug_read_tc2_fault(&a));
+  W2VS_TRY(debug_read_attn_tc_fault(&b));
+  W2VS_TRY(debug_read_fused_fault(&c));
+  *flags = (a ? 1 : 0) | (b ? 2 : 0) | (c ? 4 : 0);
+  return W2VS_OK;
 }
 
 }  // extern "C"

@@ -738,4 +738,12 @@ w2vs_status_t launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
   return W2VS_OK;
 }
 
+w2vs_status_t debug_read_attn_tc_fault(int* out) {
+  int v = 0;
+  cudaError_t e = cudaMemcpyFromSymbol(&v, g_attn_tc_fault, sizeof(int));
+  if (e != cudaSuccess) { set_error("read g_attn_tc_fault: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
+  *out = v;
+  return W2VS_OK;
+}
+
 }  // namespace w2vs

@@ -14,6 +14,18 @@ __global__ void pack_copy_kernel(const float* __restrict__ src, TOut* __restrict
     dst[i] = from_f32<TOut>(src[i]);
 }
 
+// Linear weight [N][K] fp32 -> bf16 slabs [N/8][K/KC][8][KC] (every 8-row x KC-wide slab contiguous: one bulk copy
+// per slab in the fused incremental step)
+__global__ void pack_slabs_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int N, int K, int KC) {
+  const int64_t n = (int64_t)N * K;
+  const int nch = K / KC;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K), row = (int)(i / K);
+    const int u = row >> 3, r = row & 7, j = k / KC, kk = k - j * KC;
+    dst[(((size_t)u * nch + j) * 8 + r) * KC + kk] = __float2bfloat16_rn(src[i]);
+  }
+}
+
 // Conv1d weight [C_out, C_in, k] -> K-major GEMM operand [C_out][j*C_in + ci]
 template <typename TOut>
 __global__ void pack_conv_kernel(const float* __restrict__ src, TOut* __restrict__ dst, int C_out, int C_in, int k) {
@@ -120,6 +132,12 @@ __global__ void posconv_pack_x_kernel(const float* __restrict__ feats, int feat_
 static int grid_for(int64_t n) {
   int64_t g = ceil_div64(n, 256);
   return (int)(g < 1 ? 1 : (g > 8192 ? 8192 : g));
+}
+
+w2vs_status_t launch_pack_slabs(const float* src, void* dst, int N, int K, int KC, cudaStream_t st) {
+  pack_slabs_kernel<<<grid_for((int64_t)N * K), 256, 0, st>>>(src, (bf16*)dst, N, K, KC);
+  W2VS_CHECK_LAUNCH("pack_slabs_kernel");
+  return W2VS_OK;
 }
 
 w2vs_status_t launch_pack_copy(const float* src, void* dst, int dst_dtype, int64_t n, cudaStream_t st) {

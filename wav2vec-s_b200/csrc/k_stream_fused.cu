@@ -35,6 +35,12 @@
 
 namespace w2vs {
 __device__ int g_fused_fault = 0;   // set when a barrier / pipeline wait timed out (diagnostics)
+// phase timestamps (globaltimer ns) of the last launch, written by thread 0 of the first and the last CTA:
+// [cta 0 | cta G-1][layer][event]; events: 0 layer start, 1 QKV done, 2 barrier, 3 attention done, 4 barrier,
+// 5 out_proj done, 6 barrier, 7 fc1 done, 8 barrier, 9 fc2 done, 10 barrier, 11 clock64 at layer start.  Read by
+// tools/stream_trace.py through w2vs_debug_fused_trace (one store per phase: free).
+__device__ unsigned long long g_fused_trace[2][64][12];
+__device__ unsigned long long g_fused_trace2[2][96];   // spare fine-grained slots (layer FS_TRACE_LAYER)
 }
 #define W2VS_TC_FAULT_FLAG (&::w2vs::g_fused_fault)
 #include "tc_common.cuh"
@@ -43,11 +49,12 @@ namespace w2vs {
 namespace {
 using namespace tc;
 
-constexpr int FS_CW = 8;                        // warps: all of them consume; thread 0 also drives the weight ring
+constexpr int FS_CW = 8;                        // warps: all of them consume; thread 0 also drives the copies
 constexpr int FS_THREADS = 32 * FS_CW;
 constexpr int FS_ROWS = 32;                     // token rows of a step (two m16 tiles)
 constexpr int FS_UMAX = 4;                      // 8-column units of one product a CTA may own
 constexpr int FS_MAX_STAGES = 12;
+constexpr int FS_SCHED = 32;                    // slabs of one layer a CTA may own
 constexpr int FS_KT = 64;                       // attention key tile
 constexpr int FS_ATT_GROUP_BYTES = 5 * 8192;    // Q + 2 K + 2 V tiles of 64 x 64 bf16
 constexpr int FS_MAX_SPLITS = 16;
@@ -73,6 +80,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// non-blocking probe (mbarrier.try_wait may suspend the thread for a system-dependent time when the phase is not
+// complete -- measured ~1-2 us here -- which is the last thing the producer cursor should do)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -95,13 +113,13 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
 
 struct FusedArgs {
   const uint8_t* W;                    // packed weights
-  unsigned long long wqkv, bqkv, wo, bo, ln1_w, ln1_b, w1, b1, w2, b2, ln2_w, ln2_b;   // layer 0 offsets (bytes)
+  unsigned long long wqkv, bqkv, wo, bo, ln1_w, ln1_b, w1, b1, w2s, b2, ln2_w, ln2_b;   // layer 0 offsets (bytes)
   unsigned long long layer_stride, enc_ln_w, enc_ln_b, sin_table;
   int layers, D, F, H, pre_ln;
   int B, ntok, n_main, f0;             // tokens per stream in this step, frames emitted, first frame index
   const float* feats; long long feat_rows;     // projected frames [B][feat_rows][D] fp32
   float* R;                            // residual stream [B * ntok][D] fp32
-  bf16* q; bf16* ctx; bf16* h;         // [B * ntok][D], [.][D], [.][F]
+  bf16* q; bf16* ctx; bf16* h;         // [B * ntok][D], [.][D], FFN hidden chunk-major [F / D][32][D]
   bf16* kv; long long kv_layer_elems, kv_rows;   // cache [layers][B][kv_rows][2D]
   float* partials; unsigned* counters; // attention split states [B*H][splits][32][66]; zeroed counters [B*H]
   bf16* out;                           // [n_main][B][D]
@@ -110,73 +128,58 @@ struct FusedArgs {
   float scale_log2;
 };
 
-struct Smem {
-  uint32_t ring, uni, stats, bars_full, bars_empty, flags;
-  int stage_bytes, pitch_w, pitch_a;
-};
+// Shared memory map: byte offsets from a 1024-aligned base.
+//   ring   weight slabs, n_stages x (8 rows x D bf16)
+//   abuf   the A operand of the running product: 32 rows x D bf16 (written by the LayerNorm or by a bulk copy)
+//   part   per-warp partial sums [8 warps][4 units][32 rows][8] fp32          (abuf + part: attention tiles)
+//   lnp    LayerNorm parameters of the two LN phases: 2 x [gamma D | beta D] fp32 (bulk copies, a layer ahead)
+//   sched  this CTA's slab list of one layer (byte offsets from the layer's weights), stats [32][2], barriers, flags
+struct Smem { uint32_t ring, abuf, part, lnp, sched, stats, bars, flags; int stage_bytes; };
+// barriers: full[12] @0, empty[12] @96, A operand @192, LayerNorm parameters [2] @200
 
-// One weight matrix of a phase: W [N][K] row-major bf16.
-struct Mat { const bf16* w; int N, K; };
-__device__ __forceinline__ Mat phase_mat(const FusedArgs& a, int layer, int p) {
-  const uint8_t* base = a.W + (size_t)layer * a.layer_stride;
-  Mat m;
-  if (p == 0) { m.w = reinterpret_cast<const bf16*>(base + a.wqkv); m.N = 3 * a.D; m.K = a.D; }
-  else if (p == 1) { m.w = reinterpret_cast<const bf16*>(base + a.wo); m.N = a.D; m.K = a.D; }
-  else if (p == 2) { m.w = reinterpret_cast<const bf16*>(base + a.w1); m.N = a.F; m.K = a.D; }
-  else { m.w = reinterpret_cast<const bf16*>(base + a.w2); m.N = a.D; m.K = a.F; }
-  return m;
-}
 __device__ __forceinline__ const float* lw(const FusedArgs& a, int layer, unsigned long long off) {
   return reinterpret_cast<const float*>(a.W + (size_t)layer * a.layer_stride + off);
 }
 
+// Consumer and producer cursors of the weight ring.  The producer side lives in thread 0: slabs are requested in
+// consumption order (layer, product, unit, K chunk) from the per-CTA list `sched`, never blocking.
+// One out-of-line copy of the mbarrier wait: its time-out logic is ~40 instructions per inlined site, and the code
+// size of this kernel is what bounds its speed (see the layer loop).
+__device__ __noinline__ bool wait_bar(uint32_t bar, uint32_t parity) { return mbar_wait(bar, parity); }
 struct Ring { int stage; uint32_t phase; };
+struct Prod { int e, l, n_entries, stage; uint32_t phase; };
 
-// Producer cursor over this CTA's weight slabs in consumption order: layer, product, unit, K chunk.
-struct Prod { int l, p, u, j, stage; uint32_t phase; int done; };
-__device__ __forceinline__ void prod_skip_empty(const FusedArgs& a, Prod& pr, int G) {
-  // move to the next (layer, product) in which this CTA owns a unit
-  while (!pr.done) {
-    const Mat m = phase_mat(a, pr.l, pr.p);
-    if (pr.u < (m.N >> 3)) return;
-    pr.u = blockIdx.x; pr.j = 0;
-    if (++pr.p == 4) { pr.p = 0; if (++pr.l == a.layers) pr.done = 1; }
-  }
-  (void)G;
-}
-// Refill up to `budget` free stages; never blocks.  Thread 0 only.
-__device__ __noinline__ void pump(const FusedArgs& a, const Smem& sm, Prod& pr, int budget) {
-  const int KC = a.D, G = gridDim.x;
-  while (!pr.done && budget-- > 0) {
-    if (!mbar_try_wait(sm.bars_empty + 8 * pr.stage, pr.phase ^ 1)) return;    // not yet released by all 8 warps
-    const Mat m = phase_mat(a, pr.l, pr.p);
-    mbar_expect_tx(sm.bars_full + 8 * pr.stage, 8u * KC * 2u);
-    const bf16* src = m.w + (size_t)pr.u * 8 * m.K + (size_t)pr.j * KC;
-    const uint32_t dst = sm.ring + (uint32_t)pr.stage * sm.stage_bytes;
-#pragma unroll
-    for (int r = 0; r < 8; ++r)
-      bulk_g2s(dst + r * sm.pitch_w, src + (size_t)r * m.K, (uint32_t)KC * 2u, sm.bars_full + 8 * pr.stage);
+__device__ __forceinline__ void pump(const FusedArgs& a, const Smem& sm, uint32_t sb, const uint8_t* smem_gen, Prod& pr,
+                                     int budget) {
+  const unsigned long long* sched = reinterpret_cast<const unsigned long long*>(smem_gen + sm.sched);
+  while (budget-- > 0 && pr.l < a.layers) {
+    if (!mbar_test(sb + sm.bars + 96 + 8 * pr.stage, pr.phase ^ 1)) return;    // not yet released by all 8 warps
+    const uint32_t full = sb + sm.bars + 8 * pr.stage;
+    mbar_expect_tx(full, (uint32_t)sm.stage_bytes);
+    // every slab is 8 rows x D bf16, contiguous in global memory (8 whole rows of W, or the slab-ordered fc2 copy):
+    // ONE bulk copy -- issuing a copy costs the issuing thread ~80 ns, whatever its size
+    bulk_g2s(sb + sm.ring + (uint32_t)pr.stage * sm.stage_bytes, a.W + (size_t)pr.l * a.layer_stride + sched[pr.e],
+             (uint32_t)sm.stage_bytes, full);
     if (++pr.stage == a.n_stages) { pr.stage = 0; pr.phase ^= 1; }
-    if (++pr.j == m.K / KC) { pr.j = 0; pr.u += G; }
-    prod_skip_empty(a, pr, G);
+    if (++pr.e == pr.n_entries) { pr.e = 0; ++pr.l; }
   }
 }
 
-// Grid-wide barrier for the 256 consumer threads of every CTA.  Arrival counter in global memory, monotonically
-// increasing inside a launch (target = barriers so far x CTAs); the last CTA to leave the kernel resets it.
-__device__ __noinline__ bool grid_barrier(const FusedArgs& a, const Smem& sm, Prod& pr, unsigned long long target,
-                                          volatile int* s_abort) {
-  unsigned long long* bar = a.bar;
+// Grid-wide barrier for the 256 threads of every CTA.  Arrival counter in global memory, monotonically increasing
+// inside a launch (target = barriers so far x CTAs); the last CTA to leave the kernel resets it.  Thread 0 uses the
+// time between its arrival and the release to refill the weight ring.
+__device__ __noinline__ bool grid_barrier(const FusedArgs& a, const Smem& sm, uint32_t sb, const uint8_t* smem_gen,
+                                             Prod& pr, unsigned long long target, volatile int* s_abort) {
   named_bar(1, 32 * FS_CW);
   if (threadIdx.x == 0) {
     __threadfence();
-    atomicAdd(bar, 1ull);
-    pump(a, sm, pr, FS_MAX_STAGES);      // every stage consumed in the phase that just ended is free now
+    atomicAdd(a.bar, 1ull);
+    pump(a, sm, sb, smem_gen, pr, FS_MAX_STAGES);      // every stage consumed in the phase that just ended is free now
     unsigned long long v;
     unsigned spins = 0;
     unsigned long long t0 = 0;
     for (;;) {
-      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.bar) : "memory");
       if (v >= target) break;
       if ((++spins & 0x3ff) == 0) {
         const unsigned long long now = global_ns();
@@ -184,22 +187,20 @@ __device__ __noinline__ bool grid_barrier(const FusedArgs& a, const Smem& sm, Pr
         else if (now - t0 > FS_TIMEOUT_NS) { atomicExch(&g_fused_fault, 1); *s_abort = 1; break; }
       }
     }
-    __threadfence();
   }
   named_bar(1, 32 * FS_CW);
   return *s_abort == 0;
 }
 
-// LayerNorm of one fp32 row held as float4 v[NV] per lane (columns 4 lane + 128 j): returns mean / rstd.
-template <int NVMAX>
-__device__ __forceinline__ void row_stats(const float4 (&v)[NVMAX], int nv, int D, float& mean, float& rstd) {
+// mean / rstd of one fp32 row held as float4 v[8] per lane
+__device__ __forceinline__ void row_stats(const float4 (&v)[8], int nv, int D, float& mean, float& rstd) {
   float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < NVMAX; ++j) if (j < nv) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  for (int j = 0; j < 8; ++j) if (j < nv) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
   mean = warp_sum(s) * (1.0f / D);
   float q = 0.f;
 #pragma unroll
-  for (int j = 0; j < NVMAX; ++j)
+  for (int j = 0; j < 8; ++j)
     if (j < nv) {
       const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
       q = fmaf(a, a, q); q = fmaf(b, b, q); q = fmaf(c, c, q); q = fmaf(d, d, q);
@@ -207,141 +208,168 @@ __device__ __forceinline__ void row_stats(const float4 (&v)[NVMAX], int nv, int 
   rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
 }
 
-// ---- LN phase prologue: operand rows A = bf16(LN(R)) into shared memory, row statistics into `stats` ----
-__device__ __noinline__ void ln_rows_to_smem(const FusedArgs& a, const Smem& sm, uint8_t* smem_gen, int warp, int lane,
-                                                const float* gamma, const float* beta) {
+// ---- LN phase prologue: operand rows A = bf16(LN(R)) into abuf, row statistics into `stats` ----
+// Warp w normalises four rows; the next row's loads are in flight while a row is normalised.  gamma / beta come from
+// shared memory (`lnp`, bulk-copied a layer ahead): as global loads they were sixteen dependent L2 round trips per
+// row.  Which rows a warp takes is rotated by the CTA index, so that the CTAs of the grid, which all read the same
+// 96 KB, do not ask the same L2 lines at the same instant.
+__device__ __forceinline__ void ln_rows_to_smem(const FusedArgs& a, const Smem& sm, uint8_t* smem_gen, int warp, int lane,
+                                                const float* lnp) {
   const int Mt = a.B * a.ntok, D = a.D, nv = D >> 7;
-  float* stats = reinterpret_cast<float*>(smem_gen + (sm.stats - sm.ring));
-  for (int row = warp; row < FS_ROWS; row += FS_CW) {
-    uint8_t* dst = smem_gen + (sm.uni - sm.ring) + (size_t)row * sm.pitch_a;
+  float* stats = reinterpret_cast<float*>(smem_gen + sm.stats);
+  constexpr int RPW = FS_ROWS / FS_CW;
+  const int cta = blockIdx.x;
+  const int wrot = (warp + cta) & (FS_CW - 1), irot = (cta >> 3) & (RPW - 1);
+  float4 vn[8];
+  {
+    const int row = wrot + FS_CW * irot;
     if (row < Mt) {
-      float4 v[8];
-      const float* xr = a.R + (size_t)row * D + 4 * lane;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) if (j < nv) v[j] = __ldcg(reinterpret_cast<const float4*>(xr + 128 * j));
+      for (int j = 0; j < 8; ++j) if (j < nv) vn[j] = __ldcg(reinterpret_cast<const float4*>(a.R + (size_t)row * D + 4 * lane + 128 * j));
+    }
+  }
+#pragma unroll 1
+  for (int it = 0; it < RPW; ++it) {
+    const int row = wrot + FS_CW * ((it + irot) & (RPW - 1));
+    float4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = vn[j];
+    if (it + 1 < RPW) {
+      const int rown = wrot + FS_CW * ((it + 1 + irot) & (RPW - 1));
+      if (rown < Mt) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j < nv) vn[j] = __ldcg(reinterpret_cast<const float4*>(a.R + (size_t)rown * D + 4 * lane + 128 * j));
+      }
+    }
+    uint8_t* dst = smem_gen + sm.abuf + (size_t)row * (2 * D);
+    if (row < Mt) {
       float mean, rstd;
-      row_stats<8>(v, nv, D, mean, rstd);
+      row_stats(v, nv, D, mean, rstd);
       if (lane == 0) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (j < nv) {
-          const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * lane + 128 * j);
-          const float4 bt = *reinterpret_cast<const float4*>(beta + 4 * lane + 128 * j);
+          const float4 gm = *reinterpret_cast<const float4*>(lnp + 4 * lane + 128 * j);
+          const float4 bt = *reinterpret_cast<const float4*>(lnp + D + 4 * lane + 128 * j);
           uint2 u;
-          u.x = pack_bf16x2((v[j].x - mean) * rstd * g.x + bt.x, (v[j].y - mean) * rstd * g.y + bt.y);
-          u.y = pack_bf16x2((v[j].z - mean) * rstd * g.z + bt.z, (v[j].w - mean) * rstd * g.w + bt.w);
+          u.x = pack_bf16x2((v[j].x - mean) * rstd * gm.x + bt.x, (v[j].y - mean) * rstd * gm.y + bt.y);
+          u.y = pack_bf16x2((v[j].z - mean) * rstd * gm.z + bt.z, (v[j].w - mean) * rstd * gm.w + bt.w);
           *reinterpret_cast<uint2*>(dst + (4 * lane + 128 * j) * 2) = u;
         }
     } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) if (j < nv) *reinterpret_cast<uint2*>(dst + (4 * lane + 128 * j) * 2) = make_uint2(0u, 0u);
+      for (int j = 0; j < nv; ++j) *reinterpret_cast<uint2*>(dst + (4 * lane + 128 * j) * 2) = make_uint2(0u, 0u);
     }
   }
 }
 
 enum { EPI_QKV = 0, EPI_RESID = 1, EPI_GELU = 2 };
 
-// One matrix product of a phase for this CTA's units.  A operand: shared-memory rows (a_glob == nullptr, LN phases)
-// or a global bf16 matrix [rows][lda] read through L2.
+// One matrix product of a phase for this CTA's units.  The A operand sits in abuf (32 rows x D bf16): written by the
+// LayerNorm (a_glob == nullptr), or bulk-copied from global memory by thread 0 -- chunk 0 was requested by the caller
+// right after the grid barrier, chunk j + 1 of the long-K product (fc2; the FFN hidden is stored chunk-major,
+// [K / D][32][D], so that every chunk is one dense block) as soon as all warps hold chunk j in registers.  One
+// instance serves all four products (rolled loops over units and K chunks: code size bounds this kernel).
 template <int MT>
-__device__ __noinline__ bool gemm_phase(const FusedArgs& a, const Smem& sm, uint8_t* smem_gen, Ring& rs, Prod& pr, int layer,
-                                           int N, int K, const bf16* a_glob, int lda, int epi, const float* bias,
-                                           const float* res_gamma, const float* res_beta, int warp, int lane) {
+__device__ __forceinline__ bool gemm_phase(const FusedArgs& a, const Smem& sm, uint32_t sb, uint8_t* smem_gen, Ring& rs,
+                                           uint32_t& aphase, int layer, int N, int K, const bf16* a_glob, int epi,
+                                           const float* bias, const float* res_lnp, int warp, int lane) {
   const int G = gridDim.x, cta = blockIdx.x;
   const int D = a.D, KC = D, Mt = a.B * a.ntok;
   const int kw = KC / FS_CW, nsteps = kw >> 4, nch = K / KC;
   const int g = lane >> 2, q = lane & 3;
   const int units_total = N >> 3;
   const int n_units = units_total > cta ? (units_total - 1 - cta) / G + 1 : 0;
-  float* part = reinterpret_cast<float*>(smem_gen + (sm.uni - sm.ring) + (size_t)FS_ROWS * sm.pitch_a);
-  const float* stats = reinterpret_cast<const float*>(smem_gen + (sm.stats - sm.ring));
+  float* part = reinterpret_cast<float*>(smem_gen + sm.part);
+  const float* stats = reinterpret_cast<const float*>(smem_gen + sm.stats);
+  const uint32_t abar = sb + sm.bars + 192;
 
-  float acc[FS_UMAX][MT][4];
-#pragma unroll
-  for (int i = 0; i < FS_UMAX; ++i)
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[i][mt][e] = 0.f;
-
-  uint2 af[MT][2][8];
-  auto load_a = [&](int j) {
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        const int row = mt * 16 + g + 8 * hf;
-        if (a_glob == nullptr) {
-          const uint32_t base = sm.uni + (uint32_t)row * sm.pitch_a + (uint32_t)(warp * kw + 4 * q) * 2;
-#pragma unroll
-          for (int s = 0; s < 8; ++s) if (s < nsteps) af[mt][hf][s] = lds64(base + s * 32);
-        } else {
-          const bf16* p = a_glob + (size_t)min(row, Mt - 1) * lda + (size_t)j * KC + warp * kw + 4 * q;
-#pragma unroll
-          for (int s = 0; s < 8; ++s) if (s < nsteps) af[mt][hf][s] = __ldcg(reinterpret_cast<const uint2*>(p + 16 * s));
-        }
-      }
-  };
-  if (n_units > 0 && nch == 1) load_a(0);
-
-  bool ok = true;
-#pragma unroll
-  for (int i = 0; i < FS_UMAX; ++i) {
-    if (i < n_units) {
-      for (int j = 0; j < nch; ++j) {
-        if (nch > 1) load_a(j);
-        ok = mbar_wait(sm.bars_full + 8 * rs.stage, rs.phase) && ok;
-        const uint32_t wrow = sm.ring + (uint32_t)rs.stage * sm.stage_bytes + (uint32_t)g * sm.pitch_w +
-                              (uint32_t)(warp * kw + 4 * q) * 2;
-        uint2 bw[8];
-#pragma unroll
-        for (int s = 0; s < 8; ++s) if (s < nsteps) bw[s] = lds64(wrow + s * 32);
-#pragma unroll
-        for (int s = 0; s < 8; ++s)
-          if (s < nsteps) {
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-              mma_16816(acc[i][mt], af[mt][0][s].x, af[mt][1][s].x, af[mt][0][s].y, af[mt][1][s].y, bw[s].x, bw[s].y);
-          }
-        // the MMAs have consumed the registers, so every lane's loads from the stage have completed: hand the
-        // stage back to the producer
-        __syncwarp();
-        if (lane == 0) mbar_arrive(sm.bars_empty + 8 * rs.stage);
-        if (++rs.stage == a.n_stages) { rs.stage = 0; rs.phase ^= 1; }
-        if (threadIdx.x == 0) pump(a, sm, pr, 2);
-      }
+  // the epilogue's residual and bias values do not depend on the product: request them first
+  const int tid = threadIdx.x;
+  const bool epi_thread = tid < n_units * Mt;
+  const int ei = epi_thread ? tid / Mt : 0, er = epi_thread ? tid - ei * Mt : 0;
+  const int en0 = (cta + ei * G) * 8;
+  float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0, bb0 = o0, bb1 = o0;
+  if (epi_thread) {
+    bb0 = *reinterpret_cast<const float4*>(bias + en0);
+    bb1 = *reinterpret_cast<const float4*>(bias + en0 + 4);
+    if (epi == EPI_RESID) {
+      const float* xr = a.R + (size_t)er * D + en0;
+      o0 = __ldcg(reinterpret_cast<const float4*>(xr));
+      o1 = __ldcg(reinterpret_cast<const float4*>(xr + 4));
     }
   }
-  // ---- partial sums of the 8 K slices -> shared memory
+
+  uint2 af[MT][2][8];       // A fragments of one K chunk: [m tile][row half][k16 step] x 8 bytes
+  bool ok = true, need_a = true;
+#pragma unroll 1
+  for (int i = 0; i < n_units; ++i) {
+    float acc[MT][4];
 #pragma unroll
-  for (int i = 0; i < FS_UMAX; ++i)
-    if (i < n_units) {
+    for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < nch; ++j) {
+      if (need_a) {
+        need_a = nch > 1;      // K == D: the same fragments serve every unit
+        if (a_glob != nullptr) { ok = wait_bar(abar, aphase) && ok; aphase ^= 1; }
+        const uint32_t base = sb + sm.abuf + (uint32_t)g * (2 * D) + (uint32_t)(warp * kw + 4 * q) * 2;
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        float* p0 = part + (((size_t)warp * FS_UMAX + i) * FS_ROWS + mt * 16 + g) * 8 + 2 * q;
-        *reinterpret_cast<float2*>(p0) = make_float2(acc[i][mt][0], acc[i][mt][1]);
-        *reinterpret_cast<float2*>(p0 + 64) = make_float2(acc[i][mt][2], acc[i][mt][3]);
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+              if (s < nsteps) af[mt][hf][s] = lds64(base + (uint32_t)(mt * 16 + 8 * hf) * (2 * D) + s * 32);
+        if (nch > 1) {
+          // every warp holds chunk j in registers: thread 0 may overwrite abuf with chunk j + 1
+          named_bar(1, 32 * FS_CW);
+          if (tid == 0 && j + 1 < nch) {
+            mbar_expect_tx(abar, (uint32_t)Mt * KC * 2);
+            bulk_g2s(sb + sm.abuf, a_glob + (size_t)(j + 1) * FS_ROWS * KC, (uint32_t)Mt * KC * 2, abar);
+          }
+        }
       }
+      ok = wait_bar(sb + sm.bars + 8 * rs.stage, rs.phase) && ok;
+      const uint32_t wrow = sb + sm.ring + (uint32_t)rs.stage * sm.stage_bytes + (uint32_t)g * (2 * D) +
+                            (uint32_t)(warp * kw + 4 * q) * 2;
+#pragma unroll
+      for (int s = 0; s < 8; ++s)
+        if (s < nsteps) {
+          const uint2 bw = lds64(wrow + s * 32);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            mma_16816(acc[mt], af[mt][0][s].x, af[mt][1][s].x, af[mt][0][s].y, af[mt][1][s].y, bw.x, bw.y);
+        }
+      // the MMAs have consumed the registers, so every lane's loads from the stage have completed: hand the
+      // stage back to the producer
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sb + sm.bars + 96 + 8 * rs.stage);
+      if (++rs.stage == a.n_stages) { rs.stage = 0; rs.phase ^= 1; }
     }
+    // partial sums of this warp's K slice -> shared memory
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      float* p0 = part + (((size_t)warp * FS_UMAX + i) * FS_ROWS + mt * 16 + g) * 8 + 2 * q;
+      *reinterpret_cast<float2*>(p0) = make_float2(acc[mt][0], acc[mt][1]);
+      *reinterpret_cast<float2*>(p0 + 64) = make_float2(acc[mt][2], acc[mt][3]);
+    }
+  }
+  if (n_units == 0 && a_glob != nullptr) {
+    // no unit in this product: still consume the A operand barrier phases (one per chunk)
+    for (int j = 0; j < nch; ++j) { ok = wait_bar(abar, aphase) && ok; aphase ^= 1;
+      if (nch > 1) { named_bar(1, 32 * FS_CW);
+        if (tid == 0 && j + 1 < nch) { mbar_expect_tx(abar, (uint32_t)Mt * KC * 2); bulk_g2s(sb + sm.abuf, a_glob + (size_t)(j + 1) * FS_ROWS * KC, (uint32_t)Mt * KC * 2, abar); } } }
+  }
   named_bar(1, 32 * FS_CW);
   // ---- fixed-order reduction + epilogue: one thread per (unit, row), 8 consecutive columns
-  const int tid = threadIdx.x;
-  if (tid < n_units * Mt) {
-    const int i = tid / Mt, r = tid - i * Mt;
-    const int n0 = (cta + i * G) * 8;
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+  if (epi_thread) {
+    const int i = ei, r = er, n0 = en0;
+    float v[8] = {bb0.x, bb0.y, bb0.z, bb0.w, bb1.x, bb1.y, bb1.z, bb1.w};
 #pragma unroll
     for (int w = 0; w < FS_CW; ++w) {
       const float* p = part + (((size_t)w * FS_UMAX + i) * FS_ROWS + r) * 8;
       const float4 x0 = *reinterpret_cast<const float4*>(p), x1 = *reinterpret_cast<const float4*>(p + 4);
       v[0] += x0.x; v[1] += x0.y; v[2] += x0.z; v[3] += x0.w; v[4] += x1.x; v[5] += x1.y; v[6] += x1.z; v[7] += x1.w;
     }
-    float bb[8];
-    load8(bias + n0, bb);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] += bb[e];
     if (epi == EPI_QKV) {
       bf16* dst;
       if (n0 < D) dst = a.q + (size_t)r * D + n0;
@@ -353,22 +381,21 @@ __device__ __noinline__ bool gemm_phase(const FusedArgs& a, const Smem& sm, uint
     } else if (epi == EPI_GELU) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = gelu_tanh(v[e]);
-      store8(a.h + (size_t)r * a.F + n0, v);
+      const int jc = n0 / KC;
+      store8(a.h + ((size_t)jc * FS_ROWS + r) * KC + (n0 - jc * KC), v);
     } else {
-      float* xr = a.R + (size_t)r * D + n0;
-      const float4 o0 = __ldcg(reinterpret_cast<const float4*>(xr)), o1 = __ldcg(reinterpret_cast<const float4*>(xr + 4));
       float o[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
-      if (res_gamma != nullptr) {     // post-LN: the residual term is the pending LayerNorm of the stored sum
+      if (res_lnp != nullptr) {     // post-LN: the residual term is the pending LayerNorm of the stored sum
         const float mean = stats[2 * r], rstd = stats[2 * r + 1];
         float gg[8], bt[8];
-        load8(res_gamma + n0, gg);
-        load8(res_beta + n0, bt);
+        load8(res_lnp + n0, gg);
+        load8(res_lnp + D + n0, bt);
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = (o[e] - mean) * rstd * gg[e] + bt[e];
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] += o[e];
-      store8(xr, v);
+      store8(a.R + (size_t)r * D + n0, v);
     }
   }
   return ok;
@@ -387,8 +414,8 @@ __device__ __forceinline__ void load_tile(bf16* tile, const bf16* src, long long
   }
 }
 
-__device__ __noinline__ void attention_phase(const FusedArgs& a, const Smem& sm, uint8_t* smem_gen, Prod& pr, int layer,
-                                            int warp, int lane) {
+__device__ __forceinline__ void attention_phase(const FusedArgs& a, const Smem& sm, uint8_t* smem_gen, int layer,
+                                                int warp, int lane) {
   const int G = gridDim.x, cta = blockIdx.x;
   const int gi = warp >> 2, wi = warp & 3, gtid = threadIdx.x & 127;
   const int mt = wi & 1, par = wi >> 1;
@@ -396,16 +423,14 @@ __device__ __noinline__ void attention_phase(const FusedArgs& a, const Smem& sm,
   const int D = a.D, H = a.H, S = a.n_splits, ntok = a.ntok;
   const int n_keys = a.f0 + ntok, n_kt = (n_keys + FS_KT - 1) / FS_KT, per = (n_kt + S - 1) / S;
   const long long krs = 2ll * D;
-  bf16* Qs = reinterpret_cast<bf16*>(smem_gen + (sm.uni - sm.ring) + (size_t)gi * FS_ATT_GROUP_BYTES);
+  bf16* Qs = reinterpret_cast<bf16*>(smem_gen + sm.abuf + (size_t)gi * FS_ATT_GROUP_BYTES);
   bf16* Ks = Qs + 4096;          // [2][64 x 64]
   bf16* Vs = Ks + 2 * 4096;      // [2][64 x 64]
-  int* s_last = reinterpret_cast<int*>(smem_gen + (sm.flags - sm.ring)) + 4 + gi;
+  int* s_last = reinterpret_cast<int*>(smem_gen + sm.flags) + 4 + gi;
   const bf16* kv_l = a.kv + (size_t)layer * a.kv_layer_elems;
   const float sl2 = a.scale_log2;
   const bool active = mt * 16 < ntok;      // this warp's 16 query rows exist
-
   for (int item = cta * 2 + gi; item < a.B * H * S; item += 2 * G) {
-    if (threadIdx.x == 0) pump(a, sm, pr, 2);
     const int sp = item % S, bh = item / S, h = bh % H, b = bh / H;
     const int t_begin = min(sp * per, n_kt), t_end = min(t_begin + per, n_kt);
     const bf16* qbase = a.q + (size_t)b * ntok * D + (size_t)h * 64;
@@ -438,67 +463,62 @@ __device__ __noinline__ void attention_phase(const FusedArgs& a, const Smem& sm,
         const bf16* Kt = Ks + par * 4096;
         const bf16* Vt = Vs + par * 4096;
         const int cnt = min(FS_KT, n_keys - (t0 + par) * FS_KT);
-        float s[8][4];
+        const int mi = lane >> 3;
+        // 16 keys at a time in a rolled loop (S = Q K^T for 16 keys, online softmax, O += P V): a fraction of the
+        // code of the fully unrolled 64-key step, which this kernel cannot afford
+#pragma unroll 1
+        for (int sub = 0; sub * 16 < cnt; ++sub) {
+          float s[2][4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+          for (int jj = 0; jj < 2; ++jj) { s[jj][0] = s[jj][1] = s[jj][2] = s[jj][3] = 0.f; }
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-          for (int jp = 0; jp < 4; ++jp) {
+          for (int kk = 0; kk < 4; ++kk) {
             uint32_t kf[4];
-            const int mi = lane >> 3;
-            const int row = jp * 16 + (lane & 7) + (mi >> 1) * 8;
-            ldsm_x4(smem_u32(Kt + sw(row, kk * 2 + (mi & 1))), kf);
-            mma_16816(s[2 * jp], qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], kf[0], kf[1]);
-            mma_16816(s[2 * jp + 1], qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], kf[2], kf[3]);
+            ldsm_x4(smem_u32(Kt + sw(sub * 16 + (lane & 7) + (mi >> 1) * 8, kk * 2 + (mi & 1))), kf);
+            mma_16816(s[0], qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], kf[0], kf[1]);
+            mma_16816(s[1], qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], kf[2], kf[3]);
           }
-        }
-        float mx0 = -INFINITY, mx1 = -INFINITY;
+          float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+          for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const bool vis = j * 8 + 2 * t4 + e < cnt;      // keys past the end of the cache (tile tail)
-            s[j][e] = vis ? s[j][e] : -INFINITY;
-            s[j][2 + e] = vis ? s[j][2 + e] : -INFINITY;
-            mx0 = fmaxf(mx0, s[j][e]);
-            mx1 = fmaxf(mx1, s[j][2 + e]);
+            for (int e = 0; e < 2; ++e) {
+              const bool vis = sub * 16 + jj * 8 + 2 * t4 + e < cnt;      // keys past the end of the cache (tile tail)
+              s[jj][e] = vis ? s[jj][e] : -INFINITY;
+              s[jj][2 + e] = vis ? s[jj][2 + e] : -INFINITY;
+              mx0 = fmaxf(mx0, s[jj][e]);
+              mx1 = fmaxf(mx1, s[jj][2 + e]);
+            }
+          mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+          mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+          mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+          mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+          const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+          const float ms0 = mn0 == -INFINITY ? 0.f : mn0 * sl2;
+          const float ms1 = mn1 == -INFINITY ? 0.f : mn1 * sl2;
+          const float a0 = exp2f(m0 * sl2 - ms0), a1 = exp2f(m1 * sl2 - ms1);
+          m0 = mn0; m1 = mn1;
+          uint32_t pf[4];
+          float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const float p0 = exp2f(fmaf(s[jj][0], sl2, -ms0)), p1 = exp2f(fmaf(s[jj][1], sl2, -ms0));
+            const float p2 = exp2f(fmaf(s[jj][2], sl2, -ms1)), p3 = exp2f(fmaf(s[jj][3], sl2, -ms1));
+            sum0 += p0 + p1;
+            sum1 += p2 + p3;
+            pf[2 * jj] = pack_bf16x2(p0, p1);          // row g,     keys 8 jj + 2 t4 ..
+            pf[2 * jj + 1] = pack_bf16x2(p2, p3);      // row g + 8
           }
-        }
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-        const float ms0 = mn0 == -INFINITY ? 0.f : mn0 * sl2;
-        const float ms1 = mn1 == -INFINITY ? 0.f : mn1 * sl2;
-        const float a0 = exp2f(m0 * sl2 - ms0), a1 = exp2f(m1 * sl2 - ms1);
-        m0 = mn0; m1 = mn1;
-        float sum0 = 0.f, sum1 = 0.f;
-        uint32_t pf[8][2];
+          l0 = l0 * a0 + sum0;
+          l1 = l1 * a1 + sum1;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float p0 = exp2f(fmaf(s[j][0], sl2, -ms0)), p1 = exp2f(fmaf(s[j][1], sl2, -ms0));
-          const float p2 = exp2f(fmaf(s[j][2], sl2, -ms1)), p3 = exp2f(fmaf(s[j][3], sl2, -ms1));
-          sum0 += p0 + p1;
-          sum1 += p2 + p3;
-          pf[j][0] = pack_bf16x2(p0, p1);
-          pf[j][1] = pack_bf16x2(p2, p3);
-        }
-        l0 = l0 * a0 + sum0;
-        l1 = l1 * a1 + sum1;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { o[j][0] *= a0; o[j][1] *= a0; o[j][2] *= a1; o[j][3] *= a1; }
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
+          for (int j = 0; j < 8; ++j) { o[j][0] *= a0; o[j][1] *= a0; o[j][2] *= a1; o[j][3] *= a1; }
 #pragma unroll
           for (int jp = 0; jp < 4; ++jp) {
             uint32_t vf[4];
-            const int mi = lane >> 3;
-            const int row = kk * 16 + (lane & 7) + (mi & 1) * 8;
-            ldsm_x4_trans(smem_u32(Vt + sw(row, jp * 2 + (mi >> 1))), vf);
-            mma_16816(o[2 * jp], pf[2 * kk][0], pf[2 * kk][1], pf[2 * kk + 1][0], pf[2 * kk + 1][1], vf[0], vf[1]);
-            mma_16816(o[2 * jp + 1], pf[2 * kk][0], pf[2 * kk][1], pf[2 * kk + 1][0], pf[2 * kk + 1][1], vf[2], vf[3]);
+            ldsm_x4_trans(smem_u32(Vt + sw(sub * 16 + (lane & 7) + (mi & 1) * 8, jp * 2 + (mi >> 1))), vf);
+            mma_16816(o[2 * jp], pf[0], pf[1], pf[2], pf[3], vf[0], vf[1]);
+            mma_16816(o[2 * jp + 1], pf[0], pf[1], pf[2], pf[3], vf[2], vf[3]);
           }
         }
       }
@@ -568,23 +588,45 @@ __device__ __noinline__ void attention_phase(const FusedArgs& a, const Smem& sm,
       if (*s_last) {
         __threadfence();
         const float* P0 = a.partials + (size_t)bh * S * (size_t)(FS_ROWS * 66);
+        // every thread owns (row, 8-column chunk) pairs; the splits are folded in batches of 8 whose loads are all
+        // issued before the first one is used (a serial loop over 16 splits was 30 dependent L2 round trips)
         for (int idx = gtid; idx < ntok * 8; idx += 128) {
           const int row = idx >> 3, chunk = idx & 7;
-          float mx = -INFINITY;
-          for (int s2 = 0; s2 < S; ++s2) mx = fmaxf(mx, __ldcg(P0 + (size_t)s2 * FS_ROWS * 66 + row * 66 + 64));
-          float accv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, lsum = 0.f;
-          for (int s2 = 0; s2 < S; ++s2) {
-            const float* pr = P0 + (size_t)s2 * FS_ROWS * 66 + row * 66;
-            const float2 ml = __ldcg(reinterpret_cast<const float2*>(pr + 64));
-            if (ml.x == -INFINITY) continue;
-            const float w = exp2f((ml.x - mx) * sl2);
-            lsum = fmaf(ml.y, w, lsum);
+          float mrun = -INFINITY, lsum = 0.f;
+          float accv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+          for (int s0 = 0; s0 < S; s0 += 8) {
+            float2 ml[8];
+            float4 ov[8][2];
 #pragma unroll
-            for (int e = 0; e < 8; e += 2) {
-              const float2 ov = __ldcg(reinterpret_cast<const float2*>(pr + chunk * 8 + e));
-              accv[e] = fmaf(ov.x, w, accv[e]);
-              accv[e + 1] = fmaf(ov.y, w, accv[e + 1]);
-            }
+            for (int k = 0; k < 8; ++k)
+              if (s0 + k < S) {
+                const float* pr2 = P0 + (size_t)(s0 + k) * FS_ROWS * 66 + row * 66;       // 8-byte aligned rows
+                ml[k] = __ldcg(reinterpret_cast<const float2*>(pr2 + 64));
+                const float2 x0 = __ldcg(reinterpret_cast<const float2*>(pr2 + chunk * 8)), x1 = __ldcg(reinterpret_cast<const float2*>(pr2 + chunk * 8 + 2));
+                const float2 x2 = __ldcg(reinterpret_cast<const float2*>(pr2 + chunk * 8 + 4)), x3 = __ldcg(reinterpret_cast<const float2*>(pr2 + chunk * 8 + 6));
+                ov[k][0] = make_float4(x0.x, x0.y, x1.x, x1.y);
+                ov[k][1] = make_float4(x2.x, x2.y, x3.x, x3.y);
+              }
+            float mb = mrun;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (s0 + k < S) mb = fmaxf(mb, ml[k].x);
+            if (mb == -INFINITY) continue;
+            const float resc = mrun == -INFINITY ? 0.f : exp2f((mrun - mb) * sl2);
+            lsum *= resc;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) accv[e] *= resc;
+            mrun = mb;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (s0 + k < S && ml[k].x != -INFINITY) {
+                const float w = exp2f((ml[k].x - mb) * sl2);
+                lsum = fmaf(ml[k].y, w, lsum);
+                accv[0] = fmaf(ov[k][0].x, w, accv[0]); accv[1] = fmaf(ov[k][0].y, w, accv[1]);
+                accv[2] = fmaf(ov[k][0].z, w, accv[2]); accv[3] = fmaf(ov[k][0].w, w, accv[3]);
+                accv[4] = fmaf(ov[k][1].x, w, accv[4]); accv[5] = fmaf(ov[k][1].y, w, accv[5]);
+                accv[6] = fmaf(ov[k][1].z, w, accv[6]); accv[7] = fmaf(ov[k][1].w, w, accv[7]);
+              }
           }
           const float inv = lsum > 0.f ? 1.0f / lsum : 0.f;
 #pragma unroll
@@ -602,82 +644,113 @@ template <int MT>
 __global__ void __launch_bounds__(FS_THREADS, 1)
 stream_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ Smem sm) {
   extern __shared__ uint8_t smem_raw[];
-  // `sm` holds offsets from a 1024-aligned base inside the dynamic shared memory (the ring sits at offset 0)
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));     // generic pointer to the ring
-  Smem s = sm;
-  s.ring += base; s.uni += base; s.stats += base; s.bars_full += base; s.bars_empty += base; s.flags += base;
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;      // shared-window address of the map's base
+  uint8_t* smem_gen = smem_raw + (sb - smem_u32(smem_raw));       // the same place as a generic pointer
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x, cta = blockIdx.x;
-  volatile int* s_abort = reinterpret_cast<volatile int*>(smem_gen + (s.flags - s.ring));
+  volatile int* s_abort = reinterpret_cast<volatile int*>(smem_gen + sm.flags);
+  const int D = a.D, Mt = a.B * a.ntok, nv = D >> 7;
+  const uint32_t lnbar = sb + sm.bars + 200;
+  const uint32_t ln_bytes = 8u * D;      // gamma | beta, fp32
 
+  Prod pr{0, 0, 0, 0, 0u};
   if (threadIdx.x == 0) {
-    for (int i = 0; i < a.n_stages; ++i) { mbar_init(s.bars_full + 8 * i, 1); mbar_init(s.bars_empty + 8 * i, FS_CW); }
+    for (int i = 0; i < a.n_stages; ++i) { mbar_init(sb + sm.bars + 8 * i, 1); mbar_init(sb + sm.bars + 96 + 8 * i, FS_CW); }
+    mbar_init(sb + sm.bars + 192, 1);
+    mbar_init(lnbar, 1);
+    mbar_init(lnbar + 8, 1);
     *s_abort = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // this CTA's slabs of one layer, in consumption order: product, unit, K chunk
+    unsigned long long* sched = reinterpret_cast<unsigned long long*>(smem_gen + sm.sched);
+    const int nchunk = a.F / D;
+    int n = 0;
+    for (int p = 0; p < 4; ++p) {
+      const unsigned long long off = p == 0 ? a.wqkv : (p == 1 ? a.wo : (p == 2 ? a.w1 : a.w2s));
+      const int units = (p == 0 ? 3 * D : (p == 2 ? a.F : D)) >> 3, nch = p == 3 ? nchunk : 1;
+      for (int u = cta; u < units; u += G)
+        for (int j = 0; j < nch; ++j) sched[n++] = off + ((unsigned long long)u * nch + j) * sm.stage_bytes;
+    }
+    pr.n_entries = n;
+    if (n == 0) pr.l = a.layers;
     fence_async_smem();
+    pump(a, sm, sb, smem_gen, pr, FS_MAX_STAGES);       // the weight stream starts before anything else
+    // LayerNorm parameters of layer 0's two LN phases (gamma and beta are adjacent in the packed weights)
+    mbar_expect_tx(lnbar, ln_bytes);
+    bulk_g2s(sb + sm.lnp, a.pre_ln ? (const void*)lw(a, 0, a.ln1_w) : (const void*)(a.W + a.enc_ln_w), ln_bytes, lnbar);
+    mbar_expect_tx(lnbar + 8, ln_bytes);
+    bulk_g2s(sb + sm.lnp + ln_bytes, a.pre_ln ? lw(a, 0, a.ln2_w) : lw(a, 0, a.ln1_w), ln_bytes, lnbar + 8);
   }
   __syncthreads();
-  Prod pr{0, 0, cta, 0, 0, 0u, 0};
-  if (threadIdx.x == 0) {
-    prod_skip_empty(a, pr, G);
-    pump(a, s, pr, FS_MAX_STAGES);       // the weight stream starts before anything else
-  }
 
-  const int D = a.D, Mt = a.B * a.ntok, nv = D >> 7;
   unsigned long long nbar = 0;
   Ring rs{0, 0};
+  uint32_t aphase = 0;
   bool ok = true;
+  const int tr = threadIdx.x == 0 ? (cta == 0 ? 0 : (cta == G - 1 ? 1 : -1)) : -1;
+#define FS_TRACE(l_, ev_) do { if (tr >= 0 && (l_) < 64) g_fused_trace[tr][l_][ev_] = global_ns(); } while (0)
   // ---- embed: R = projected frame + sinusoidal position (absolute index frame + 2), one warp per row
   for (int row = cta * FS_CW + warp; row < Mt; row += G * FS_CW) {
     const int b = row / a.ntok, t = row - b * a.ntok;
     const float* fr = a.feats + ((size_t)b * a.feat_rows + a.f0 + t) * D + 4 * lane;
     const float* ps = reinterpret_cast<const float*>(a.W + a.sin_table) + (size_t)(a.f0 + t + 2) * D + 4 * lane;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j < nv) {
-        const float4 x = __ldcg(reinterpret_cast<const float4*>(fr + 128 * j));
-        const float4 p = *reinterpret_cast<const float4*>(ps + 128 * j);
-        *reinterpret_cast<float4*>(a.R + (size_t)row * D + 4 * lane + 128 * j) = make_float4(x.x + p.x, x.y + p.y, x.z + p.z, x.w + p.w);
-      }
-  }
-  ok = grid_barrier(a, s, pr, ++nbar * G, s_abort);
-
-  for (int l = 0; l < a.layers && ok; ++l) {
-    // LayerNorm feeding the QKV product / the FFN, and (post-LN) the LayerNorm pending on the stored residual sum
-    const float *g_qkv, *b_qkv, *g_ffn, *b_ffn;
-    if (a.pre_ln) {
-      g_qkv = lw(a, l, a.ln1_w); b_qkv = lw(a, l, a.ln1_b); g_ffn = lw(a, l, a.ln2_w); b_ffn = lw(a, l, a.ln2_b);
-    } else {
-      g_qkv = l == 0 ? reinterpret_cast<const float*>(a.W + a.enc_ln_w) : lw(a, l - 1, a.ln2_w);
-      b_qkv = l == 0 ? reinterpret_cast<const float*>(a.W + a.enc_ln_b) : lw(a, l - 1, a.ln2_b);
-      g_ffn = lw(a, l, a.ln1_w); b_ffn = lw(a, l, a.ln1_b);
+    for (int j = 0; j < nv; ++j) {
+      const float4 x = __ldcg(reinterpret_cast<const float4*>(fr + 128 * j));
+      const float4 p = *reinterpret_cast<const float4*>(ps + 128 * j);
+      *reinterpret_cast<float4*>(a.R + (size_t)row * D + 4 * lane + 128 * j) = make_float4(x.x + p.x, x.y + p.y, x.z + p.z, x.w + p.w);
     }
-    // ---- phase 1: LN + QKV
-    ln_rows_to_smem(a, s, smem_gen, warp, lane, g_qkv, b_qkv);
-    named_bar(1, 32 * FS_CW);
-    ok = gemm_phase<MT>(a, s, smem_gen, rs, pr, l, 3 * D, D, nullptr, 0, EPI_QKV, lw(a, l, a.bqkv), nullptr, nullptr, warp, lane) && ok;
-    ok = grid_barrier(a, s, pr, ++nbar * G, s_abort) && ok;
-    if (!ok) break;
-    // ---- phase 2: attention over the cache (this step's K/V rows were appended by phase 1)
-    attention_phase(a, s, smem_gen, pr, l, warp, lane);
-    ok = grid_barrier(a, s, pr, ++nbar * G, s_abort);
-    if (!ok) break;
-    // ---- phase 3: out_proj + residual
-    ok = gemm_phase<MT>(a, s, smem_gen, rs, pr, l, D, D, a.ctx, D, EPI_RESID, lw(a, l, a.bo), a.pre_ln ? nullptr : g_qkv,
-                        a.pre_ln ? nullptr : b_qkv, warp, lane) && ok;
-    ok = grid_barrier(a, s, pr, ++nbar * G, s_abort) && ok;
-    if (!ok) break;
-    // ---- phase 4: LN + fc1 + GELU
-    ln_rows_to_smem(a, s, smem_gen, warp, lane, g_ffn, b_ffn);
-    named_bar(1, 32 * FS_CW);
-    ok = gemm_phase<MT>(a, s, smem_gen, rs, pr, l, a.F, D, nullptr, 0, EPI_GELU, lw(a, l, a.b1), nullptr, nullptr, warp, lane) && ok;
-    ok = grid_barrier(a, s, pr, ++nbar * G, s_abort) && ok;
-    if (!ok) break;
-    // ---- phase 5: fc2 + residual
-    ok = gemm_phase<MT>(a, s, smem_gen, rs, pr, l, D, a.F, a.h, a.F, EPI_RESID, lw(a, l, a.b2), a.pre_ln ? nullptr : g_ffn,
-                        a.pre_ln ? nullptr : b_ffn, warp, lane) && ok;
-    ok = grid_barrier(a, s, pr, ++nbar * G, s_abort) && ok;
+  }
+  ok = grid_barrier(a, sm, sb, smem_gen, pr, ++nbar * G, s_abort);
+
+#pragma unroll 1
+  for (int l = 0; l < a.layers && ok; ++l) {
+    // The four products of a layer run through ONE inlined copy of the LayerNorm / product / barrier code (a rolled
+    // loop): every instruction of this kernel executes once per layer, so its code must stay small.
+    FS_TRACE(l, 0);
+    if (tr >= 0 && l < 64) g_fused_trace[tr][l][11] = (unsigned long long)clock64();
+#pragma unroll 1
+    for (int ph = 0; ph < 4 && ok; ++ph) {
+      // ph 0: LN + QKV -> q, K/V cache | 1: out_proj + residual | 2: LN + fc1 + GELU | 3: fc2 + residual
+      // LayerNorm parameters: buffer 0 serves ph 0 (and the post-LN residual of ph 1), buffer 1 ph 2 (and ph 3)
+      const float* lnp = reinterpret_cast<const float*>(smem_gen + sm.lnp + (ph >> 1) * ln_bytes);
+      if ((ph & 1) == 0) {
+        ok = wait_bar(lnbar + 8 * (ph >> 1), l & 1) && ok;
+        ln_rows_to_smem(a, sm, smem_gen, warp, lane, lnp);
+        named_bar(1, 32 * FS_CW);
+      }
+      const int N = ph == 0 ? 3 * D : (ph == 2 ? a.F : D), K = ph == 3 ? a.F : D;
+      const bf16* ag = ph == 1 ? a.ctx : (ph == 3 ? a.h : nullptr);
+      const int epi = ph == 0 ? EPI_QKV : (ph == 2 ? EPI_GELU : EPI_RESID);
+      const float* bias = lw(a, l, ph == 0 ? a.bqkv : (ph == 1 ? a.bo : (ph == 2 ? a.b1 : a.b2)));
+      ok = gemm_phase<MT>(a, sm, sb, smem_gen, rs, aphase, l, N, K, ag, epi, bias, ((ph & 1) && !a.pre_ln) ? lnp : nullptr,
+                          warp, lane) && ok;
+      FS_TRACE(l, ph == 0 ? 1 : 3 + 2 * ph);
+      if (threadIdx.x == 0 && (ph & 1) && l + 1 < a.layers) {
+        // this LayerNorm-parameter buffer is free now: request the next layer's set.  Pre-LN: ln1 / ln2 of layer
+        // l + 1; post-LN: the LayerNorm pending on the residual sum, i.e. ln2 of layer l / ln1 of layer l + 1.
+        const float* src = ph == 1 ? (a.pre_ln ? lw(a, l + 1, a.ln1_w) : lw(a, l, a.ln2_w))
+                                   : (a.pre_ln ? lw(a, l + 1, a.ln2_w) : lw(a, l + 1, a.ln1_w));
+        fence_async_smem();
+        mbar_expect_tx(lnbar + 8 * (ph >> 1), ln_bytes);
+        bulk_g2s(sb + sm.lnp + (ph >> 1) * ln_bytes, src, ln_bytes, lnbar + 8 * (ph >> 1));
+      }
+      ok = grid_barrier(a, sm, sb, smem_gen, pr, ++nbar * G, s_abort) && ok;
+      FS_TRACE(l, ph == 0 ? 2 : 4 + 2 * ph);
+      if (ph == 0 && ok) {
+        // attention over the cache (this step's K/V rows were appended by the QKV epilogue)
+        attention_phase(a, sm, smem_gen, l, warp, lane);
+        FS_TRACE(l, 3);
+        ok = grid_barrier(a, sm, sb, smem_gen, pr, ++nbar * G, s_abort);
+        FS_TRACE(l, 4);
+      }
+      if (threadIdx.x == 0 && ok && (ph == 0 || ph == 2)) {
+        // the next product reads its A operand from global memory (attention context / FFN hidden): one bulk
+        // copy into abuf (every warp of this CTA is past its last use: they all arrived at the barrier above)
+        fence_async_smem();
+        mbar_expect_tx(sb + sm.bars + 192, (uint32_t)Mt * D * 2);
+        bulk_g2s(sb + sm.abuf, ph == 0 ? a.ctx : a.h, (uint32_t)Mt * D * 2, sb + sm.bars + 192);
+      }
+    }
   }
   if (ok) {
     // ---- final LayerNorm of the emitted frames: encoder.layer_norm (pre-LN) or the pending final_layer_norm
@@ -690,7 +763,7 @@ stream_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__
 #pragma unroll
       for (int j = 0; j < 8; ++j) if (j < nv) v[j] = __ldcg(reinterpret_cast<const float4*>(xr + 128 * j));
       float mean, rstd;
-      row_stats<8>(v, nv, D, mean, rstd);
+      row_stats(v, nv, D, mean, rstd);
       bf16* dst = a.out + ((size_t)t * a.B + b) * D + 4 * lane;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
@@ -731,32 +804,35 @@ w2vs_status_t launch_stream_fused(const StreamFusedArgs& h, cudaStream_t st) {
   W2VS_REQUIRE(stream_fused_applicable(cfg, h.B, h.ntok), "fused incremental step: configuration not supported");
   const int D = cfg->embed_dim, F = cfg->ffn_dim, G = num_sms();
   Smem sm;
-  sm.pitch_w = 2 * D + 32;
-  sm.pitch_a = 2 * D + 32;
-  sm.stage_bytes = 8 * sm.pitch_w;
-  const int a_bytes = FS_ROWS * sm.pitch_a + FS_CW * FS_UMAX * FS_ROWS * 8 * 4;
-  const int uni_bytes = (int)align_up((size_t)(a_bytes > 2 * FS_ATT_GROUP_BYTES ? a_bytes : 2 * FS_ATT_GROUP_BYTES), 1024);
-  const int tail_bytes = 1024;     // stats (256) + barriers (2 x 96) + flags
-  int n_stages = (FS_SMEM_LIMIT - 1024 - uni_bytes - tail_bytes) / sm.stage_bytes;
+  sm.stage_bytes = 8 * 2 * D;               // a slab lands exactly as it lies in global memory: one bulk copy
+  const int abuf_bytes = FS_ROWS * 2 * D, part_bytes = FS_CW * FS_UMAX * FS_ROWS * 8 * 4;
+  const int uni_bytes = (int)align_up((size_t)(abuf_bytes + part_bytes > 2 * FS_ATT_GROUP_BYTES ? abuf_bytes + part_bytes
+                                                                                                : 2 * FS_ATT_GROUP_BYTES), 1024);
+  const int lnp_bytes = 2 * 8 * D;          // two [gamma | beta] fp32 sets
+  const int tail_bytes = 1024;              // slab list (256) + stats (256) + barriers (256) + flags (64)
+  int n_stages = (FS_SMEM_LIMIT - 1024 - uni_bytes - lnp_bytes - tail_bytes) / sm.stage_bytes;
   if (n_stages > FS_MAX_STAGES) n_stages = FS_MAX_STAGES;
   // the ring is topped up at every grid barrier, so it has to hold what one product phase of a CTA consumes
   const int u_qkv = (3 * D / 8 + G - 1) / G, u_fc1 = (F / 8 + G - 1) / G, u_fc2 = ((D / 8 + G - 1) / G) * (F / D);
   const int need = u_qkv > u_fc1 ? (u_qkv > u_fc2 ? u_qkv : u_fc2) : (u_fc1 > u_fc2 ? u_fc1 : u_fc2);
   W2VS_REQUIRE(n_stages >= need && n_stages >= 2, "fused incremental step: shared memory too small for the weight ring");
+  W2VS_REQUIRE(u_qkv + (D / 8 + G - 1) / G + u_fc1 + u_fc2 <= FS_SCHED, "fused incremental step: too few SMs for this model");
   const int ring_bytes = (int)align_up((size_t)n_stages * sm.stage_bytes, 1024);
   sm.ring = 0;
-  sm.uni = ring_bytes;
-  sm.stats = sm.uni + uni_bytes;
-  sm.bars_full = sm.stats + 256;
-  sm.bars_empty = sm.bars_full + 8 * FS_MAX_STAGES;
-  sm.flags = sm.bars_empty + 8 * FS_MAX_STAGES;
-  const size_t smem_bytes = (size_t)ring_bytes + uni_bytes + tail_bytes + 1024;
+  sm.abuf = ring_bytes;
+  sm.part = sm.abuf + abuf_bytes;
+  sm.lnp = sm.abuf + uni_bytes;
+  sm.sched = sm.lnp + lnp_bytes;
+  sm.stats = sm.sched + 256;
+  sm.bars = sm.stats + 256;
+  sm.flags = sm.bars + 256;
+  const size_t smem_bytes = (size_t)ring_bytes + uni_bytes + lnp_bytes + tail_bytes + 1024;
 
   FusedArgs a{};
   a.W = reinterpret_cast<const uint8_t*>(h.W);
   const LayerW& l0 = h.wl->layer0;
   a.wqkv = l0.wqkv; a.bqkv = l0.bqkv; a.wo = l0.wo; a.bo = l0.bo; a.ln1_w = l0.ln1_w; a.ln1_b = l0.ln1_b;
-  a.w1 = l0.w1; a.b1 = l0.b1; a.w2 = l0.w2; a.b2 = l0.b2; a.ln2_w = l0.ln2_w; a.ln2_b = l0.ln2_b;
+  a.w1 = l0.w1; a.b1 = l0.b1; a.w2s = l0.w2s; a.b2 = l0.b2; a.ln2_w = l0.ln2_w; a.ln2_b = l0.ln2_b;
   a.layer_stride = h.wl->layer_stride; a.enc_ln_w = h.wl->enc_ln_w; a.enc_ln_b = h.wl->enc_ln_b; a.sin_table = h.wl->sin_table;
   a.layers = cfg->layers; a.D = D; a.F = F; a.H = cfg->heads; a.pre_ln = cfg->layer_norm_first != 0;
   a.B = h.B; a.ntok = h.ntok; a.n_main = h.n_main; a.f0 = h.f0;
@@ -792,6 +868,18 @@ w2vs_status_t launch_stream_fused(const StreamFusedArgs& h, cudaStream_t st) {
   cudaError_t e = cudaLaunchKernelEx(&lc, kern, a, sm);
   if (e != cudaSuccess) { set_error("stream_fused_kernel launch: %s", cudaGetErrorString(e)); cudaGetLastError(); return W2VS_CUDA_ERROR; }
   W2VS_CHECK_LAUNCH("stream_fused_kernel");
+  return W2VS_OK;
+}
+
+w2vs_status_t debug_read_fused_trace(unsigned long long* out, int n) {
+  if (n > 2 * 64 * 12) {      // the fine-grained events follow the per-phase table
+    const int n2 = n - 2 * 64 * 12 > 2 * 96 ? 2 * 96 : n - 2 * 64 * 12;
+    cudaError_t e2 = cudaMemcpyFromSymbol(out + 2 * 64 * 12, g_fused_trace2, (size_t)n2 * 8);
+    if (e2 != cudaSuccess) { set_error("read g_fused_trace2: %s", cudaGetErrorString(e2)); return W2VS_CUDA_ERROR; }
+    n = 2 * 64 * 12;
+  }
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_fused_trace, (size_t)n * 8);
+  if (e != cudaSuccess) { set_error("read g_fused_trace: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
   return W2VS_OK;
 }
 

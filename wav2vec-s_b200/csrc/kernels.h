@@ -81,6 +81,7 @@ w2vs_status_t launch_gemm_skinny(const GemmArgs& g, cudaStream_t st); // M <= 64
 bool gemm_skinny_applicable(const GemmArgs& g);
 w2vs_status_t launch_gemm(int impl, const GemmArgs& g, cudaStream_t st);  // impl: w2vs_gemm_impl_t
 w2vs_status_t debug_read_tc2_fault(int* out);
+w2vs_status_t debug_read_attn_tc_fault(int* out);
 
 // ---- attention ------------------------------------------------------------------------------------
 // Two modes share the kernels:
@@ -130,6 +131,7 @@ struct StreamFusedArgs {
 bool stream_fused_applicable(const w2vs_config* cfg, int B, int ntok);
 w2vs_status_t launch_stream_fused(const StreamFusedArgs& a, cudaStream_t st);
 w2vs_status_t debug_read_fused_fault(int* out);
+w2vs_status_t debug_read_fused_trace(unsigned long long* out, int n);
 
 // ---- positional conv + weight packing -----------------------------------------------------------------
 struct PosConvArgs {
@@ -147,6 +149,7 @@ w2vs_status_t launch_pack_posconv_tc(const float* w_folded, void* dst, int D, in
                                      cudaStream_t st);
 
 w2vs_status_t launch_pack_copy(const float* src, void* dst, int dst_dtype, int64_t n, cudaStream_t st);
+w2vs_status_t launch_pack_slabs(const float* src, void* dst, int N, int K, int KC, cudaStream_t st);
 w2vs_status_t launch_pack_conv(const float* src, void* dst, int dst_dtype, int C_out, int C_in, int k,
                                cudaStream_t st);
 w2vs_status_t launch_pack_posconv(const float* g, const float* v, float* dst, int D, int groups, int k,

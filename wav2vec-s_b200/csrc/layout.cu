@@ -215,6 +215,7 @@ void make_weight_layout(const w2vs_config* cfg, WeightLayout* wl) {
   l.b2 = b.take((size_t)D * 4);
   l.ln2_w = b.take((size_t)D * 4);
   l.ln2_b = b.take((size_t)D * 4);
+  l.w2s = stream_fused_model(cfg) ? b.take((size_t)D * F * 2) : kNone;
   wl->layer_stride = b.off - wl->layers_begin;
   wl->total = wl->layers_begin + wl->layer_stride * (size_t)cfg->layers;
 }

@@ -36,6 +36,8 @@ struct LayerW {
   size_t ln1_w, ln1_b;    // self_attn_layer_norm
   size_t w1, b1;          // act [F][D], fp32 [F]
   size_t w2, b2;          // act [D][F], fp32 [D]
+  size_t w2s;             // bf16 [D/8][F/D][8][D]: fc2 weights in the slab order of the fused incremental step (each
+                          // 8-row x D-wide slab contiguous), or SIZE_MAX when that kernel does not apply
   size_t ln2_w, ln2_b;    // final_layer_norm
 };
 struct WeightLayout {
@@ -58,6 +60,7 @@ inline LayerW layer_at(const WeightLayout& wl, int n) {
   size_t d = (size_t)n * wl.layer_stride;
   l.wqkv += d; l.bqkv += d; l.wo += d; l.bo += d; l.ln1_w += d; l.ln1_b += d;
   l.w1 += d; l.b1 += d; l.w2 += d; l.b2 += d; l.ln2_w += d; l.ln2_b += d;
+  if (l.w2s != kNone) l.w2s += d;
   return l;
 }
 
@@ -83,6 +86,12 @@ struct Workspace {
 void make_workspace(const w2vs_config* cfg, const Geometry& g, int B, Workspace* ws);
 
 inline size_t act_size(const w2vs_config* cfg) { return cfg->dtype == W2VS_BF16 ? 2 : 4; }
+// Models the persistent incremental-step kernel (k_stream_fused.cu) can run: they carry the slab-ordered fc2 copy.
+inline bool stream_fused_model(const w2vs_config* cfg) {
+  const int D = cfg->embed_dim, F = cfg->ffn_dim;
+  return cfg->dtype == W2VS_BF16 && D % 128 == 0 && D <= 1024 && F % D == 0 && cfg->heads * 64 == D &&
+         cfg->pos_type == W2VS_POS_SIN && cfg->extractor_mode == W2VS_EXTRACTOR_LAYER_NORM;
+}
 
 // Positional conv (pos_type = conv) on the tensor cores: bf16 models whose group width is a multiple of 8.
 // Each group is an implicit GEMM over a group-major copy of the frames, channels padded to Dgp (multiple of 64).

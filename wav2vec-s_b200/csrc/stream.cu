@@ -146,8 +146,9 @@ w2vs_status_t block_step(const w2vs_config* cfg, const WeightLayout& wl, const S
   void* ctx = at<void>(d_ws, L.ctx);
   void* h = at<void>(d_ws, L.h);
   const bool pre_ln = cfg->layer_norm_first != 0;
-  if (cfg->stream_step_impl == 0 && stream_fused_applicable(cfg, B, ntok)) {
-    // bf16 models, at most 32 tokens per step: the whole step is one persistent cooperative kernel
+  if (cfg->stream_step_impl == 2 && stream_fused_applicable(cfg, B, ntok)) {
+    // opt-in (stream_step_impl = 2; bf16 models, at most 32 tokens per step): the whole step as one persistent
+    // cooperative kernel
     StreamFusedArgs fa{};
     fa.cfg = cfg; fa.wl = &wl; fa.W = W;
     fa.B = B; fa.ntok = ntok; fa.n_main = n_main; fa.f0 = f0;
