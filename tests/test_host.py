@@ -145,7 +145,9 @@ def test_posconv_layout_sizes():
     folded = D * (D // groups) * k * 4 + D * 4                                    # fp32 folded weights + bias
     sin_tab = 64 * D * 4
     assert sizes(torch.float32)[0] - (sizes_sin(torch.float32) - sin_tab) == folded
-    assert sizes(torch.bfloat16)[0] - (sizes_sin(torch.bfloat16) - sin_tab) == folded + D * k * Dgp * 2
+    # (the sinusoidal bf16 model also carries the slab-ordered fc2 copy of the fused incremental step, layout.h)
+    w2s = 12 * D * 3072 * 2
+    assert sizes(torch.bfloat16)[0] - (sizes_sin(torch.bfloat16) - sin_tab - w2s) == folded + D * k * Dgp * 2
     T = m.geometry(16000, 16, 8).frames
     assert sizes(torch.bfloat16)[1] > 2 * (T + k) * D * 4 + groups * (2 * (T + k) + k) * Dgp * 2
 
