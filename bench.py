@@ -296,9 +296,11 @@ def stream_bench(a, kind, B, seconds):
     print(json.dumps(line))
 
 
-def incremental_probe(model, cfg, dev, seconds=30):
-    """p50 / p90 device latency of a decision step (first chunk 24 frames, then 16 frames = 5120 samples per step) of
-    one stream through BlockWiseWav2Vec2Model.open_stream -> w2vs_stream_step, on the bench's own weights."""
+def incremental_probe(model, cfg, dev, B=1, seconds=30):
+    """configs[3]: p50 / p90 device latency of a decision step (first chunk 24 frames, then 16 frames = 5120 samples per
+    step) of B lock-step streams through BlockWiseWav2Vec2Model.open_stream -> w2vs_stream_step, on the bench's own
+    weights, with its HBM roofline: a step has to read the packed bf16 weights once (613 MB for the large model) plus
+    the cached K/V of the left context."""
     import torch
     import wav2vec_s_b200 as W
     from wav2vec_s_b200.model import EncoderStream
@@ -306,14 +308,14 @@ def incremental_probe(model, cfg, dev, seconds=30):
     sm.load_state_dict(model.state_dict(), strict=False)
     sm = sm.to(dev, next(model.parameters()).dtype).eval()
     L = seconds * SR
-    wav = torch.randn(1, L, generator=torch.Generator().manual_seed(4321)).to(dev)
+    wav = torch.randn(B, L, generator=torch.Generator().manual_seed(4321)).to(dev)
     bounds = [7760]
     while bounds[-1] + 5120 < L:
         bounds.append(bounds[-1] + 5120)
     bounds.append(L)
     lats = []
     for rep in range(3):
-        st = sm.open_stream(B=1, max_seconds=seconds + 1, max_new_samples=7760 + 400)
+        st = sm.open_stream(B=B, max_seconds=seconds + 1, max_new_samples=7760 + 400)
         pos, lat = 0, []
         for n in bounds:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -328,9 +330,33 @@ def incremental_probe(model, cfg, dev, seconds=30):
             lats += lat[1:-1]
     lats.sort()
     p50 = lats[len(lats) // 2]
-    return {"metric": "p50 per-chunk latency (wav2vec-S large incremental, 1 stream, 16 frames/step)",
-            "p50_ms": p50, "p90_ms": lats[int(0.9 * len(lats))], "unit": "ms", "steps": len(lats),
-            "realtime_factor": 0.32 / (p50 / 1e3)}
+    D, Ly, F = cfg["encoder_embed_dim"], cfg["encoder_layers"], cfg["encoder_ffn_embed_dim"]
+    wbytes = Ly * (4 * D * D + 2 * D * F) * 2 + (4 * 512 * 512 * 3 + 2 * 512 * 512 * 2 + 512 * D) * 2   # GEMM operands, bf16
+    kvbytes = B * Ly * 2 * D * 2 * (seconds * 50 // 2)                 # cached K/V read at the mean left context
+    pk, pk_kind = peaks()
+    ach = (wbytes + kvbytes) / (p50 / 1e3) / 1e9
+    return {"metric": f"p50 per-chunk latency (wav2vec-S large incremental, {B} stream(s), 16 frames/step)",
+            "streams": B, "p50_ms": p50, "p90_ms": lats[int(0.9 * len(lats))], "unit": "ms", "steps": len(lats),
+            "realtime_factor": 0.32 / (p50 / 1e3),
+            "roofline": {"bound": "hbm", "kernel": "one decision step (weights streamed once + cached K/V)",
+                         "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                         "traffic": None, "algorithmic_bytes": wbytes + kvbytes, "peak_source": pk_kind}}
+
+
+def rows_bytes_per_utt(cfg, L):
+    """Algorithmic HBM bytes of the stand-alone row passes of one utterance (bf16 model): conv LayerNorm + GELU passes
+    (read + write bf16), feature LayerNorm, token embedding, two LayerNorms per transformer layer (read fp32, write
+    bf16), final LayerNorm."""
+    spec = conv_spec(cfg)
+    t, lens = L, []
+    for (c, k, s_) in spec:
+        t = (t - k) // s_ + 1
+        lens.append(t)
+    n_ln = 1 if cfg["encoder_layers"] == 12 else 7
+    conv_ln = sum(4 * spec[i][0] * lens[i] for i in range(1, len(spec)) if i < n_ln)
+    fl = flops_per_utt(cfg, L)
+    T, M, D, Ly = fl["T"], fl["M"], cfg["encoder_embed_dim"], cfg["encoder_layers"]
+    return conv_ln + 4 * spec[-1][0] * T + (4 * T * D + 6 * M * D) + 2 * Ly * M * D * 6 + 6 * T * D
 
 
 def main():
@@ -343,6 +369,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-incremental", action="store_true", help="skip the incremental-mode latency probe")
+    ap.add_argument("--no-extra-points", action="store_true", help="N > 1: skip the 30 s weak / global-128 strong points")
     ap.add_argument("--kernel-detail", action="store_true", help="per-kernel (name, shape) device ms in the JSON line")
     ap.add_argument("--cpu-sample-batch", type=int, default=4,
                     help="utterances per step of the CPU reference arm (a bounded sample of the workload's batch)")
@@ -499,6 +526,65 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
 
+    # ---- N > 1: the one collective of the data plane -- gather every rank's outputs (NCCL all-gather over NVLink) ----
+    gather = None
+    if world > 1:
+        from wav2vec_s_b200 import sharding
+        yb = step_device()
+        nfr = torch.full((B,), yb.size(1), dtype=torch.int64, device=dev)
+        for _ in range(2):
+            sharding.gather_outputs(yb, nfr)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        g0.record()
+        for _ in range(reps):
+            outs, counts = sharding.gather_outputs(yb, nfr)
+        g1.record()
+        barrier()
+        assert len(outs) == B * world and int(counts.sum()) == B * world * yb.size(1)
+        gms = g0.elapsed_time(g1) / reps
+        # step + gather back to back (what a consumer that needs every rank's output on every rank pays)
+        g2, g3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        g2.record()
+        for _ in range(a.steps):
+            sharding.gather_outputs(step_device(), nfr)
+        g3.record()
+        barrier()
+        tg = torch.tensor([gms, g2.elapsed_time(g3)], device=dev, dtype=torch.float64)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        rx = yb.numel() * yb.element_size() * (world - 1)
+        gather = {"what": "all-gather of every rank's [B, T, D] outputs + frame counts (sharding.gather_outputs, NCCL)",
+                  "ms": float(tg[0]), "bytes_received_per_rank": rx, "gbps_per_rank": rx / (float(tg[0]) / 1e3) / 1e9,
+                  "ms_per_step_with_gather": float(tg[1]) / a.steps,
+                  "value_with_gather": B * seconds * world / (float(tg[1]) / a.steps / 1e3)}
+        del outs, yb
+
+    # ---- N > 1: two more points of SURVEY.md 8(d) on the same ranks: 30 s utterances (weak) and a fixed global batch
+    #      of 128 x 20 s (strong) ----
+    extra_points = None
+    if world > 1 and a.workload == "large_64x20s" and not a.no_extra_points:
+        extra_points = {}
+        for name, (bb, secs) in {"large_64x30s_weak": (64, 30), "large_global128x20s_strong": (max(1, 128 // world), 20)}.items():
+            gx = torch.Generator().manual_seed(99 + rank)
+            xw = torch.randn(bb, secs * SR, generator=gx).to(dev).to(dtype)
+            for _ in range(2):
+                model.extract_features(xw, None)
+            barrier()
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x0.record()
+            for _ in range(5):
+                model.extract_features(xw, None)
+            x1.record()
+            barrier()
+            tx = torch.tensor([x0.elapsed_time(x1)], device=dev, dtype=torch.float64)
+            dist.all_reduce(tx, op=dist.ReduceOp.MAX)
+            extra_points[name] = {"batch_per_gpu": bb, "utterance_s": secs, "ms_per_step": float(tx[0]) / 5,
+                                  "value": bb * secs * world / (float(tx[0]) / 5 / 1e3), "unit": "audio-s/s"}
+            del xw
+        model._ws = None
+
     # ---- per-kernel-class device time of one step (CUDA events on the launching stream) -----
     prof = None
     if hasattr(cabi.lib(), "w2vs_prof_enable"):
@@ -526,14 +612,17 @@ def main():
         if prof is not None and prof.get("gemm", {}).get("count"):
             gm = prof["gemm"]
             ach = fl["gemm"] * B / (gm["ms"] / 1e3) / 1e12
-            traffic, traffic_note = None, None
-            tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic_cfg3.json")
-            if a.workload == "large_64x20s" and os.path.isfile(tpath):
-                tj = json.load(open(tpath))
-                traffic = tj["bytes_per_step_covered"]
-                traffic_note = (f"DRAM bytes of the {tj['launches_covered']} transformer GEMM launches of a step (of "
-                                f"{tj['launches_per_step']}; conv/proj launches not captured), {tj['source']}; algorithmic "
-                                f"bytes of the same launches: {24 * sum(tj['algorithmic_bytes'].values())}")
+            # DRAM traffic per class and step: dram__bytes_read.sum + dram__bytes_write.sum of EVERY launch of one step,
+            # one ncu pass of this command (tools/ncu_traffic.py; a profiler cannot run inside the timed process)
+            traffic, traffic_note, tclass = None, None, {}
+            for tname in ("r02_traffic_" + a.workload + ".json",):
+                tpath = os.path.join(ROOT, "profiles", tname)
+                if os.path.isfile(tpath):
+                    tj = json.load(open(tpath))
+                    tclass = tj.get("bytes_per_step", {})
+                    traffic = tclass.get("gemm")
+                    traffic_note = (f"{tj.get('source', 'ncu')}; launches per step covered: {tj.get('launches_per_step')}; "
+                                    f"algorithmic bytes of the GEMM class: {tj.get('algorithmic_bytes', {}).get('gemm')}")
             line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc2_kernel (all launches of one step)",
                                 "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                                 "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic,
@@ -541,6 +630,27 @@ def main():
                                 "peak_source": pk_kind + " (sustained: timed inside a long step)",
                                 "launches_per_step": gm["count"], "ms_per_step": gm["ms"]}
             line["kernel_ms_per_step"] = {k: round(v["ms"], 3) for k, v in prof.items() if "[" not in k and "_kernel" not in k}
+            # every kernel class against the roofline that bounds it (tensor pipe: sustained bf16 peak; HBM: copy peak)
+            rl = [dict(line["roofline"], **{"class": "gemm"})]
+            if prof.get("attention", {}).get("ms"):
+                t_at = prof["attention"]["ms"]
+                rl.append({"class": "attention", "kernel": "attn_tc_kernel (block-mask-visible pairs only)", "bound": "tensor",
+                           "achieved": fl["attn"] * B / (t_at / 1e3) / 1e12, "peak": pk["bf16_tflops_sustained"],
+                           "unit": "TFLOP/s", "frac": fl["attn"] * B / (t_at / 1e3) / 1e12 / pk["bf16_tflops_sustained"],
+                           "ms_per_step": t_at, "traffic": tclass.get("attention")})
+            if prof.get("rows", {}).get("ms"):
+                rb = rows_bytes_per_utt(cfg, L) * B
+                rl.append({"class": "rows", "kernel": "LayerNorm / LN+GELU / embed / finalize passes", "bound": "hbm",
+                           "achieved": rb / (prof["rows"]["ms"] / 1e3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                           "frac": rb / (prof["rows"]["ms"] / 1e3) / 1e9 / pk["hbm_gbs"], "ms_per_step": prof["rows"]["ms"],
+                           "traffic": tclass.get("rows"), "algorithmic_bytes": rb})
+            if prof.get("conv0", {}).get("ms"):
+                cb = (wav_dev.element_size() * L + 2 * conv_spec(cfg)[0][0] * ((L - 10) // 5 + 1)) * B
+                rl.append({"class": "conv0", "kernel": "conv0_kernel (Conv1d 1->512 k10 s5 + LayerNorm + GELU)", "bound": "hbm",
+                           "achieved": cb / (prof["conv0"]["ms"] / 1e3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                           "frac": cb / (prof["conv0"]["ms"] / 1e3) / 1e9 / pk["hbm_gbs"], "ms_per_step": prof["conv0"]["ms"],
+                           "traffic": tclass.get("conv0"), "algorithmic_bytes": cb})
+            line["rooflines"] = rl
             if a.kernel_detail:
                 line["kernel_detail"] = {k: [round(v["ms"], 3), v["count"]] for k, v in sorted(prof.items())
                                          if "[" in k or "_kernel" in k}
@@ -550,9 +660,17 @@ def main():
             # the other half of BASELINE.json's metric: p50 latency of one decision step (16 new frames) of the
             # incremental path, one stream, same model; measured after the timed regions above
             try:
-                line["incremental"] = incremental_probe(model, cfg, dev)
+                line["incremental"] = incremental_probe(model, cfg, dev, B=1)
+                line["incremental_b16"] = incremental_probe(model, cfg, dev, B=16)
+                if line.get("rooflines") is not None:
+                    for key in ("incremental", "incremental_b16"):
+                        line["rooflines"].append(dict(line[key]["roofline"], **{"class": key, "ms_per_step": line[key]["p50_ms"]}))
             except Exception as ex:   # never lose the headline line to the secondary measurement
                 line["incremental"] = {"error": f"{type(ex).__name__}: {ex}"}
+        if gather is not None:
+            line["gather"] = gather
+        if extra_points is not None:
+            line["extra_points"] = extra_points
         if not a.no_cpu_baseline and world == 1:      # reported on rank 0 at N=1 only
             r = cpu_reference_run(kind, a.cpu_sample_batch, seconds, 3, 1)      # ~15 s of CPU work at cfg3
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -43,8 +43,9 @@ typedef enum {
 } w2vs_status_t;
 
 typedef enum { W2VS_F32 = 0, W2VS_BF16 = 1,
-               W2VS_I16 = 2   /* waveform samples only: 16-bit PCM, read as x / 32768 (what the SimulEval agent does on
+               W2VS_I16 = 2,  /* waveform samples only: 16-bit PCM, read as x / 32768 (what the SimulEval agent does on
                                  the host, rain/simul/transducer_searcher.py:74-80) */
+               W2VS_F16 = 3   /* input / output element type only (w2vs_config.io_dtype): IEEE half */
 } w2vs_dtype_t;
 typedef enum { W2VS_EXTRACTOR_DEFAULT = 0, W2VS_EXTRACTOR_LAYER_NORM = 1 } w2vs_extractor_mode_t;
 typedef enum { W2VS_POS_SIN = 0, W2VS_POS_CONV = 1 } w2vs_pos_type_t;
@@ -76,7 +77,13 @@ typedef struct {
                                           programmatic dependent launches; 2 = one persistent cooperative kernel per
                                           decision step where it applies (bf16, <= 32 tokens per step; parity-tested,
                                           measured slower than the chain so far: DESIGN.md section 5) */
-  int32_t reserved[6];
+  int32_t io_dtype;                    /* 0 = outputs in `dtype`; W2VS_F16 = the model was given in fp16 (`.half()`, as
+                                          the reference trainer does under --fp16, fairseq/fairseq/trainer.py:86-90):
+                                          encoder outputs are written as fp16.  Arithmetic is that of dtype = BF16:
+                                          bf16 tensor-core operands (the fp16 weights are rounded to bf16 when packed),
+                                          fp32 accumulation, residual stream and statistics -- the range-safe choice
+                                          for a 24-layer pre-LN residual stream */
+  int32_t reserved[5];
 } w2vs_config;
 
 /* ---- reference tensors handed to w2vs_weights_pack -------------------------------------
@@ -178,6 +185,15 @@ w2vs_status_t w2vs_stream_step(const w2vs_config* cfg, const void* d_packed_weig
                                int32_t wav_dtype, int32_t n_new, int32_t flush,
                                void* d_out_frames, int32_t out_capacity_frames, int32_t* n_out,
                                void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Move a live stream into larger state buffers (the K/V cache and the frame buffer are sized by max_frames): copies
+ * the conv carries, the projected frames and the cached K/V on `stream`, and the bookkeeping into host_state_new.
+ * The new buffers are sized by w2vs_stream_state_size(..., new_max_frames, ...); cfg.sin_rows must cover
+ * new_max_frames + 2 (re-pack the weights with a longer sinusoidal table first if needed).  The old buffers may be
+ * released once the copies have completed (stream order). */
+w2vs_status_t w2vs_stream_grow(const w2vs_config* cfg, const void* host_state_old, const void* d_state_old,
+                               int32_t new_max_frames, void* host_state_new, size_t host_bytes,
+                               void* d_state_new, size_t device_bytes, void* stream);
 
 /* Host-side counters of a stream: samples consumed, frames produced by the conv stack, and frames of
  * committed (final) blocks.  Any pointer may be NULL. */

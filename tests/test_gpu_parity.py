@@ -292,3 +292,114 @@ def test_online_encoder_wrapper_vs_oracle(use_proj):
     assert torch.equal(fm.cpu(), fmo)
     assert tuple(y.shape) == tuple(yo.shape)
     assert valid_rel_err(y.detach().cpu(), yo, fmo.numpy(), time_first=True) < FP32_TOL
+
+
+@pytest.mark.parametrize("name", ["tiny_preln_bias_ragged", "tiny_postln_ln1", "large_1s"])
+def test_fp16_model_vs_oracle(name):
+    """`.half()` models (the reference trainer halves the model under --fp16, fairseq/fairseq/trainer.py:86-90, as every
+    reference training script does): accepted, fp16 in / fp16 out, arithmetic of the bf16 path (bf16 tensor-core operands,
+    fp32 accumulation and residual stream -- include/w2vs.h, w2vs_config.io_dtype).  Against the reference algorithm in
+    fp32 arithmetic on the identical (fp16-valued) weights and waveform, at the bf16-mode bound."""
+    cfg, sd, wav, pm, _ = case_inputs(name)
+    m = build(W.Wav2VecSModel, cfg, sd, torch.float16)
+    src = wav.to(torch.float16)
+    y, fm = m.extract_features(src.cuda(), None if pm is None else pm.cuda())
+    assert y.dtype == torch.float16
+    sd16 = {k: (v.to(torch.float16).float() if v.is_floating_point() else v) for k, v in sd.items()}
+    yo, fmo = O.extract_features(sd16, cfg, src.float(), pm)
+    if fmo is not None:
+        assert torch.equal(fm.cpu(), fmo)
+    assert valid_rel_err(y.cpu(), yo, None if fmo is None else fmo.numpy()) < BF16_TOL
+    # the rain API and the incremental path return fp16 as well
+    r = build(W.BlockWiseWav2Vec2Model, cfg, sd, torch.float16)
+    out = r(src.cuda(), None if pm is None else pm.cuda())
+    assert out["encoder_out"][0].dtype == torch.float16
+    assert valid_rel_err(out["encoder_out"][0].transpose(0, 1).cpu(), yo, None if fmo is None else fmo.numpy()) < BF16_TOL
+    if cfg["extractor_mode"] == "layer_norm" and pm is None:
+        st = r.open_stream(B=src.size(0), max_seconds=2.0, max_new_samples=src.size(1))
+        ys = st.step(src.cuda(), 1)
+        assert ys.dtype == torch.float16 and valid_rel_err(ys.transpose(0, 1).cpu(), yo) < BF16_TOL
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("era", ["argparse", "hydra"])
+def test_from_checkpoint_forward_vs_oracle(era, dtype):
+    """Checkpoint ingestion end to end (rain/layers/unidirect_w2v2_encoder.py:541-555): a
+    composite CAAT-style checkpoint -- encoder under `encoder.w2v2_model.`, foreign decoder / joiner keys, pre-training
+    heads -- in both config eras (argparse-era: `args` Namespace without extractor_mode / pos_type, which the reference
+    then forces to layer_norm / sin; hydra-era: cfg.model dict), context overridden at load time, strict=False; the
+    forward of the model it builds against the oracle."""
+    import argparse
+    from oracle import synth
+    cfg = cases.tiny(layer_norm_first=True, conv_bias=True)
+    sd = synth.make_state_dict(cfg, 71)
+    full = {"encoder.w2v2_model." + k: v for k, v in sd.items()}
+    full["encoder.w2v2_model.mask_emb"] = torch.zeros(cfg["encoder_embed_dim"])
+    full["encoder.w2v2_model.quantizer.vars"] = torch.zeros(1, 8, 4)
+    full["decoder.embed_tokens.weight"] = torch.zeros(10, 16)
+    full["joiner.proj.weight"] = torch.zeros(4, 4)
+    if era == "argparse":
+        fields = {k: v for k, v in cfg.items() if k not in ("extractor_mode", "pos_type")}
+        ckpt = {"args": argparse.Namespace(**fields), "cfg": None, "model": full}
+    else:
+        ckpt = {"args": None, "cfg": {"model": dict(cfg)}, "model": full}
+    m, missing, unexpected = W.BlockWiseWav2Vec2Model.from_checkpoint(ckpt, main_context=8, right_context=4)
+    assert set(missing) <= {"mask_emb"} and not any(k.startswith(("decoder.", "joiner.")) for k in unexpected)
+    assert (m.encoder.main_context, m.encoder.right_context) == (8, 4)
+    assert m.args.extractor_mode == "layer_norm" and m.args.pos_type == "sin"
+    m = m.to("cuda", dtype).eval()
+    B, L = 2, 9000
+    wav = synth.make_waveform(B, L, 72)
+    pm = O.lengths_to_padding_mask(synth.make_lengths(B, L, 73))
+    wav = wav.masked_fill(pm, 0.0)
+    y = m(wav.cuda(), pm.cuda())["encoder_out"][0]
+    ocfg = dict(cfg, main_context=8, right_context=4)
+    yo, fmo = O.rain_forward(sd if dtype == torch.float32 else bf16_valued(sd), ocfg, wav, pm)
+    assert valid_rel_err(y.cpu(), yo, fmo.numpy(), time_first=True) < (FP32_TOL if dtype == torch.float32 else BF16_TOL)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_online_encoder_proj_on_library_gemm(dtype):
+    """OnlineW2V2TransformerEncoder.encoder_proj (unidirect_w2v2_encoder.py:559-562,590-594) in both modes: fp32 on the
+    CUDA-core product, bf16 on the tcgen05 kernel (M = T x B rows is a few hundred: the 2-CTA kernel with narrow tiles)."""
+    import argparse
+    from oracle import synth
+    cfg = cases.tiny(layer_norm_first=True, conv_bias=True)
+    sd = synth.make_state_dict(cfg, 31)
+    args = argparse.Namespace(main_context=16, right_context=8, encoder_embed_dim=96, use_linear_layer=True)
+    enc = W.OnlineW2V2TransformerEncoder(args, wav2vec_ckpt={"args": None, "cfg": {"model": dict(cfg)}, "model": sd})
+    enc = enc.to("cuda", dtype).eval()
+    B, L = 4, 40000
+    wav = synth.make_waveform(B, L, 32)
+    lens = synth.make_lengths(B, L, 33)
+    pm = O.lengths_to_padding_mask(lens)
+    wav = wav.masked_fill(pm, 0.0)
+    out = enc(wav.cuda().to(dtype), lens.cuda())
+    y, fm = out["encoder_out"][0], out["encoder_padding_mask"][0]
+    assert y.dtype == dtype and y.size(-1) == 96
+    wsd = sd if dtype == torch.float32 else bf16_valued(sd)
+    yo, fmo = O.rain_forward(wsd, cfg, wav.to(dtype).float(), pm)
+    pw, pb = enc.encoder_proj.weight.detach().float().cpu(), enc.encoder_proj.bias.detach().float().cpu()
+    yo = torch.nn.functional.linear(yo, pw, pb)
+    assert torch.equal(fm.cpu(), fmo)
+    assert valid_rel_err(y.detach().cpu(), yo, fmo.numpy(), time_first=True) < (FP32_TOL if dtype == torch.float32 else BF16_TOL)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two CUDA devices in one process")
+def test_two_devices_in_one_process():
+    """One process, a model replica on each of two devices (the library keeps its per-device caches -- SM count,
+    shared-memory opt-ins -- keyed by the current device): same bits on both."""
+    from oracle import synth
+    cfg = cases.tiny(layer_norm_first=True, conv_bias=True)
+    sd = synth.make_state_dict(cfg, 81)
+    wav = synth.make_waveform(2, 12000, 82)
+    ys = []
+    for dev in ("cuda:0", "cuda:1"):
+        m = W.Wav2VecSModel(cfg)
+        m.load_state_dict(sd, strict=False)
+        m = m.to(dev, torch.bfloat16).eval()
+        with torch.cuda.device(dev):
+            y, _ = m.extract_features(wav.to(dev), None)
+            torch.cuda.synchronize()
+        ys.append(y.cpu())
+    assert torch.equal(ys[0], ys[1])

@@ -187,3 +187,47 @@ def test_fused_step_kernel_equals_operator_chain(pre_ln, B, main, rc):
     assert tuple(y_fused.shape) == tuple(ref.shape)
     assert valid_rel_err(y_fused, y_chain) < 1e-2
     assert valid_rel_err(y_fused, ref) < TOL[torch.bfloat16] and valid_rel_err(y_chain, ref) < TOL[torch.bfloat16]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_stream_grows_past_its_initial_capacity(dtype):
+    """A stream opened for 0.5 s keeps going: its state moves into larger buffers (w2vs_stream_grow, K/V cache and
+    frame buffer copied on the device) instead of returning INVALID_VALUE -- the reference driver re-encodes prefixes
+    of any length up to --max-audio-positions.  Same frames as the offline forward."""
+    from oracle import synth
+    cfg = cases.tiny(layer_norm_first=True, conv_bias=True)
+    sd = synth.make_state_dict(cfg, 61)
+    L = 40000                                   # 2.5 s = 124 frames; the stream starts with room for 26
+    wav = synth.make_waveform(2, L, 62)
+    m = build(cfg, sd, dtype)
+    ref, _ = O.rain_forward(sd, cfg, wav, None, finished=True, is_infer=True)
+    st = m.open_stream(B=2, max_seconds=0.5, max_new_samples=6000)
+    cap0 = st.max_frames
+    src = wav.cuda()
+    outs, pos = [], 0
+    while pos < L:
+        n = min(5120, L - pos)
+        outs.append(st.step(src[:, pos:pos + n], EncoderStream.FINAL if pos + n >= L else EncoderStream.NONE))
+        pos += n
+    y = torch.cat(outs, 0).cpu()
+    assert st.max_frames > cap0 and tuple(y.shape) == tuple(ref.shape)
+    assert valid_rel_err(y, ref) < TOL[dtype]
+
+
+def test_incremental_forward_from_host_prefix_uploads_new_samples_only():
+    """The streaming driver keeps the growing prefix on the host (rain/simul/transducer_searcher.py:728-731 uploads all
+    of it at every step); with incremental_state the model takes the host tensor as is and moves only the samples it
+    has not seen: same result as feeding a device prefix."""
+    from oracle import synth
+    cfg = cases.tiny(layer_norm_first=True, conv_bias=True)
+    sd = synth.make_state_dict(cfg, 5)
+    wav = synth.make_waveform(1, 30000, 17)                      # host tensor
+    m = build(cfg, sd, torch.float32)
+    s_host, s_dev = {}, {}
+    for i, n in enumerate([7760, 12880, 13000, 23120, 30000]):
+        fin = n == 30000
+        y_h = m(wav[:, :n], None, s_host, fin, True)["encoder_out"][0]
+        y_d = m(wav[:, :n].cuda(), None, s_dev, fin, True)["encoder_out"][0]
+        assert y_h.is_cuda and torch.equal(y_h, y_d)
+    ref, _ = O.rain_forward(sd, cfg, wav, None, finished=True, is_infer=True)
+    assert valid_rel_err(y_h.cpu(), ref) < 1e-4

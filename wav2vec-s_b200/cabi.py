@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("W2VS_LIBRARY") or os.path.join(HERE, "lib", "libw2vs.
 W2VS_MAX_CONV = 8
 W2VS_ABI_VERSION = 2
 OK, INVALID_VALUE, UNSUPPORTED, WORKSPACE_TOO_SMALL, CUDA_ERROR = range(5)
-F32, BF16, I16 = 0, 1, 2
+F32, BF16, I16, F16 = 0, 1, 2, 3
 EXTRACTOR_DEFAULT, EXTRACTOR_LAYER_NORM = 0, 1
 POS_SIN, POS_CONV = 0, 1
 LAYOUT_BTD, LAYOUT_TBD = 0, 1
@@ -36,7 +36,7 @@ class Config(C.Structure):
         ("ffn_dim", C.c_int32), ("heads", C.c_int32), ("layers", C.c_int32),
         ("layer_norm_first", C.c_int32), ("pos_type", C.c_int32), ("conv_pos", C.c_int32),
         ("conv_pos_groups", C.c_int32), ("seq_multiple", C.c_int32), ("sin_rows", C.c_int32),
-        ("stream_step_impl", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("stream_step_impl", C.c_int32), ("io_dtype", C.c_int32), ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -73,6 +73,8 @@ PROTOTYPES = {
                                    C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "w2vs_stream_step": (C.c_int, [_P(Config), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                    C.c_int32, C.c_int32, C.c_void_p, C.c_int32, _P(C.c_int32), C.c_void_p,
+                                   C.c_size_t, C.c_void_p]),
+    "w2vs_stream_grow": (C.c_int, [_P(Config), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p,
                                    C.c_size_t, C.c_void_p]),
     "w2vs_stream_info": (C.c_int, [C.c_void_p, _P(C.c_int64), _P(C.c_int32), _P(C.c_int32)]),
     "w2vs_op_gemm": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,

@@ -384,7 +384,7 @@ w2vs_status_t w2vs_encode(const w2vs_config* cfg, const void* d_packed, const w2
   {
     FinalizeArgs f{};
     f.X = X; f.gamma = pre_ln ? at<float>(W, wl.enc_ln_w) : nullptr; f.beta = pre_ln ? at<float>(W, wl.enc_ln_b) : nullptr;
-    f.out = a->d_out; f.out_dtype = adt; f.B = B; f.T_out = T_out; f.in_rows_per_utt = g.M; f.D = D;
+    f.out = a->d_out; f.out_dtype = cfg->io_dtype == W2VS_F16 ? W2VS_F16 : adt; f.B = B; f.T_out = T_out; f.in_rows_per_utt = g.M; f.D = D;
     f.tbd = a->out_layout == W2VS_LAYOUT_TBD;
     W2VS_TRY(launch_finalize(f, st));
   }

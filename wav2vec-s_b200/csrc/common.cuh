@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include "../../include/w2vs.h"
@@ -101,6 +102,7 @@ __device__ __forceinline__ float to_f32(int16_t v) { return (float)v * (1.0f / 3
 template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
@@ -125,6 +127,11 @@ __device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
 __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
+  __half2 h[4] = {__floats2half2_rn(v[0], v[1]), __floats2half2_rn(v[2], v[3]), __floats2half2_rn(v[4], v[5]),
+                  __floats2half2_rn(v[6], v[7])};
+  *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(h);
 }
 __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
   uint4 u;

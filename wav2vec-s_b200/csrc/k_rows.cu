@@ -466,6 +466,7 @@ static w2vs_status_t finalize_dispatch(const FinalizeArgs& a, cudaStream_t st) {
 
 w2vs_status_t launch_finalize(const FinalizeArgs& a, cudaStream_t st) {
   if (a.B * a.T_out <= 0) return W2VS_OK;
+  if (a.out_dtype == W2VS_F16) return finalize_dispatch<__half>(a, st);     // fp16 models: w2vs_config.io_dtype
   return a.out_dtype == W2VS_F32 ? finalize_dispatch<float>(a, st) : finalize_dispatch<bf16>(a, st);
 }
 

@@ -83,6 +83,7 @@ w2vs_status_t validate_config(const w2vs_config* cfg) {
   W2VS_REQUIRE(cfg != nullptr, "cfg is NULL");
   W2VS_REQUIRE(cfg->abi_version == W2VS_ABI_VERSION, "abi_version mismatch");
   W2VS_REQUIRE(cfg->dtype == W2VS_F32 || cfg->dtype == W2VS_BF16, "dtype");
+  W2VS_REQUIRE(cfg->io_dtype == 0 || (cfg->io_dtype == W2VS_F16 && cfg->dtype == W2VS_BF16), "io_dtype (fp16 I/O runs on the bf16 path)");
   W2VS_REQUIRE(cfg->n_conv >= 1 && cfg->n_conv <= W2VS_MAX_CONV, "n_conv");
   for (int i = 0; i < cfg->n_conv; ++i) {
     W2VS_REQUIRE(cfg->conv_dim[i] >= 32 && cfg->conv_dim[i] % 32 == 0 && cfg->conv_dim[i] <= 1024,

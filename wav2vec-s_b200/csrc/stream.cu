@@ -146,7 +146,7 @@ w2vs_status_t block_step(const w2vs_config* cfg, const WeightLayout& wl, const S
   void* ctx = at<void>(d_ws, L.ctx);
   void* h = at<void>(d_ws, L.h);
   const bool pre_ln = cfg->layer_norm_first != 0;
-  if (cfg->stream_step_impl == 2 && stream_fused_applicable(cfg, B, ntok)) {
+  if (cfg->stream_step_impl == 2 && cfg->io_dtype == 0 && stream_fused_applicable(cfg, B, ntok)) {
     // opt-in (stream_step_impl = 2; bf16 models, at most 32 tokens per step): the whole step as one persistent
     // cooperative kernel
     StreamFusedArgs fa{};
@@ -210,7 +210,7 @@ w2vs_status_t block_step(const w2vs_config* cfg, const WeightLayout& wl, const S
   }
   FinalizeArgs f{};
   f.X = X; f.gamma = pre_ln ? at<float>(W, wl.enc_ln_w) : nullptr; f.beta = pre_ln ? at<float>(W, wl.enc_ln_b) : nullptr;
-  f.out = out_frames; f.out_dtype = adt; f.B = B; f.T_out = n_main; f.in_rows_per_utt = ntok; f.D = D; f.tbd = 1;
+  f.out = out_frames; f.out_dtype = cfg->io_dtype == W2VS_F16 ? W2VS_F16 : adt; f.B = B; f.T_out = n_main; f.in_rows_per_utt = ntok; f.D = D; f.tbd = 1;
   return launch_finalize(f, st);
 }
 
@@ -254,6 +254,56 @@ w2vs_status_t w2vs_stream_init(const w2vs_config* cfg, int32_t B, int32_t max_fr
   // (L.sync and L.fused_bar are adjacent allocations: one memset covers both)
   cudaError_t e = cudaMemsetAsync(at<uint8_t>(d_state, L.sync), 0, L.fused_bar + 64 - L.sync, (cudaStream_t)stream);
   if (e != cudaSuccess) { set_error("stream init memset: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
+  return W2VS_OK;
+}
+
+w2vs_status_t w2vs_stream_grow(const w2vs_config* cfg, const void* host_state_old, const void* d_state_old,
+                               int32_t new_max_frames, void* host_state_new, size_t host_bytes, void* d_state_new,
+                               size_t device_bytes, void* stream) {
+  W2VS_TRY(check_supported(cfg));
+  W2VS_REQUIRE(host_state_old && d_state_old && host_state_new && d_state_new, "NULL pointer");
+  const StreamHost* ho = reinterpret_cast<const StreamHost*>(host_state_old);
+  W2VS_REQUIRE(ho->magic == kMagic, "host_state was not initialised by w2vs_stream_init");
+  W2VS_REQUIRE(new_max_frames >= ho->max_frames, "new_max_frames must not shrink the stream");
+  W2VS_REQUIRE(cfg->sin_rows >= new_max_frames + 2, "sinusoidal table too short for new_max_frames (re-pack with more rows)");
+  StreamLayout Lo, Ln;
+  W2VS_TRY(make_stream_layout(cfg, ho->B, ho->max_frames, ho->max_new, ho->main_ctx, ho->rc, &Lo));
+  W2VS_TRY(make_stream_layout(cfg, ho->B, new_max_frames, ho->max_new, ho->main_ctx, ho->rc, &Ln));
+  if (host_bytes < sizeof(StreamHost) || device_bytes < Ln.dev_total) {
+    set_error("stream state buffers too small");
+    return W2VS_WORKSPACE_TOO_SMALL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = ho->B, D = cfg->embed_dim;
+  const size_t as = act_size(cfg);
+  auto fail = [](cudaError_t e) { set_error("stream grow copy: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; };
+  cudaError_t e;
+  // conv carries (their size depends on max_new_samples only): both halves of every double buffer
+  for (int i = 0; i < cfg->n_conv; ++i)
+    for (int h = 0; h < 2; ++h) {
+      const size_t row = i == 0 ? 4 : (size_t)cfg->conv_dim[i - 1] * as;
+      e = cudaMemcpyAsync(at<uint8_t>(d_state_new, Ln.in[i][h]), at<uint8_t>(d_state_old, Lo.in[i][h]),
+                          ((size_t)B * Lo.cap_in[i] + 128) * row, cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) return fail(e);
+    }
+  // projected frames [B][fcap][D] fp32 and the K/V cache [layers][B][kv_rows][2D]: row pitch per stream changes
+  if (ho->frames_total > 0) {
+    e = cudaMemcpy2DAsync(at<uint8_t>(d_state_new, Ln.fbuf), (size_t)Ln.fcap * D * 4, at<uint8_t>(d_state_old, Lo.fbuf),
+                          (size_t)Lo.fcap * D * 4, (size_t)ho->frames_total * D * 4, B, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return fail(e);
+  }
+  const size_t kv_row = (size_t)2 * D * as;
+  for (int l = 0; l < cfg->layers; ++l) {
+    e = cudaMemcpy2DAsync(at<uint8_t>(d_state_new, Ln.kv + (size_t)l * Ln.kv_layer_bytes), (size_t)Ln.kv_rows * kv_row,
+                          at<uint8_t>(d_state_old, Lo.kv + (size_t)l * Lo.kv_layer_bytes), (size_t)Lo.kv_rows * kv_row,
+                          (size_t)Lo.kv_rows * kv_row, B, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return fail(e);
+  }
+  e = cudaMemsetAsync(at<uint8_t>(d_state_new, Ln.sync), 0, Ln.fused_bar + 64 - Ln.sync, st);
+  if (e != cudaSuccess) return fail(e);
+  StreamHost hn = *ho;
+  hn.max_frames = new_max_frames;
+  *reinterpret_cast<StreamHost*>(host_state_new) = hn;
   return W2VS_OK;
 }
 

@@ -266,8 +266,8 @@ class Wav2VecSModel(nn.Module):
             ckpt = torch.load(ckpt, map_location="cpu", weights_only=False)
         if ckpt.get("args") is not None:
             margs = vars(ckpt["args"]).copy()
-            margs.setdefault("extractor_mode", "layer_norm")       # rain :545-547 for argparse-era checkpoints
-            margs.setdefault("pos_type", "sin")
+            margs["extractor_mode"] = "layer_norm"                 # rain :545-547 forces both for argparse-era
+            margs["pos_type"] = "sin"                              # checkpoints (they predate the two options)
         else:
             model_cfg = ckpt["cfg"]["model"]
             margs = dict(model_cfg) if isinstance(model_cfg, dict) else dict(vars(model_cfg))
@@ -322,15 +322,18 @@ class Wav2VecSModel(nn.Module):
         if p.device.type != "cuda":
             raise RuntimeError("wav2vec-S B200 path: parameters must live on a CUDA device "
                                "(no CPU fallback exists); call .cuda() first")
-        if p.dtype not in (torch.float32, torch.bfloat16):
-            raise RuntimeError(f"unsupported parameter dtype {p.dtype}: use float32 or bfloat16")
+        if p.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+            raise RuntimeError(f"unsupported parameter dtype {p.dtype}: use float32, bfloat16 or float16")
         return p.device, p.dtype
 
     def _c_config(self, dtype, sin_rows):
         a = self.args
         c = cabi.Config()
         c.abi_version = cabi.W2VS_ABI_VERSION
-        c.dtype = cabi.BF16 if dtype == torch.bfloat16 else cabi.F32
+        # fp16 models (`.half()`, what the reference trainer does under --fp16, trainer.py:86-90): fp16 in and out,
+        # arithmetic of the bf16 path (w2vs_config.io_dtype)
+        c.dtype = cabi.BF16 if dtype in (torch.bfloat16, torch.float16) else cabi.F32
+        c.io_dtype = cabi.F16 if dtype == torch.float16 else 0
         spec = self.feature_extractor.conv_spec
         if len(spec) > cabi.W2VS_MAX_CONV:
             raise ValueError("too many conv layers")
@@ -527,8 +530,32 @@ class EncoderStream:
         self.out_cap = 0
         self._out = None
 
+    def _grow(self, need_frames):
+        """The stream outgrew its K/V cache: move it into buffers twice as large (w2vs_stream_grow) instead of
+        failing -- the reference driver has no length limit other than --max-audio-positions."""
+        new_max = max(2 * self.max_frames, int(need_frames))
+        ccfg, self.packed = self.model._ensure_packed(new_max + 2)      # longer sinusoidal table if needed
+        new_cfg = cabi.Config.from_buffer_copy(ccfg)
+        new_cfg.stream_step_impl = self.ccfg.stream_step_impl
+        lib = cabi.lib()
+        hb, db, wb = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        cabi.check(lib.w2vs_stream_state_size(C.byref(new_cfg), self.B, new_max, self.max_new, self.main, self.rc,
+                                              C.byref(hb), C.byref(db), C.byref(wb)), "w2vs_stream_state_size")
+        host_new = C.create_string_buffer(hb.value)
+        d_new = torch.empty(db.value, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            cabi.check(lib.w2vs_stream_grow(C.byref(new_cfg), self.host_state, self.d_state.data_ptr(), new_max, host_new,
+                                            hb.value, d_new.data_ptr(), db.value, C.c_void_p(stream)), "w2vs_stream_grow")
+        # (the old device buffer is released in stream order by the caching allocator)
+        self.ccfg, self.host_state, self.d_state, self.max_frames = new_cfg, host_new, d_new, new_max
+        if self.ws.numel() < wb.value:
+            self.ws = torch.empty(wb.value, dtype=torch.uint8, device=self.device)
+
     def step(self, new_samples=None, flush=0):
         n_new = 0 if new_samples is None else int(new_samples.size(1))
+        if n_new and self.frames() + n_new // 320 + 2 > self.max_frames:
+            self._grow(self.frames() + n_new // 320 + 2)
         src_ptr, wdt = None, cabi.F32
         if n_new:
             if new_samples.size(0) != self.B:
@@ -627,7 +654,13 @@ class BlockWiseWav2Vec2Model(Wav2VecSModel):
             last = pos + n >= L
             flush = (EncoderStream.FINAL if finished else EncoderStream.PEEK) if last else EncoderStream.NONE
             before = stream.final_frames()
-            out = stream.step(source[:, pos:pos + n] if n else None, flush)
+            chunk = source[:, pos:pos + n] if n else None
+            if chunk is not None and chunk.device != stream.device:
+                # host-resident prefix (what the SimulEval agent holds, rain/simul/transducer_searcher.py:728-731, where
+                # the reference uploads the WHOLE prefix at every decision step): only the samples the device has
+                # not seen cross the bus; conv carries, projected frames and K/V stay resident in the stream state
+                chunk = chunk.to(stream.device, non_blocking=True)
+            out = stream.step(chunk, flush)
             n_final = stream.final_frames() - before
             if n_final:
                 hist.append(out[:n_final])   # frames of whole blocks never change again
@@ -693,9 +726,11 @@ class OnlineW2V2TransformerEncoder(nn.Module):
             from . import ops
             x = output["encoder_out"][0]
             T_, B_, D_ = x.shape
-            w = self.encoder_proj.weight.detach().to(x.dtype).contiguous()
-            y = ops.gemm(x.reshape(T_ * B_, D_), w, self.encoder_proj.bias.detach().float().contiguous(),
-                         out_dtype=x.dtype) if T_ * B_ > 0 else x.new_zeros((0, w.size(0)))
+            # fp16 models run on the bf16 operand path (w2vs_config.io_dtype): so does this product
+            gdt = torch.bfloat16 if x.dtype == torch.float16 else x.dtype
+            w = self.encoder_proj.weight.detach().to(gdt).contiguous()
+            y = ops.gemm(x.reshape(T_ * B_, D_).to(gdt), w, self.encoder_proj.bias.detach().float().contiguous(),
+                         out_dtype=gdt).to(x.dtype) if T_ * B_ > 0 else x.new_zeros((0, w.size(0)))
             output = dict(output)
             output["encoder_out"] = [y.view(T_, B_, w.size(0))]
         return output

@@ -55,14 +55,19 @@ def gather_outputs(x: torch.Tensor, n_frames: torch.Tensor, dst: Optional[int] =
     dist.all_gather(shapes, shape)
     Bm = int(max(int(s[0]) for s in shapes))
     Tm = int(max(int(s[1]) for s in shapes))
-    pad = x.new_zeros((Bm, Tm, x.size(2)))
-    pad[: x.size(0), : x.size(1)] = x
+    if x.size(0) == Bm and x.size(1) == Tm and x.is_contiguous():
+        pad = x                                       # equal shards (the usual case): no staging copy
+    else:
+        pad = x.new_zeros((Bm, Tm, x.size(2)))
+        pad[: x.size(0), : x.size(1)] = x
     nf = torch.zeros(Bm, dtype=torch.int64, device=x.device)
     nf[: x.size(0)] = n_frames.to(torch.int64)
-    xs = [torch.empty_like(pad) for _ in range(world)]
-    nfs = [torch.empty_like(nf) for _ in range(world)]
-    dist.all_gather(xs, pad)
-    dist.all_gather(nfs, nf)
+    # one collective per tensor into a single [world, ...] buffer (NCCL all-gather over NVLink on GPUs)
+    xs = x.new_empty((world * Bm,) + tuple(pad.shape[1:]))
+    nfs = nf.new_empty((world * Bm,))
+    dist.all_gather_into_tensor(xs, pad)
+    dist.all_gather_into_tensor(nfs, nf)
+    xs, nfs = xs.view((world, Bm) + tuple(pad.shape[1:])), nfs.view(world, Bm)
     if dst is not None and rank != dst:
         return None
     outs, counts = [], []
