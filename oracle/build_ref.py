@@ -3,7 +3,7 @@
     python oracle/build_ref.py          (build container only: needs /root/reference)
 
 Byte-compiles the UNMODIFIED reference source files of the hot path, where they lie under /root/reference, into
-``oracle/_ref/`` (``*.pyc`` only -- no reference source text is copied into this repository; ``oracle/_ref/`` is
+``oracle/_ref/`` (marshalled code objects, ``*.code`` -- no reference source text is copied into this repository; ``oracle/_ref/`` is
 git-ignored like any other build output but is not gpurun-ignored, so it ships with the snapshot exactly like the
 ``.so`` this repository builds).  ``oracle/ref_shim.py`` loads the modules from /root/reference when that exists and
 from these compiled files otherwise, which lets
@@ -15,8 +15,8 @@ from these compiled files otherwise, which lets
 The file list is the one SURVEY.md section 8(c) names (and ``ref_shim`` documents); the interpreter on the box is
 the same image's Python, which is what the bytecode magic number requires (checked at load time).
 """
+import marshal
 import os
-import py_compile
 import sys
 
 REF_ROOT = os.environ.get("W2VS_REFERENCE_ROOT", "/root/reference")
@@ -38,11 +38,14 @@ def build(verbose=True):
     n = 0
     for rel in FILES:
         src = os.path.join(REF_ROOT, rel)
-        dst = os.path.join(OUT, rel + "c")
+        dst = os.path.join(OUT, rel[:-3] + ".code")
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         if not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
-            # dfile: the path tracebacks show (the reference's own file:line, what the oracle cites)
-            py_compile.compile(src, cfile=dst, dfile=os.path.join("/root/reference", rel), doraise=True, optimize=0)
+            # the code object keeps the reference's own path, so tracebacks show the file:line the oracle cites
+            with open(src, "rb") as f:
+                code = compile(f.read(), os.path.join("/root/reference", rel), "exec", dont_inherit=True, optimize=0)
+            with open(dst, "wb") as f:
+                f.write(marshal.dumps(code))
             n += 1
     with open(os.path.join(OUT, "PYTHON_VERSION"), "w") as f:
         f.write(sys.version.split()[0] + "\n")

@@ -4,7 +4,7 @@ Executes the reference's own hot-path files under a stub ``fairseq`` namespace (
 fairseq`` itself fails here: no omegaconf/hydra, py3.12).  No reference source is copied into
 this repository: in the build container the files are loaded where they lie under
 ``/root/reference``; on the GPU box (where that path does not exist) the same modules are loaded
-from ``oracle/_ref/`` -- bytecode of the unmodified files, produced by ``oracle/build_ref.py``,
+from ``oracle/_ref/`` -- marshalled code objects of the unmodified files, produced by ``oracle/build_ref.py``,
 git-ignored, shipped with the snapshot like a built ``.so``.  Used for:
 
   * ``tests/golden/make_golden.py``  -- generate golden input/output vectors,
@@ -49,7 +49,12 @@ def source_available() -> bool:
 
 
 def compiled_available() -> bool:
-    return os.path.isfile(os.path.join(PYC_ROOT, _KEY + "c"))
+    if not os.path.isfile(os.path.join(PYC_ROOT, _KEY[:-3] + ".code")):
+        return False
+    try:      # code objects are only valid for the interpreter version that made them
+        return open(os.path.join(PYC_ROOT, "PYTHON_VERSION")).read().strip() == sys.version.split()[0]
+    except OSError:
+        return False
 
 
 def available() -> bool:
@@ -62,7 +67,7 @@ def kind() -> str:
 
 
 _ROOT = REF_ROOT if source_available() else PYC_ROOT
-_EXT = ".py" if source_available() else ".pyc"
+_EXT = ".py" if source_available() else ".code"
 _FS = os.path.join(_ROOT, "fairseq", "fairseq")
 
 
@@ -75,11 +80,15 @@ def _mod(name, is_pkg=False):
 
 
 def _load(name, path):
-    if _EXT == ".pyc":
-        path = path + "c"
-        spec = importlib.util.spec_from_file_location(name, path, loader=importlib.machinery.SourcelessFileLoader(name, path))
-    else:
-        spec = importlib.util.spec_from_file_location(name, path)
+    if _EXT == ".code":
+        import marshal
+        m = types.ModuleType(name)
+        m.__file__ = path[:-3] + ".code"
+        sys.modules[name] = m
+        with open(m.__file__, "rb") as f:
+            exec(marshal.loads(f.read()), m.__dict__)
+        return m
+    spec = importlib.util.spec_from_file_location(name, path)
     m = importlib.util.module_from_spec(spec)
     sys.modules[name] = m
     spec.loader.exec_module(m)

@@ -150,6 +150,7 @@ struct TileSeq {   // key tiles visible to one query tile
 struct Shape {
   int T2, M, main_ctx, rc, rcd, nb, D, H, B, n_main_tiles, n_tiles;
   int HB, n_vcta;                       // H*B; pipelines in the grid (work-list stride)
+  int flag_fold;                        // log2 of the 128-token padding-flag blocks folded into one mask bit
   int G, S, g_div, g_mod;               // (b,h) pairs per block, items per block (G * n_tiles), stride / S, stride % S
   uint32_t magic_main, magic_rcd, magic_H, magic_G;
 };
@@ -410,23 +411,27 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // (2 per lane).
     const int pad_stride = (sh.M + 127) >> 7;
     const bool flags_usable = pad_blk != nullptr;
-    int fs = 0;
-    while (((pad_stride + (1 << fs) - 1) >> fs) > 32) ++fs;
-    const int flag_shift = 7 + fs;
+    const int fs = sh.flag_fold;                      // host: smallest fs with ceil(pad_stride / 2^fs) <= 32
+    const int flag_shift = 7 + fs, flag_shift_it = 1 + fs;     // token -> mask bit; 64-key main tile index -> mask bit
     auto fetch_flags = [&](int b_) -> uint32_t {      // this lane's flags of utterance b_ (raw loads, consumed later)
       uint32_t v = 0;
       if (flags_usable) {
-        const int j0 = lane << fs, j1 = min(j0 + (1 << fs), pad_stride);
-        for (int j = j0; j < j1; ++j) {
-          uint32_t u;
-          asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(u) : "l"(pad_blk + (size_t)b_ * pad_stride + j));
-          v |= u;
+        if (fs == 0) {
+          if (lane < pad_stride) asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(pad_blk + (size_t)b_ * pad_stride + lane));
+        } else {
+          const int j0 = lane << fs, j1 = min(j0 + (1 << fs), pad_stride);
+          for (int j = j0; j < j1; ++j) {
+            uint32_t u;
+            asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(u) : "l"(pad_blk + (size_t)b_ * pad_stride + j));
+            v |= u;
+          }
         }
       }
       return v;
     };
-    // flag of the mask bit that covers token `tok` (callers without flags: always "may have padding")
-    auto flagged = [&](uint32_t mask, int tok) -> bool { return !flags_usable || ((mask >> (tok >> flag_shift)) & 1u) != 0; };
+    // mask bit that covers token `tok` (callers without flags: the mask is all ones, "may have padding"; the fold
+    // keeps every bit index below 32)
+    auto flagged = [&](uint32_t mask, int tok) -> bool { return ((mask >> (tok >> flag_shift)) & 1u) != 0; };
     Walker wk, wnext;
     wk.init(sh, vcta);
     wnext = wk;
@@ -459,7 +464,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         int lo = 0;
         uint32_t span = KT;
         bool all_vis[2] = {true, true}, none_vis[2] = {false, false};
-        if (!(it < n_fullvis && !flagged(flag_mask, it * KT))) {
+        if (!(it < n_fullvis && ((flag_mask >> (it >> flag_shift_it)) & 1u) == 0)) {
           int k0, cnt; bool s1;
           im.ts.get(it, k0, cnt, s1);
           if (flagged(flag_mask, k0) || flagged(flag_mask, k0 + cnt - 1)) {
@@ -713,6 +718,8 @@ w2vs_status_t launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
   const int grid = (int)(n_items < max_ctas ? n_items : max_ctas);
   sh.HB = a.heads * a.B;
   sh.n_vcta = grid;
+  sh.flag_fold = 0;
+  while (((((sh.M + 127) >> 7) + (1 << sh.flag_fold) - 1) >> sh.flag_fold) > 32) ++sh.flag_fold;
   // block of G pairs: the largest divisor of H*B that is at most 32 (the heads alone give 1, 2, 4, 8, 16)
   sh.G = 1;
   for (int d = 2; d <= 32; ++d) if (sh.HB % d == 0) sh.G = d;
