@@ -135,7 +135,7 @@ struct FusedArgs {
 //   lnp    LayerNorm parameters of the two LN phases: 2 x [gamma D | beta D] fp32 (bulk copies, a layer ahead)
 //   sched  this CTA's slab list of one layer (byte offsets from the layer's weights), stats [32][2], barriers, flags
 struct Smem { uint32_t ring, abuf, part, lnp, sched, stats, bars, flags; int stage_bytes; };
-// barriers: full[12] @0, empty[12] @96, A operand @192, LayerNorm parameters [2] @200
+// barriers: full[12] @0, empty[12] @96, A operand buffers @192 / @216, LayerNorm parameters [2] @200 / @208
 
 __device__ __forceinline__ const float* lw(const FusedArgs& a, int layer, unsigned long long off) {
   return reinterpret_cast<const float*>(a.W + (size_t)layer * a.layer_stride + off);
@@ -172,8 +172,9 @@ __device__ __noinline__ bool grid_barrier(const FusedArgs& a, const Smem& sm, ui
                                              Prod& pr, unsigned long long target, volatile int* s_abort) {
   named_bar(1, 32 * FS_CW);
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(a.bar, 1ull);
+    // release at gpu scope: the CTA's writes of this phase (ordered before this thread by the bar.sync above) are
+    // visible to whoever observes the arrival
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(a.bar), "l"(1ull) : "memory");
     pump(a, sm, sb, smem_gen, pr, FS_MAX_STAGES);      // every stage consumed in the phase that just ended is free now
     unsigned long long v;
     unsigned spins = 0;
@@ -272,7 +273,7 @@ enum { EPI_QKV = 0, EPI_RESID = 1, EPI_GELU = 2 };
 template <int MT>
 __device__ __forceinline__ bool gemm_phase(const FusedArgs& a, const Smem& sm, uint32_t sb, uint8_t* smem_gen, Ring& rs,
                                            uint32_t& aphase, int layer, int N, int K, const bf16* a_glob, int epi,
-                                           const float* bias, const float* res_lnp, int warp, int lane) {
+                                           const float* bias, const float* res_lnp, int a_bufs, int warp, int lane) {
   const int G = gridDim.x, cta = blockIdx.x;
   const int D = a.D, KC = D, Mt = a.B * a.ntok;
   const int kw = KC / FS_CW, nsteps = kw >> 4, nch = K / KC;
@@ -281,10 +282,21 @@ __device__ __forceinline__ bool gemm_phase(const FusedArgs& a, const Smem& sm, u
   const int n_units = units_total > cta ? (units_total - 1 - cta) / G + 1 : 0;
   float* part = reinterpret_cast<float*>(smem_gen + sm.part);
   const float* stats = reinterpret_cast<const float*>(smem_gen + sm.stats);
-  const uint32_t abar = sb + sm.bars + 192;
+  const uint32_t abar = sb + sm.bars + 192;        // A operand arrival: buffer 0; buffer 1 at + 24
+  const uint32_t a_chunk_bytes = (uint32_t)Mt * KC * 2;
+  const int tid = threadIdx.x;
+  if (tid == 0 && a_glob != nullptr && n_units > 0) {
+    // the A operand comes from global memory (attention context / FFN hidden): bulk copies into abuf -- every warp
+    // of this CTA is past its last use of that memory (they all arrived at the grid barrier before this phase).
+    // Long-K product: the first a_bufs chunks now, chunk j + a_bufs once every warp holds chunk j in registers.
+    fence_async_smem();
+    for (int j = 0; j < a_bufs && j < nch; ++j) {
+      mbar_expect_tx(abar + 24 * j, a_chunk_bytes);
+      bulk_g2s(sb + sm.abuf + j * a_chunk_bytes, a_glob + (size_t)j * FS_ROWS * KC, a_chunk_bytes, abar + 24 * j);
+    }
+  }
 
   // the epilogue's residual and bias values do not depend on the product: request them first
-  const int tid = threadIdx.x;
   const bool epi_thread = tid < n_units * Mt;
   const int ei = epi_thread ? tid / Mt : 0, er = epi_thread ? tid - ei * Mt : 0;
   const int en0 = (cta + ei * G) * 8;
@@ -310,8 +322,10 @@ __device__ __forceinline__ bool gemm_phase(const FusedArgs& a, const Smem& sm, u
     for (int j = 0; j < nch; ++j) {
       if (need_a) {
         need_a = nch > 1;      // K == D: the same fragments serve every unit
-        if (a_glob != nullptr) { ok = wait_bar(abar, aphase) && ok; aphase ^= 1; }
-        const uint32_t base = sb + sm.abuf + (uint32_t)g * (2 * D) + (uint32_t)(warp * kw + 4 * q) * 2;
+        const int ab = a_glob != nullptr && a_bufs == 2 ? (j & 1) : 0;      // which A buffer holds chunk j
+        if (a_glob != nullptr) { ok = wait_bar(abar + 24 * ab, (aphase >> ab) & 1u) && ok; aphase ^= 1u << ab; }
+        const uint32_t base = sb + sm.abuf + (a_glob != nullptr ? ab * a_chunk_bytes : 0u) + (uint32_t)g * (2 * D) +
+                              (uint32_t)(warp * kw + 4 * q) * 2;
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -320,11 +334,11 @@ __device__ __forceinline__ bool gemm_phase(const FusedArgs& a, const Smem& sm, u
             for (int s = 0; s < 8; ++s)
               if (s < nsteps) af[mt][hf][s] = lds64(base + (uint32_t)(mt * 16 + 8 * hf) * (2 * D) + s * 32);
         if (nch > 1) {
-          // every warp holds chunk j in registers: thread 0 may overwrite abuf with chunk j + 1
+          // every warp holds chunk j in registers: thread 0 may refill that buffer with chunk j + a_bufs
           named_bar(1, 32 * FS_CW);
-          if (tid == 0 && j + 1 < nch) {
-            mbar_expect_tx(abar, (uint32_t)Mt * KC * 2);
-            bulk_g2s(sb + sm.abuf, a_glob + (size_t)(j + 1) * FS_ROWS * KC, (uint32_t)Mt * KC * 2, abar);
+          if (tid == 0 && j + a_bufs < nch) {
+            mbar_expect_tx(abar + 24 * ab, a_chunk_bytes);
+            bulk_g2s(sb + sm.abuf + ab * a_chunk_bytes, a_glob + (size_t)(j + a_bufs) * FS_ROWS * KC, a_chunk_bytes, abar + 24 * ab);
           }
         }
       }
@@ -352,12 +366,6 @@ __device__ __forceinline__ bool gemm_phase(const FusedArgs& a, const Smem& sm, u
       *reinterpret_cast<float2*>(p0) = make_float2(acc[mt][0], acc[mt][1]);
       *reinterpret_cast<float2*>(p0 + 64) = make_float2(acc[mt][2], acc[mt][3]);
     }
-  }
-  if (n_units == 0 && a_glob != nullptr) {
-    // no unit in this product: still consume the A operand barrier phases (one per chunk)
-    for (int j = 0; j < nch; ++j) { ok = wait_bar(abar, aphase) && ok; aphase ^= 1;
-      if (nch > 1) { named_bar(1, 32 * FS_CW);
-        if (tid == 0 && j + 1 < nch) { mbar_expect_tx(abar, (uint32_t)Mt * KC * 2); bulk_g2s(sb + sm.abuf, a_glob + (size_t)(j + 1) * FS_ROWS * KC, (uint32_t)Mt * KC * 2, abar); } } }
   }
   named_bar(1, 32 * FS_CW);
   // ---- fixed-order reduction + epilogue: one thread per (unit, row), 8 consecutive columns
@@ -426,7 +434,6 @@ __device__ __forceinline__ void attention_phase(const FusedArgs& a, const Smem& 
   bf16* Qs = reinterpret_cast<bf16*>(smem_gen + sm.abuf + (size_t)gi * FS_ATT_GROUP_BYTES);
   bf16* Ks = Qs + 4096;          // [2][64 x 64]
   bf16* Vs = Ks + 2 * 4096;      // [2][64 x 64]
-  int* s_last = reinterpret_cast<int*>(smem_gen + sm.flags) + 4 + gi;
   const bf16* kv_l = a.kv + (size_t)layer * a.kv_layer_elems;
   const float sl2 = a.scale_log2;
   const bool active = mt * 16 < ntok;      // this warp's 16 query rows exist
@@ -582,60 +589,73 @@ __device__ __forceinline__ void attention_phase(const FusedArgs& a, const Smem& 
       }
     }
     if (S > 1) {
+      // every split of this (stream, head) has to be in global memory before anyone folds them: a head-level
+      // barrier on a counter that only grows inside a launch (target = splits x layers so far), then the S groups
+      // share the fold -- group `sp` takes the (row, 8-column chunk) pairs congruent to sp.  (Letting the group that
+      // arrives last fold all pairs alone put 5 us on the critical path of every layer.)  The groups of a head sit
+      // on consecutive work-item slots, all of them running, so the wait cannot deadlock.
       named_bar(2 + gi, 128);
-      if (gtid == 0) *s_last = atomicAdd(a.counters + bh, 1u) == (unsigned)S - 1;
-      named_bar(2 + gi, 128);
-      if (*s_last) {
-        __threadfence();
-        const float* P0 = a.partials + (size_t)bh * S * (size_t)(FS_ROWS * 66);
-        // every thread owns (row, 8-column chunk) pairs; the splits are folded in batches of 8 whose loads are all
-        // issued before the first one is used (a serial loop over 16 splits was 30 dependent L2 round trips)
-        for (int idx = gtid; idx < ntok * 8; idx += 128) {
-          const int row = idx >> 3, chunk = idx & 7;
-          float mrun = -INFINITY, lsum = 0.f;
-          float accv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-          for (int s0 = 0; s0 < S; s0 += 8) {
-            float2 ml[8];
-            float4 ov[8][2];
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              if (s0 + k < S) {
-                const float* pr2 = P0 + (size_t)(s0 + k) * FS_ROWS * 66 + row * 66;       // 8-byte aligned rows
-                ml[k] = __ldcg(reinterpret_cast<const float2*>(pr2 + 64));
-                const float2 x0 = __ldcg(reinterpret_cast<const float2*>(pr2 + chunk * 8)), x1 = __ldcg(reinterpret_cast<const float2*>(pr2 + chunk * 8 + 2));
-                const float2 x2 = __ldcg(reinterpret_cast<const float2*>(pr2 + chunk * 8 + 4)), x3 = __ldcg(reinterpret_cast<const float2*>(pr2 + chunk * 8 + 6));
-                ov[k][0] = make_float4(x0.x, x0.y, x1.x, x1.y);
-                ov[k][1] = make_float4(x2.x, x2.y, x3.x, x3.y);
-              }
-            float mb = mrun;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) if (s0 + k < S) mb = fmaxf(mb, ml[k].x);
-            if (mb == -INFINITY) continue;
-            const float resc = mrun == -INFINITY ? 0.f : exp2f((mrun - mb) * sl2);
-            lsum *= resc;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) accv[e] *= resc;
-            mrun = mb;
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              if (s0 + k < S && ml[k].x != -INFINITY) {
-                const float w = exp2f((ml[k].x - mb) * sl2);
-                lsum = fmaf(ml[k].y, w, lsum);
-                accv[0] = fmaf(ov[k][0].x, w, accv[0]); accv[1] = fmaf(ov[k][0].y, w, accv[1]);
-                accv[2] = fmaf(ov[k][0].z, w, accv[2]); accv[3] = fmaf(ov[k][0].w, w, accv[3]);
-                accv[4] = fmaf(ov[k][1].x, w, accv[4]); accv[5] = fmaf(ov[k][1].y, w, accv[5]);
-                accv[6] = fmaf(ov[k][1].z, w, accv[6]); accv[7] = fmaf(ov[k][1].w, w, accv[7]);
-              }
+      if (gtid == 0) {
+        atomicAdd(a.counters + bh, 1u);
+        const unsigned target = (unsigned)S * (unsigned)(layer + 1);
+        unsigned v, spins = 0;
+        unsigned long long t0 = 0;
+        for (;;) {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.counters + bh) : "memory");
+          if (v >= target) break;
+          if ((++spins & 0x3ff) == 0) {
+            const unsigned long long now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > FS_TIMEOUT_NS) { atomicExch(&g_fused_fault, 1); break; }
           }
-          const float inv = lsum > 0.f ? 1.0f / lsum : 0.f;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) accv[e] *= inv;
-          store8(a.ctx + ((size_t)b * ntok + row) * D + (size_t)h * 64 + chunk * 8, accv);
         }
-        if (gtid == 0) a.counters[bh] = 0u;      // the next use is a grid barrier away
       }
-      named_bar(2 + gi, 128);     // s_last and the scratch are reused by the group's next item
+      named_bar(2 + gi, 128);
+      const float* P0 = a.partials + (size_t)bh * S * (size_t)(FS_ROWS * 66);
+      for (int idx = sp + S * gtid; idx < ntok * 8; idx += S * 128) {
+        const int row = idx >> 3, chunk = idx & 7;
+        float mrun = -INFINITY, lsum = 0.f;
+        float accv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int s0 = 0; s0 < S; s0 += 8) {       // batches of 8 splits: all loads of a batch in flight together
+          float2 ml[8];
+          float4 ov[8][2];
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (s0 + k < S) {
+              const float* pr2 = P0 + (size_t)(s0 + k) * FS_ROWS * 66 + row * 66;       // 8-byte aligned rows
+              ml[k] = __ldcg(reinterpret_cast<const float2*>(pr2 + 64));
+              const float2 x0 = __ldcg(reinterpret_cast<const float2*>(pr2 + chunk * 8)), x1 = __ldcg(reinterpret_cast<const float2*>(pr2 + chunk * 8 + 2));
+              const float2 x2 = __ldcg(reinterpret_cast<const float2*>(pr2 + chunk * 8 + 4)), x3 = __ldcg(reinterpret_cast<const float2*>(pr2 + chunk * 8 + 6));
+              ov[k][0] = make_float4(x0.x, x0.y, x1.x, x1.y);
+              ov[k][1] = make_float4(x2.x, x2.y, x3.x, x3.y);
+            }
+          float mb = mrun;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) if (s0 + k < S) mb = fmaxf(mb, ml[k].x);
+          if (mb == -INFINITY) continue;
+          const float resc = mrun == -INFINITY ? 0.f : exp2f((mrun - mb) * sl2);
+          lsum *= resc;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) accv[e] *= resc;
+          mrun = mb;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (s0 + k < S && ml[k].x != -INFINITY) {
+              const float w = exp2f((ml[k].x - mb) * sl2);
+              lsum = fmaf(ml[k].y, w, lsum);
+              accv[0] = fmaf(ov[k][0].x, w, accv[0]); accv[1] = fmaf(ov[k][0].y, w, accv[1]);
+              accv[2] = fmaf(ov[k][0].z, w, accv[2]); accv[3] = fmaf(ov[k][0].w, w, accv[3]);
+              accv[4] = fmaf(ov[k][1].x, w, accv[4]); accv[5] = fmaf(ov[k][1].y, w, accv[5]);
+              accv[6] = fmaf(ov[k][1].z, w, accv[6]); accv[7] = fmaf(ov[k][1].w, w, accv[7]);
+            }
+        }
+        const float inv = lsum > 0.f ? 1.0f / lsum : 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) accv[e] *= inv;
+        store8(a.ctx + ((size_t)b * ntok + row) * D + (size_t)h * 64 + chunk * 8, accv);
+      }
+      named_bar(2 + gi, 128);     // the scratch tiles are reused by the group's next item
     }
   }
 }
@@ -657,6 +677,7 @@ stream_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__
   if (threadIdx.x == 0) {
     for (int i = 0; i < a.n_stages; ++i) { mbar_init(sb + sm.bars + 8 * i, 1); mbar_init(sb + sm.bars + 96 + 8 * i, FS_CW); }
     mbar_init(sb + sm.bars + 192, 1);
+    mbar_init(sb + sm.bars + 216, 1);
     mbar_init(lnbar, 1);
     mbar_init(lnbar + 8, 1);
     *s_abort = 0;
@@ -686,6 +707,9 @@ stream_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__
   unsigned long long nbar = 0;
   Ring rs{0, 0};
   uint32_t aphase = 0;
+  // two A-operand buffers for the long-K product when two chunks of Mt rows fit into abuf + part (part is written
+  // only after the last chunk has been read)
+  const int a_bufs = 2u * Mt * D * 2u <= sm.lnp - sm.abuf ? 2 : 1;
   bool ok = true;
   const int tr = threadIdx.x == 0 ? (cta == 0 ? 0 : (cta == G - 1 ? 1 : -1)) : -1;
 #define FS_TRACE(l_, ev_) do { if (tr >= 0 && (l_) < 64) g_fused_trace[tr][l_][ev_] = global_ns(); } while (0)
@@ -723,7 +747,7 @@ stream_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__
       const int epi = ph == 0 ? EPI_QKV : (ph == 2 ? EPI_GELU : EPI_RESID);
       const float* bias = lw(a, l, ph == 0 ? a.bqkv : (ph == 1 ? a.bo : (ph == 2 ? a.b1 : a.b2)));
       ok = gemm_phase<MT>(a, sm, sb, smem_gen, rs, aphase, l, N, K, ag, epi, bias, ((ph & 1) && !a.pre_ln) ? lnp : nullptr,
-                          warp, lane) && ok;
+                          a_bufs, warp, lane) && ok;
       FS_TRACE(l, ph == 0 ? 1 : 3 + 2 * ph);
       if (threadIdx.x == 0 && (ph & 1) && l + 1 < a.layers) {
         // this LayerNorm-parameter buffer is free now: request the next layer's set.  Pre-LN: ln1 / ln2 of layer
@@ -742,13 +766,6 @@ stream_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__
         FS_TRACE(l, 3);
         ok = grid_barrier(a, sm, sb, smem_gen, pr, ++nbar * G, s_abort);
         FS_TRACE(l, 4);
-      }
-      if (threadIdx.x == 0 && ok && (ph == 0 || ph == 2)) {
-        // the next product reads its A operand from global memory (attention context / FFN hidden): one bulk
-        // copy into abuf (every warp of this CTA is past its last use: they all arrived at the barrier above)
-        fence_async_smem();
-        mbar_expect_tx(sb + sm.bars + 192, (uint32_t)Mt * D * 2);
-        bulk_g2s(sb + sm.abuf, ph == 0 ? a.ctx : a.h, (uint32_t)Mt * D * 2, sb + sm.bars + 192);
       }
     }
   }
@@ -784,6 +801,7 @@ stream_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__
     if (atomicAdd(a.bar + 1, 1ull) == (unsigned long long)G - 1) {
       a.bar[0] = 0ull;
       a.bar[1] = 0ull;
+      for (int i = 0; i < a.B * a.H; ++i) a.counters[i] = 0u;      // head-level barriers of the attention phase
       __threadfence();
     }
   }
