@@ -6,7 +6,9 @@ second, wav2vec-S large, bf16).
 
 A "step" is one pass of the hot path (`extract_features`) over one batch of synthetic waveforms.
 Workloads (BASELINE.json configs): large_64x20s (default; configs[2], the largest single-GPU
-config of the model the metric is quoted on), base_32x15s (configs[1]), large_64x30s (configs[4]).
+config of the model the metric is quoted on), base_1x10s (configs[0], with --dtype fp32), base_32x15s
+(configs[1]), stream_large_b1 / _b16 (configs[3]; also probed by the default run), large_64x30s (configs[4];
+at N > 1 the default run adds it as `extra_points`).
 With N > 1 (torchrun, one rank per GPU) every rank encodes its own batch -- utterances are
 independent, no collective sits in the data path ("scaling": "weak"); NCCL only carries the
 barrier and the max-over-ranks timing.
@@ -32,6 +34,7 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (model, B per GPU, seconds)
     "large_64x20s": ("large", 64, 20),
+    "base_1x10s": ("base", 1, 10),                     # configs[0] (run with --dtype fp32: the reference's CPU-runnable case)
     "base_32x15s": ("base", 32, 15),
     "base_posconv_32x15s": ("base_posconv", 32, 15),   # same model with the wav2vec 2.0 convolutional positions
     "large_64x30s": ("large", 64, 30),
@@ -353,6 +356,22 @@ def incremental_probe(model, cfg, dev, B=1, seconds=30):
                          "traffic": None, "algorithmic_bytes": wbytes + kvbytes, "peak_source": pk_kind}}
 
 
+def gemm_bytes_per_utt(cfg, L):
+    """Algorithmic HBM bytes of the GEMM launches of one utterance (bf16 model), weights not included: conv inputs and
+    outputs, QKV / FFN operands and results, the fp32 residual stream read and written by out_proj and fc2."""
+    spec = conv_spec(cfg)
+    t, lens = L, []
+    for (c, k, s_) in spec:
+        t = (t - k) // s_ + 1
+        lens.append(t)
+    fl = flops_per_utt(cfg, L)
+    T, M, D, F, Ly = fl["T"], fl["M"], cfg["encoder_embed_dim"], cfg["encoder_ffn_embed_dim"], cfg["encoder_layers"]
+    conv = sum(2 * spec[i - 1][0] * lens[i - 1] + 2 * spec[i][0] * lens[i] for i in range(1, len(spec)))
+    proj = 2 * spec[-1][0] * T + 4 * D * T
+    layer = (2 * M * D + 2 * M * 3 * D) + (2 * M * D + 8 * M * D) + (2 * M * D + 2 * M * F) + (2 * M * F + 8 * M * D)
+    return conv + proj + Ly * layer
+
+
 def rows_bytes_per_utt(cfg, L):
     """Algorithmic HBM bytes of the stand-alone row passes of one utterance (bf16 model): conv LayerNorm + GELU passes
     (read + write bf16), feature LayerNorm, token embedding, two LayerNorms per transformer layer (read fp32, write
@@ -631,8 +650,10 @@ def main():
                     tj = json.load(open(tpath))
                     tclass = tj.get("bytes_per_step", {})
                     traffic = tclass.get("gemm")
+                    wbytes = cfg["encoder_layers"] * (4 * cfg["encoder_embed_dim"] ** 2 + 2 * cfg["encoder_embed_dim"] * cfg["encoder_ffn_embed_dim"]) * 2
                     traffic_note = (f"{tj.get('source', 'ncu')}; launches per step covered: {tj.get('launches_per_step')}; "
-                                    f"algorithmic bytes of the GEMM class: {tj.get('algorithmic_bytes', {}).get('gemm')}")
+                                    f"algorithmic bytes of the GEMM class (activations once + weights once per launch): "
+                                    f"{int(gemm_bytes_per_utt(cfg, L) * B + wbytes)}")
             line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc2_kernel (all launches of one step)",
                                 "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                                 "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic,

@@ -11,6 +11,7 @@ classes follow wav2vec-s_b200/cabi.py:KERNEL_CLASS.  bench.py reads the JSON for
 import csv
 import json
 import os
+import re
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -33,15 +34,15 @@ def main(path, workload):
     ids = sorted(launches)
     names = [launches[i]["name"] for i in ids]
     # one step = from a conv0_kernel launch to just before the next one; take the last complete step
-    starts = [k for k, n in enumerate(names) if n.startswith("conv0_kernel")]
+    starts = [k for k, n in enumerate(names) if "conv0_kernel" in n]
     if len(starts) < 2:
         raise SystemExit("need at least two steps in the log")
     lo, hi = starts[-2], starts[-1]
     per_class, counts, time_ns = {}, {}, {}
     for k in range(lo, hi):
         d = launches[ids[k]]
-        base = d["name"].split("<")[0].split("(")[0]
-        cls = cabi.KERNEL_CLASS.get(base, "rows")
+        mm = re.search(r"(\w+_kernel)", d["name"])
+        cls = cabi.KERNEL_CLASS.get(mm.group(1) if mm else "", "rows")
         per_class[cls] = per_class.get(cls, 0.0) + d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
         counts[cls] = counts.get(cls, 0) + 1
         time_ns[cls] = time_ns.get(cls, 0.0) + d.get("gpu__time_duration.sum", 0.0)

@@ -51,10 +51,11 @@ def gather_outputs(x: torch.Tensor, n_frames: torch.Tensor, dst: Optional[int] =
         return [x[i, : int(n_frames[i])] for i in range(x.size(0))], n_frames.clone()
     world, rank = dist.get_world_size(), dist.get_rank()
     shape = torch.tensor([x.size(0), x.size(1)], dtype=torch.int64, device=x.device)
-    shapes = [torch.zeros_like(shape) for _ in range(world)]
-    dist.all_gather(shapes, shape)
-    Bm = int(max(int(s[0]) for s in shapes))
-    Tm = int(max(int(s[1]) for s in shapes))
+    shapes = shape.new_empty((world * 2,))
+    dist.all_gather_into_tensor(shapes, shape)
+    shapes = shapes.view(world, 2).tolist()                 # one device -> host read for all ranks' shapes
+    Bm = max(s_[0] for s_ in shapes)
+    Tm = max(s_[1] for s_ in shapes)
     if x.size(0) == Bm and x.size(1) == Tm and x.is_contiguous():
         pad = x                                       # equal shards (the usual case): no staging copy
     else:
@@ -70,10 +71,11 @@ def gather_outputs(x: torch.Tensor, n_frames: torch.Tensor, dst: Optional[int] =
     xs, nfs = xs.view((world, Bm) + tuple(pad.shape[1:])), nfs.view(world, Bm)
     if dst is not None and rank != dst:
         return None
+    nfs_host = nfs.tolist()                                 # one read for every utterance's frame count
     outs, counts = [], []
     for r in range(world):
-        for i in range(int(shapes[r][0])):
-            n = int(nfs[r][i])
-            outs.append(xs[r][i, :n])
+        for i in range(shapes[r][0]):
+            n = nfs_host[r][i]
+            outs.append(xs[r, i, :n])                       # views into the gathered buffer: no copies
             counts.append(n)
     return outs, torch.tensor(counts, dtype=torch.int64, device=x.device)
