@@ -426,7 +426,7 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        r = cpu_reference_run(kind, a.cpu_sample_batch, seconds, a.steps, a.warmup)
+        r = cpu_reference_run(kind, min(a.cpu_sample_batch, B), seconds, a.steps, a.warmup)
         line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": "audio-s/s",
                 "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -686,7 +686,9 @@ def main():
                 line["kernel_detail"] = {k: [round(v["ms"], 3), v["count"]] for k, v in sorted(prof.items())
                                          if "[" in k or "_kernel" in k}
         else:
-            line["roofline"] = None
+            line["roofline"] = None     # fp32 parity mode: CUDA-core kernels, no tensor-pipe roofline claimed
+            if prof is not None:
+                line["kernel_ms_per_step"] = {k: round(v["ms"], 3) for k, v in prof.items() if "[" not in k and "_kernel" not in k}
         if kind == "large" and world == 1 and not a.no_incremental:
             # the other half of BASELINE.json's metric: p50 latency of one decision step (16 new frames) of the
             # incremental path, one stream, same model; measured after the timed regions above
@@ -703,7 +705,7 @@ def main():
         if extra_points is not None:
             line["extra_points"] = extra_points
         if not a.no_cpu_baseline and world == 1:      # reported on rank 0 at N=1 only
-            r = cpu_reference_run(kind, a.cpu_sample_batch, seconds, 3, 1)      # ~15 s of CPU work at cfg3
+            r = cpu_reference_run(kind, min(a.cpu_sample_batch, B), seconds, 3, 1)      # ~15 s of CPU work at cfg3
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
     if world > 1:
