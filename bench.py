@@ -214,7 +214,8 @@ def stream_bench(a, kind, B, seconds):
     bounds.append(L)
     metric = f"p50 per-chunk latency (wav2vec-S {kind} incremental, batch {B}, {16 * a.step_blocks} frames/step)"
     config = {"workload": f"wav2vec-S {kind} incremental encoder, {B} stream(s) x {seconds} s, first chunk 24 frames, "
-                          f"then {16 * a.step_blocks} frames per step, {a.dtype}", "name": a.workload,
+                          f"then {16 * a.step_blocks} frames per step, {a.dtype}"
+                          + (", persistent step kernel" if a.step_impl == 2 else ""), "name": a.workload,
               "chunks": len(bounds), "l2_policy": "weights (613 MB bf16) exceed the 126 MB L2"}
     if a.impl == "reference":
         import warnings
@@ -261,7 +262,7 @@ def stream_bench(a, kind, B, seconds):
     wav = wav_host.to(dev)
 
     def run(e2e):
-        st = model.open_stream(B=B, max_seconds=seconds + 1, max_new_samples=max(7760, step) + 400)
+        st = model.open_stream(B=B, max_seconds=seconds + 1, max_new_samples=max(7760, step) + 400, step_impl=a.step_impl)
         lat, pos, outs = [], 0, 0
         for n in bounds:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -403,6 +404,7 @@ def main():
     ap.add_argument("--cpu-sample-batch", type=int, default=4,
                     help="utterances per step of the CPU reference arm (a bounded sample of the workload's batch)")
     ap.add_argument("--step-blocks", type=int, default=1, help="streaming workloads: blocks of 16 frames per decision step")
+    ap.add_argument("--step-impl", type=int, default=0, help="streaming workloads: 0 = operator chain (default), 2 = persistent step kernel")
     a = ap.parse_args()
     if a.workload.startswith("stream_"):
         kind, B, seconds = WORKLOADS[a.workload]

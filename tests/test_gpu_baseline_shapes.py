@@ -118,8 +118,9 @@ def test_base_2x15s_ragged_vs_oracle(dtype):
     assert e2 < BF16_TOL and err < BF16_TOL_FP32_WEIGHTS
 
 
-@pytest.mark.parametrize("dtype", DTYPES, ids=IDS)
-def test_incremental_large_30s_vs_oracle_offline_rows(dtype):
+@pytest.mark.parametrize("dtype,step_impl", [(torch.float32, 0), (torch.bfloat16, 0), (torch.bfloat16, 2)],
+                         ids=["fp32", "bf16", "bf16-persistent-kernel"])
+def test_incremental_large_30s_vs_oracle_offline_rows(dtype, step_impl):
     """configs[3]: large, chunk by chunk (first chunk 24 frames = 7760 samples, then 16 frames = 5120 samples) with
     cached left context over 30 s; every emitted frame against the oracle's OFFLINE row of the complete utterance
     (what the reference's prefix re-encoding converges to, rain/simul/transducer_agent.py:138-167)."""
@@ -128,7 +129,7 @@ def test_incremental_large_30s_vs_oracle_offline_rows(dtype):
     wav = synth.make_waveform(1, 30 * SR, cases.XSEED + 30)
     yo = oracle_once("large_30s", lambda: O.extract_features(sd, cfg, wav, None)[0])      # [1, T, D]
     m = build(W.BlockWiseWav2Vec2Model, cfg, sd, dtype)
-    st = m.open_stream(B=1, max_seconds=31, max_new_samples=7760 + 400)
+    st = m.open_stream(B=1, max_seconds=31, max_new_samples=7760 + 400, step_impl=step_impl)
     dev = wav.cuda()
     outs, pos, L = [], 0, wav.size(1)
     while pos < L:
@@ -138,7 +139,7 @@ def test_incremental_large_30s_vs_oracle_offline_rows(dtype):
     y = torch.cat(outs, 0).transpose(0, 1)                                                 # [1, T, D]
     assert tuple(y.shape) == tuple(yo.shape)
     err = valid_rel_err(y.cpu(), yo)
-    print(f"\n[parity] incremental large_30s {dtype}: vs oracle offline rows {err:.3e}")
+    print(f"\n[parity] incremental large_30s {dtype} step_impl={step_impl}: vs oracle offline rows {err:.3e}")
     assert err < TOL[dtype]
 
 

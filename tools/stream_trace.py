@@ -37,13 +37,12 @@ for _ in range(3):
     torch.cuda.synchronize()
     lat.append(e0.elapsed_time(e1))
     pos += 5120
-buf = (C.c_uint64 * (2 * 64 * 12 + 2 * 96))()
+buf = (C.c_uint64 * (2 * 64 * 12))()
 cabi.check(cabi.lib().w2vs_debug_fused_trace(buf, len(buf)), "trace")
 raw = np.frombuffer(buf, dtype=np.uint64).astype(np.int64)
 tc = raw[:2 * 64 * 12].reshape(2, 64, 12)[:, :24, 11]
 t = raw[:2 * 64 * 12].reshape(2, 64, 12)[:, :24, :11]
 print("SM clock during the kernel (MHz):", [round(float((tc[c, 23] - tc[c, 0]) / ((t[c, 23, 0] - t[c, 0, 0]) / 1e3)), 1) for c in range(2)])
-t2 = raw[2 * 64 * 12:].reshape(2, 96)
 names = ["LN+QKV", "barrier", "attention", "barrier", "out_proj", "barrier", "LN+fc1", "barrier", "fc2", "barrier"]
 print(f"step latency (ms): {lat}; left context {pos / 16000:.1f} s")
 for c, who in enumerate(("first CTA", "last CTA")):
@@ -52,10 +51,7 @@ for c, who in enumerate(("first CTA", "last CTA")):
           f"all layers {(t[c, -1, 10] - t[c, 0, 0]) / 1e3:.1f} us")
 for c, who in enumerate(("first CTA", "last CTA")):
     t0 = t[c, 12, 0]
-    ev = {i: (int(v) - int(t0)) / 1e3 for i, v in enumerate(t2[c]) if v > 0}
-    print(who, "raw fine events:", [int(v - t2[c][0]) for v in t2[c][:16] if v > 0])
-    print(who, "layer 12 events (us from layer start):", " ".join(f"{k}:{v:.2f}" for k, v in sorted(ev.items())))
-    print("   phase marks:", " ".join(f"{i}:{(int(t[c, 12, i]) - int(t0)) / 1e3:.2f}" for i in range(11)))
+    print(who, "layer 12 phase marks (us from layer start):", " ".join(f"{i}:{(int(t[c, 12, i]) - int(t0)) / 1e3:.2f}" for i in range(11)))
 flags = C.c_int32(0)
 cabi.check(cabi.lib().w2vs_debug_fault_flags(C.byref(flags)), "faults")
 print("fault flags:", flags.value)

@@ -40,7 +40,6 @@ __device__ int g_fused_fault = 0;   // set when a barrier / pipeline wait timed 
 // 5 out_proj done, 6 barrier, 7 fc1 done, 8 barrier, 9 fc2 done, 10 barrier, 11 clock64 at layer start.  Read by
 // tools/stream_trace.py through w2vs_debug_fused_trace (one store per phase: free).
 __device__ unsigned long long g_fused_trace[2][64][12];
-__device__ unsigned long long g_fused_trace2[2][96];   // spare fine-grained slots (layer FS_TRACE_LAYER)
 }
 #define W2VS_TC_FAULT_FLAG (&::w2vs::g_fused_fault)
 #include "tc_common.cuh"
@@ -145,7 +144,24 @@ __device__ __forceinline__ const float* lw(const FusedArgs& a, int layer, unsign
 // consumption order (layer, product, unit, K chunk) from the per-CTA list `sched`, never blocking.
 // One out-of-line copy of the mbarrier wait: its time-out logic is ~40 instructions per inlined site, and the code
 // size of this kernel is what bounds its speed (see the layer loop).
-__device__ __noinline__ bool wait_bar(uint32_t bar, uint32_t parity) { return mbar_wait(bar, parity); }
+#ifndef W2VS_FS_SPIN_TEST
+#define W2VS_FS_SPIN_TEST 1
+#endif
+__device__ __noinline__ bool wait_bar(uint32_t bar, uint32_t parity) {
+#if W2VS_FS_SPIN_TEST
+  // spin on the non-blocking probe: mbarrier.try_wait parks the thread for a hardware-chosen time when the phase is
+  // not complete yet, and every wait in this kernel sits on the critical path of a phase
+  if (mbar_test(bar, parity)) return true;
+  const unsigned long long t0 = global_ns();
+  unsigned spins = 0;
+  while (!mbar_test(bar, parity)) {
+    if ((++spins & 0xfff) == 0 && global_ns() - t0 > FS_TIMEOUT_NS) { atomicExch(&g_fused_fault, 1); return false; }
+  }
+  return true;
+#else
+  return mbar_wait(bar, parity);
+#endif
+}
 struct Ring { int stage; uint32_t phase; };
 struct Prod { int e, l, n_entries, stage; uint32_t phase; };
 
@@ -890,12 +906,7 @@ w2vs_status_t launch_stream_fused(const StreamFusedArgs& h, cudaStream_t st) {
 }
 
 w2vs_status_t debug_read_fused_trace(unsigned long long* out, int n) {
-  if (n > 2 * 64 * 12) {      // the fine-grained events follow the per-phase table
-    const int n2 = n - 2 * 64 * 12 > 2 * 96 ? 2 * 96 : n - 2 * 64 * 12;
-    cudaError_t e2 = cudaMemcpyFromSymbol(out + 2 * 64 * 12, g_fused_trace2, (size_t)n2 * 8);
-    if (e2 != cudaSuccess) { set_error("read g_fused_trace2: %s", cudaGetErrorString(e2)); return W2VS_CUDA_ERROR; }
-    n = 2 * 64 * 12;
-  }
+  if (n > 2 * 64 * 12) n = 2 * 64 * 12;
   cudaError_t e = cudaMemcpyFromSymbol(out, g_fused_trace, (size_t)n * 8);
   if (e != cudaSuccess) { set_error("read g_fused_trace: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
   return W2VS_OK;
