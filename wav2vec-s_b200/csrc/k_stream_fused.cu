@@ -191,19 +191,20 @@ __device__ __noinline__ bool grid_barrier(const FusedArgs& a, const Smem& sm, ui
     // release at gpu scope: the CTA's writes of this phase (ordered before this thread by the bar.sync above) are
     // visible to whoever observes the arrival
     asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(a.bar), "l"(1ull) : "memory");
-    pump(a, sm, sb, smem_gen, pr, FS_MAX_STAGES);      // every stage consumed in the phase that just ended is free now
     unsigned long long v;
     unsigned spins = 0;
     unsigned long long t0 = 0;
     for (;;) {
       asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.bar) : "memory");
       if (v >= target) break;
+      pump(a, sm, sb, smem_gen, pr, 1);       // the wait is the producer's time: one slab per probe
       if ((++spins & 0x3ff) == 0) {
         const unsigned long long now = global_ns();
         if (t0 == 0) t0 = now;
         else if (now - t0 > FS_TIMEOUT_NS) { atomicExch(&g_fused_fault, 1); *s_abort = 1; break; }
       }
     }
+    pump(a, sm, sb, smem_gen, pr, FS_MAX_STAGES);     // whatever is still free: the next phase's slabs must be under way
   }
   named_bar(1, 32 * FS_CW);
   return *s_abort == 0;
@@ -288,7 +289,7 @@ enum { EPI_QKV = 0, EPI_RESID = 1, EPI_GELU = 2 };
 // instance serves all four products (rolled loops over units and K chunks: code size bounds this kernel).
 template <int MT>
 __device__ __forceinline__ bool gemm_phase(const FusedArgs& a, const Smem& sm, uint32_t sb, uint8_t* smem_gen, Ring& rs,
-                                           uint32_t& aphase, int layer, int N, int K, const bf16* a_glob, int epi,
+                                           Prod& pr, uint32_t& aphase, int layer, int N, int K, const bf16* a_glob, int epi,
                                            const float* bias, const float* res_lnp, int a_bufs, int warp, int lane) {
   const int G = gridDim.x, cta = blockIdx.x;
   const int D = a.D, KC = D, Mt = a.B * a.ntok;
@@ -374,6 +375,7 @@ __device__ __forceinline__ bool gemm_phase(const FusedArgs& a, const Smem& sm, u
       __syncwarp();
       if (lane == 0) mbar_arrive(sb + sm.bars + 96 + 8 * rs.stage);
       if (++rs.stage == a.n_stages) { rs.stage = 0; rs.phase ^= 1; }
+      if (tid == 0) pump(a, sm, sb, smem_gen, pr, 1);       // usually refills the stage released one step earlier
     }
     // partial sums of this warp's K slice -> shared memory
 #pragma unroll
@@ -762,7 +764,7 @@ stream_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__
       const bf16* ag = ph == 1 ? a.ctx : (ph == 3 ? a.h : nullptr);
       const int epi = ph == 0 ? EPI_QKV : (ph == 2 ? EPI_GELU : EPI_RESID);
       const float* bias = lw(a, l, ph == 0 ? a.bqkv : (ph == 1 ? a.bo : (ph == 2 ? a.b1 : a.b2)));
-      ok = gemm_phase<MT>(a, sm, sb, smem_gen, rs, aphase, l, N, K, ag, epi, bias, ((ph & 1) && !a.pre_ln) ? lnp : nullptr,
+      ok = gemm_phase<MT>(a, sm, sb, smem_gen, rs, pr, aphase, l, N, K, ag, epi, bias, ((ph & 1) && !a.pre_ln) ? lnp : nullptr,
                           a_bufs, warp, lane) && ok;
       FS_TRACE(l, ph == 0 ? 1 : 3 + 2 * ph);
       if (threadIdx.x == 0 && (ph & 1) && l + 1 < a.layers) {
