@@ -177,7 +177,7 @@ def reference_cpu_encoder(cfg_kind):
     return (lambda wav: O.extract_features(sd, cfg, wav, None)[0]), "port", "oracle port on torch CPU"
 
 
-def cpu_reference_run(cfg_kind, B, seconds, steps, warmup):
+def cpu_reference_run(cfg_kind, B, seconds, steps, warmup, bf16_too=False):
     """Time the reference's CPU implementation (fp32, all host threads) on a bounded sample of the workload."""
     import torch
     from oracle import synth
@@ -193,10 +193,32 @@ def cpu_reference_run(cfg_kind, B, seconds, steps, warmup):
         if i >= warmup:
             times.append(dt)
     t = statistics.median(times)
-    return dict(value=B * seconds / t, unit="audio-s/s", cores=cores, kind=kind,
-                sample=f"{cfg_kind} fp32, {B} x {seconds} s per step (a sample of the workload's batch), {what}, "
-                       f"median of {steps} after {warmup} warm-up",
-                ms_per_step=t * 1e3)
+    out = dict(value=B * seconds / t, unit="audio-s/s", cores=cores, kind=kind,
+               sample=f"{cfg_kind} fp32, {B} x {seconds} s per step (a sample of the workload's batch), {what}, "
+                      f"median of {steps} after {warmup} warm-up",
+               ms_per_step=t * 1e3)
+    if bf16_too and kind == "reference":
+        # informational: the same reference modules in bf16 on the CPU (`model.bfloat16()`, bf16 waveform) -- faster
+        # than its fp32 run on AMX/AVX512-bf16 hosts, and 2-2.6e-2 away from its own fp32 output
+        try:
+            from oracle import ref_shim
+            from oracle import w2vs_oracle as O
+            cfg = O.default_cfg(**model_cfg(cfg_kind))
+            m16 = ref_shim.build_fairseq_model(cfg)
+            m16.load_state_dict(synth.make_state_dict(cfg, 0), strict=False)
+            m16 = m16.bfloat16()
+            w16 = wav.to(torch.bfloat16)
+            tt = []
+            for i in range(2):
+                t0 = time.perf_counter()
+                with torch.no_grad():
+                    m16.extract_features(w16, None)
+                tt.append(time.perf_counter() - t0)
+            out["bf16_value"] = B * seconds / min(tt)
+        except Exception as ex:
+            out["bf16_value"] = None
+            out["bf16_note"] = f"{type(ex).__name__}: {ex}"
+    return out
 
 
 def stream_bench(a, kind, B, seconds):
@@ -707,8 +729,8 @@ def main():
         if extra_points is not None:
             line["extra_points"] = extra_points
         if not a.no_cpu_baseline and world == 1:      # reported on rank 0 at N=1 only
-            r = cpu_reference_run(kind, min(a.cpu_sample_batch, B), seconds, 3, 1)      # ~15 s of CPU work at cfg3
-            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            r = cpu_reference_run(kind, min(a.cpu_sample_batch, B), seconds, 3, 1, bf16_too=True)   # ~25 s of CPU work at cfg3
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "bf16_value") if k in r}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
