@@ -174,3 +174,27 @@ def test_ragged_60s_90s_vs_oracle(pre_ln, dtype):
         err = float((y[b].float().cpu()[keep] - yo[b][keep]).abs().max() / yo[b][keep].abs().max())
         print(f"\n[parity] ragged_90s pre_ln={pre_ln} {dtype} utterance {b} ({int(lens[b]) / SR:.1f} s): {err:.3e}")
         assert err < TOL[dtype], (b, err)
+
+
+def test_incremental_large_16_streams_vs_oracle_offline_rows():
+    """configs[3] with a batch of streams: 16 lock-step streams of the large model (384 tokens per decision step: the
+    tcgen05 GEMM path of the incremental mode), 6 s each, bf16, every emitted frame against the oracle's offline rows
+    of the same utterances (identical, bf16-valued weights)."""
+    cfg = O.large_cfg()
+    sd = synth.make_state_dict(cfg, cases.WSEED)
+    B, L = 16, 6 * SR
+    wav = synth.make_waveform(B, L, cases.XSEED + 16)
+    yq = O.extract_features(bf16_valued(sd), cfg, wav, None)[0]                       # [B, T, D]
+    m = build(W.BlockWiseWav2Vec2Model, cfg, sd, torch.bfloat16)
+    st = m.open_stream(B=B, max_seconds=7, max_new_samples=7760 + 400)
+    dev = wav.cuda()
+    outs, pos = [], 0
+    while pos < L:
+        n = min(7760 if pos == 0 else 5120, L - pos)
+        outs.append(st.step(dev[:, pos:pos + n], EncoderStream.FINAL if pos + n >= L else EncoderStream.NONE))
+        pos += n
+    y = torch.cat(outs, 0).transpose(0, 1)
+    assert tuple(y.shape) == tuple(yq.shape)
+    err = valid_rel_err(y.cpu(), yq)
+    print(f"\n[parity] incremental large 16 streams bf16: vs oracle offline rows (identical weights) {err:.3e}")
+    assert err < BF16_TOL
