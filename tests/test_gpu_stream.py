@@ -189,6 +189,42 @@ def test_fused_step_kernel_equals_operator_chain(pre_ln, B, main, rc):
     assert valid_rel_err(y_fused, ref) < TOL[torch.bfloat16] and valid_rel_err(y_chain, ref) < TOL[torch.bfloat16]
 
 
+@pytest.mark.parametrize("main,rc", [(16, 8), (8, 4), (20, 10), (6, 2), (16, 0)])
+def test_cluster_step_kernel_equals_operator_chain(main, rc):
+    """One stream of a pre-LN bf16 model can run its decision steps as one kernel of thread-block clusters
+    (k_stream_cluster.cu, stream_step_impl = 3: one cluster of 8 CTAs per attention head, two grid barriers per layer,
+    fp32 reductions at L2 into the residual stream).  Same rows as the kernel-per-operator chain with the same
+    roundings, up to summation order; irregular chunks, so that steps of every size occur (full blocks, the short
+    blocks of the final flush, several blocks per call); both also against the oracle's offline rows."""
+    from oracle import synth
+    cfg = cases.tiny(layer_norm_first=True, conv_bias=True, main_context=main, right_context=rc, encoder_layers=4)
+    sd = synth.make_state_dict(cfg, 70 + main)
+    L = 26000
+    wav = synth.make_waveform(1, L, 80 + main)
+    m = build(cfg, sd, torch.bfloat16)
+    ref, _ = O.rain_forward(sd, cfg, wav, None, finished=True, is_infer=True)
+    src = wav.cuda()
+    ys = []
+    for impl in (3, 0):
+        rs = np.random.RandomState(3)
+        st = m.open_stream(B=1, max_seconds=3.0, max_new_samples=9000, step_impl=impl)
+        W.cabi.launch_count(reset=True)
+        outs, pos = [], 0
+        while pos < L:
+            n = min(int(rs.choice([37, 400, 1600, 5120, 8999])), L - pos)
+            outs.append(st.step(src[:, pos:pos + n], EncoderStream.FINAL if pos + n >= L else EncoderStream.NONE))
+            pos += n
+        torch.cuda.synchronize()
+        ys.append((torch.cat(outs, 0).float().cpu(), W.cabi.launch_count(reset=True)))
+    (y_cl, n_cl), (y_chain, n_chain) = ys
+    assert n_cl < n_chain                      # the cluster kernel really ran (far fewer launches)
+    assert tuple(y_cl.shape) == tuple(ref.shape)
+    e_chain, e_ref = valid_rel_err(y_cl, y_chain), valid_rel_err(y_cl, ref)
+    print(f"\n[parity] cluster step kernel main={main} rc={rc}: vs chain {e_chain:.3e}, vs oracle {e_ref:.3e}")
+    assert e_chain < 1e-2
+    assert e_ref < TOL[torch.bfloat16] and valid_rel_err(y_chain, ref) < TOL[torch.bfloat16]
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 def test_stream_grows_past_its_initial_capacity(dtype):
     """A stream opened for 0.5 s keeps going: its state moves into larger buffers (w2vs_stream_grow, K/V cache and

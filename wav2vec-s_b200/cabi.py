@@ -91,12 +91,14 @@ PROTOTYPES = {
     "w2vs_prof_enable": (None, [C.c_int32, C.c_void_p]),
     "w2vs_prof_collect": (C.c_int64, [C.c_char_p, C.c_int64]),
     "w2vs_debug_fused_trace": (C.c_int, [_P(C.c_uint64), C.c_int32]),
+    "w2vs_debug_cluster_trace": (C.c_int, [_P(C.c_uint64), C.c_int32]),
     "w2vs_debug_fault_flags": (C.c_int, [_P(C.c_int32)]),
 }
 
 # kernel name -> class reported by bench.py
 KERNEL_CLASS = {"gemm_tc_kernel": "gemm", "gemm_tc2_kernel": "gemm", "gemm_simt_kernel": "gemm_simt", "attn_mma_kernel": "attention", "attn_tc_kernel": "attention",
-                "attn_simt_kernel": "attention", "conv0_kernel": "conv0", "stream_fused_kernel": "stream_fused"}
+                "attn_simt_kernel": "attention", "conv0_kernel": "conv0", "stream_fused_kernel": "stream_fused",
+                "stream_cluster_kernel": "stream_cluster"}
 
 _lib = None
 

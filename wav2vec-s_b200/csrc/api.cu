@@ -140,6 +140,9 @@ w2vs_status_t w2vs_weights_pack(const w2vs_config* cfg, const void* const* d_ref
     W2VS_TRY(copy_f32(l.b2, D));
     W2VS_TRY(copy_f32(l.ln2_w, D));
     W2VS_TRY(copy_f32(l.ln2_b, D));
+    if (l.wc != kNone)   // per-CTA operand pieces of the cluster incremental step, from the bf16 matrices just packed
+      W2VS_TRY(launch_pack_cluster(cfg, at<void>(d_packed, l.wqkv), at<void>(d_packed, l.wo), at<void>(d_packed, l.w1),
+                                   at<void>(d_packed, l.w2), at<void>(d_packed, l.wc), st));
   }
   W2VS_TRY(copy_f32(wl.enc_ln_w, D));
   W2VS_TRY(copy_f32(wl.enc_ln_b, D));
@@ -435,13 +438,19 @@ w2vs_status_t w2vs_debug_fused_trace(uint64_t* out, int32_t n) {
   return debug_read_fused_trace(reinterpret_cast<unsigned long long*>(out), n);
 }
 
+w2vs_status_t w2vs_debug_cluster_trace(uint64_t* out, int32_t n) {
+  W2VS_REQUIRE(out != nullptr && n >= 0, "out / n");
+  return debug_read_cluster_trace(reinterpret_cast<unsigned long long*>(out), n);
+}
+
 w2vs_status_t w2vs_debug_fault_flags(int32_t* flags) {
   W2VS_REQUIRE(flags != nullptr, "flags is NULL");
-  int a = 0, b = 0, c = 0;
+  int a = 0, b = 0, c = 0, d = 0;
   W2VS_TRY(debug_read_tc2_fault(&a));
   W2VS_TRY(debug_read_attn_tc_fault(&b));
   W2VS_TRY(debug_read_fused_fault(&c));
-  *flags = (a ? 1 : 0) | (b ? 2 : 0) | (c ? 4 : 0);
+  W2VS_TRY(debug_read_cluster_fault(&d));
+  *flags = (a ? 1 : 0) | (b ? 2 : 0) | (c ? 4 : 0) | (d ? 8 : 0);
   return W2VS_OK;
 }
 

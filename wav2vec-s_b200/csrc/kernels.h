@@ -133,6 +133,18 @@ w2vs_status_t launch_stream_fused(const StreamFusedArgs& a, cudaStream_t st);
 w2vs_status_t debug_read_fused_fault(int* out);
 w2vs_status_t debug_read_fused_trace(unsigned long long* out, int n);
 
+// ---- cluster incremental step (k_stream_cluster.cu): the same step as ONE kernel of H clusters x 8 CTAs, two grid
+// barriers per layer (one stream, pre-LN bf16 models of the instantiated shapes); takes the arguments above (q / ctx /
+// h / partials / counters unused, R = three residual buffers of 32 rows) and the per-CTA weight copy LayerW::wc ----
+constexpr int kStreamClusterSize = 4;
+size_t stream_cluster_layer_bytes(const w2vs_config* cfg);      // bytes of LayerW::wc per layer, 0 = kernel not available
+bool stream_cluster_applicable(const w2vs_config* cfg, int B, int ntok);
+w2vs_status_t launch_stream_cluster(const StreamFusedArgs& a, cudaStream_t st);
+w2vs_status_t launch_pack_cluster(const w2vs_config* cfg, const void* wqkv, const void* wo, const void* w1,
+                                  const void* w2, void* dst, cudaStream_t st);
+w2vs_status_t debug_read_cluster_fault(int* out);
+w2vs_status_t debug_read_cluster_trace(unsigned long long* out, int n);
+
 // ---- positional conv + weight packing -----------------------------------------------------------------
 struct PosConvArgs {
   const float* feats; int feat_rows; const uint8_t* frame_pad;

@@ -217,6 +217,8 @@ void make_weight_layout(const w2vs_config* cfg, WeightLayout* wl) {
   l.ln2_w = b.take((size_t)D * 4);
   l.ln2_b = b.take((size_t)D * 4);
   l.w2s = stream_fused_model(cfg) ? b.take((size_t)D * F * 2) : kNone;
+  const size_t wc_bytes = stream_cluster_layer_bytes(cfg);
+  l.wc = wc_bytes ? b.take(wc_bytes) : kNone;
   wl->layer_stride = b.off - wl->layers_begin;
   wl->total = wl->layers_begin + wl->layer_stride * (size_t)cfg->layers;
 }

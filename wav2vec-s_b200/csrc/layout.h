@@ -39,6 +39,8 @@ struct LayerW {
   size_t w2s;             // bf16 [D/8][F/D][8][D]: fc2 weights in the slab order of the fused incremental step (each
                           // 8-row x D-wide slab contiguous), or SIZE_MAX when that kernel does not apply
   size_t ln2_w, ln2_b;    // final_layer_norm
+  size_t wc;              // bf16, per (cluster, CTA): the four operand pieces of the cluster incremental step exactly as
+                          // they lie in shared memory (k_stream_cluster.cu), or SIZE_MAX when that kernel does not apply
 };
 struct WeightLayout {
   ConvW conv[W2VS_MAX_CONV];
@@ -61,6 +63,7 @@ inline LayerW layer_at(const WeightLayout& wl, int n) {
   l.wqkv += d; l.bqkv += d; l.wo += d; l.bo += d; l.ln1_w += d; l.ln1_b += d;
   l.w1 += d; l.b1 += d; l.w2 += d; l.b2 += d; l.ln2_w += d; l.ln2_b += d;
   if (l.w2s != kNone) l.w2s += d;
+  if (l.wc != kNone) l.wc += d;
   return l;
 }
 
@@ -92,6 +95,13 @@ inline bool stream_fused_model(const w2vs_config* cfg) {
   return cfg->dtype == W2VS_BF16 && D % 128 == 0 && D <= 1024 && F % D == 0 && cfg->heads * 64 == D &&
          cfg->pos_type == W2VS_POS_SIN && cfg->extractor_mode == W2VS_EXTRACTOR_LAYER_NORM;
 }
+
+// Models the cluster incremental-step kernel (k_stream_cluster.cu) may run, shape permitting (stream_cluster_layer_bytes)
+inline bool stream_cluster_model(const w2vs_config* cfg) {
+  return cfg->dtype == W2VS_BF16 && cfg->layer_norm_first != 0 && cfg->heads * 64 == cfg->embed_dim &&
+         cfg->pos_type == W2VS_POS_SIN && cfg->extractor_mode == W2VS_EXTRACTOR_LAYER_NORM;
+}
+size_t stream_cluster_layer_bytes(const w2vs_config* cfg);   // k_stream_cluster.cu
 
 // Positional conv (pos_type = conv) on the tensor cores: bf16 models whose group width is a multiple of 8.
 // Each group is an implicit GEMM over a group-major copy of the frames, channels padded to Dgp (multiple of 64).

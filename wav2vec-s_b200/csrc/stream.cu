@@ -146,6 +146,19 @@ w2vs_status_t block_step(const w2vs_config* cfg, const WeightLayout& wl, const S
   void* ctx = at<void>(d_ws, L.ctx);
   void* h = at<void>(d_ws, L.h);
   const bool pre_ln = cfg->layer_norm_first != 0;
+  if (cfg->stream_step_impl == 3 && cfg->io_dtype == 0 && stream_cluster_applicable(cfg, B, ntok)) {
+    // opt-in (stream_step_impl = 3; one stream, pre-LN bf16 models, at most 32 tokens per step): the whole step as
+    // one kernel of thread-block clusters, one cluster per attention head
+    StreamFusedArgs fa{};
+    fa.cfg = cfg; fa.wl = &wl; fa.W = W;
+    fa.B = B; fa.ntok = ntok; fa.n_main = n_main; fa.f0 = f0;
+    fa.feats = at<float>(d_state, L.fbuf); fa.feat_rows = L.fcap;
+    fa.R = X;
+    fa.kv = at<void>(d_state, L.kv); fa.kv_layer_elems = (int64_t)(L.kv_layer_bytes / as); fa.kv_rows = L.kv_rows;
+    fa.out = out_frames;
+    fa.bar = at<unsigned long long>(d_state, L.fused_bar);
+    return launch_stream_cluster(fa, st);
+  }
   if (cfg->stream_step_impl == 2 && cfg->io_dtype == 0 && stream_fused_applicable(cfg, B, ntok)) {
     // opt-in (stream_step_impl = 2; bf16 models, at most 32 tokens per step): the whole step as one persistent
     // cooperative kernel
