@@ -41,7 +41,7 @@
 
 namespace w2vs {
 __device__ int g_cluster_fault = 0;                       // a barrier / pipeline wait timed out (diagnostics)
-__device__ unsigned long long g_cluster_trace[64][16];    // globaltimer stamps of CTA 0, [layer][event]
+__device__ unsigned long long g_cluster_trace[64][24];    // globaltimer stamps of CTA 0, [layer][event]
 }
 #define W2VS_TC_FAULT_FLAG (&::w2vs::g_cluster_fault)
 #include "tc_common.cuh"
@@ -55,6 +55,8 @@ constexpr int CW = 8, CT = 32 * CW;           // warps / threads per CTA
 constexpr int ROWS = 32;                      // token rows of a step (two m16 tiles)
 constexpr unsigned long long CL_TIMEOUT_NS = 2000000000ull;
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
+constexpr int MRG_BLK = 16 * 68 + 32;         // floats per merge block: [16][68] O + [16][2] (m, l)
+constexpr int MRG_P = 68;                     // floats per row of a merge block (64 + 4: rows land in different banks)
 static_assert(CL == 4, "warp -> destination CTA maps below assume four CTAs per cluster");
 
 struct ClArgs {
@@ -97,10 +99,11 @@ struct CK {
   static constexpr int S_G = S_SCR + SCR_B;
   static constexpr int G_B = cmax(ROWS * PG, ROWS * PH);
   static constexpr int S_CTX = S_G + G_B;
-  static constexpr int S_BAR = S_CTX + 16 * PO;
+  static constexpr int S_MRG = S_CTX + 16 * PO;                       // attention merge: 4 x ([16][68] O + [16][2] (m, l)) fp32
+  static constexpr int S_BAR = S_MRG + 4 * MRG_BLK * 4;
   static constexpr int S_END = S_BAR + 64;
-  // phase A scratch after the reduce: o_cta [16][64], l_cta [16], wm [8][16], m_cta [16], rx2 [4][16][16], ml_rx [4][16][2]
-  static constexpr int X_L = 4096, X_WM = 4224, X_M = 4736, X_RX2 = 8192, X_ML = 12288;
+  // phase A scratch after the reduce: rx2 [4][16][16], ml_rx [4][16][2]   (fp32, written by the peers)
+  static constexpr int X_RX2 = 8192, X_ML = 12288;
   static_assert(D % 128 == 0 && D == 64 * H && HC % 64 == 0 && KS % 16 == 0, "model shape");
   static_assert(S_END + 128 <= 232448, "shared memory");
 };
@@ -141,6 +144,7 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
   return r;
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float ex2w(float m, float M, float sl2) { return m == -INFINITY ? 0.f : ex2_approx((m - M) * sl2); }
 
 // Grid-wide barrier (all CTAs are co-resident: one per SM, the launcher checked the occupancy).  One arrival counter
@@ -222,6 +226,23 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
   };
   // piece i is the (i >> 1)-th use of its slot
   auto wait_piece = [&](int i) { return mbar_wait(bar_slot + 8 * (i & 1), (uint32_t)(i >> 1) & 1u); };
+  // L2 prefetch of the parameter vectors phase `p` reads through plain loads: LayerNorm weight / bias and the second
+  // product's bias over this CTA's K slice, the first product's bias over the columns this CTA reduces
+  auto prefetch_params = [&](int p) {
+    const int l = p >> 1;
+    if (l >= a.layers) return;
+    const uint8_t* Wl = a.W + (size_t)l * a.layer_stride;
+    const bool pa_ = (p & 1) == 0;
+    constexpr int LPV = (K::KS * 4 + 127) / 128;          // 128-byte lines per vector slice
+    if (tid < 3 * LPV) {
+      const int v = tid / LPV, i = tid - v * LPV;
+      const unsigned long long off = pa_ ? (v == 0 ? a.ln1_w : (v == 1 ? a.ln1_b : a.bo)) : (v == 0 ? a.ln2_w : (v == 1 ? a.ln2_b : a.b2));
+      prefetch_l2(Wl + off + 4 * (rank * K::KS) + 128 * i);
+    } else if (tid >= 32 && tid < 32 + 6) {
+      if (pa_) prefetch_l2(Wl + a.bqkv + 4 * (((tid - 32) >> 1) * D + (cl >> 1) * 64) + 128 * ((tid - 32) & 1));
+      else if (tid < 32 + 2) prefetch_l2(Wl + a.b1 + 4 * (cl * K::HC + rank * K::HR) + 128 * (tid - 32));
+    }
+  };
   if (tid == 0) {
     mbar_init(bar_slot, 1); mbar_init(bar_slot + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -244,6 +265,7 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
     a.X[e] = v;
     a.X[(size_t)ROWS * D + e] = 0.f;
   }
+  prefetch_params(0);
   cluster_sync();                          // mbarrier inits and zeroed buffers before any remote traffic
   unsigned long long nbar = 0;
   bool ok = grid_barrier(a.bar, ++nbar * G);
@@ -258,6 +280,16 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
     CL_TRACE(l, pa ? 0 : 8);
     // zero the buffer the NEXT phase accumulates into (it was last read in the previous phase)
     a.X[(size_t)((ph + 2) % 3) * ROWS * D + gid * CT + tid] = 0.f;
+    // the small parameter vectors of the NEXT phase (first touched there: a DRAM miss on its critical path otherwise)
+    prefetch_params(ph + 1);
+    if (pa && 16 * (cl & 1) < Mt) {
+      // this warp's past K / V rows of head cl / 2 -> L2 (one 128-byte line per lane: 16 keys x {K, V} per step)
+      const uint8_t* kv_h = reinterpret_cast<const uint8_t*>(a.kv + (size_t)l * a.kv_layer_elems + (cl >> 1) * 64);
+      for (int s = rank * CW + warp; 16 * s < a.f0; s += CL * CW) {
+        const int key = min(16 * s + (lane & 15), a.f0 - 1);
+        prefetch_l2(kv_h + (size_t)key * (4 * D) + (lane >> 4) * (2 * D));
+      }
+    }
 
     // ================= LayerNorm of the K slice =================
     float4 x[4][K::NV4], gm[K::NV4], bt[K::NV4], b2v[K::NV4];
@@ -337,6 +369,7 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
       const int head = cl >> 1, mtile = cl & 1;
       ok = wait_piece(4 * l) && ok;
       ok = wait_piece(4 * l + 1) && ok;
+      CL_TRACE(l, 15);
       if (a_on) {
         float acc[2][3][4] = {};
         uint32_t bb[3];
@@ -391,8 +424,6 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
                   *reinterpret_cast<const uint4*>(sm + K::S_A + r * 96 + ch * 16);
           }
         }
-        // the scratch area becomes the merge area of the attention: zero the CTA accumulators (o_cta, l_cta)
-        for (int i = tid; i < (K::X_L + 64) / 16; i += CT) reinterpret_cast<uint4*>(sm + K::S_SCR)[i] = make_uint4(0u, 0u, 0u, 0u);
       }
       cluster_sync();
       CL_TRACE(l, 3);
@@ -410,32 +441,39 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
           const uint4 q0a = *reinterpret_cast<const uint4*>(qr), q0b = *reinterpret_cast<const uint4*>(qr + 16);
           const uint4 q1a = *reinterpret_cast<const uint4*>(qr + 8 * K::PG), q1b = *reinterpret_cast<const uint4*>(qr + 8 * K::PG + 16);
           const uint8_t* kv_h = reinterpret_cast<const uint8_t*>(a.kv + (size_t)l * a.kv_layer_elems + head * 64);
-#pragma unroll 1
-          for (int s = grp; s < n_steps; s += CL * CW) {
-            const uint8_t* kb; size_t pitch; int valid, voff;
-            if (s < n_past) { kb = kv_h + (size_t)(16 * s) * (4 * D); pitch = 4 * D; valid = min(16, a.f0 - 16 * s); voff = 2 * D; }
-            else { const int t0 = 16 * (s - n_past); kb = sm + K::S_G + t0 * K::PG + 128; pitch = K::PG; valid = min(16, Mt - t0); voff = 128; }
-            uint4 ka[2], kc[2], vv[4];
+          struct KVF { uint4 ka[2], kc[2], vv[4]; int valid; };
+          auto load_step = [&](int s, KVF& f) {
+            const uint8_t* kb; size_t pitch; int voff;
+            if (s < n_past) { kb = kv_h + (size_t)(16 * s) * (4 * D); pitch = 4 * D; f.valid = min(16, a.f0 - 16 * s); voff = 2 * D; }
+            else { const int t0 = 16 * (s - n_past); kb = sm + K::S_G + t0 * K::PG + 128; pitch = K::PG; f.valid = min(16, Mt - t0); voff = 128; }
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
-              const uint8_t* p = kb + (size_t)min(8 * t + g, valid - 1) * pitch + 32 * q;
-              ka[t] = *reinterpret_cast<const uint4*>(p);
-              kc[t] = *reinterpret_cast<const uint4*>(p + 16);
+              const uint8_t* p = kb + (size_t)min(8 * t + g, f.valid - 1) * pitch + 32 * q;
+              f.ka[t] = *reinterpret_cast<const uint4*>(p);
+              f.kc[t] = *reinterpret_cast<const uint4*>(p + 16);
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int key = 2 * q + (e & 1) + 8 * (e >> 1);
-              vv[e] = *reinterpret_cast<const uint4*>(kb + voff + (size_t)min(key, valid - 1) * pitch + 16 * g);
+              f.vv[e] = *reinterpret_cast<const uint4*>(kb + voff + (size_t)min(key, f.valid - 1) * pitch + 16 * g);
             }
+          };
+          KVF cur, nxt;
+          if (grp < n_steps) load_step(grp, cur);
+#pragma unroll 1
+          for (int s = grp; s < n_steps; s += CL * CW) {
+            // the next step's fragments are in flight while this one is computed
+            if (s + CL * CW < n_steps) load_step(s + CL * CW, nxt);
+            const int valid = cur.valid;
             // S = Q K^T for 16 keys (the d index is permuted identically for Q and K: lane q owns d = 16 q .. 16 q + 15)
             float sc[2][4];
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
               sc[t][0] = sc[t][1] = sc[t][2] = sc[t][3] = 0.f;
-              mma_16816(sc[t], q0a.x, q1a.x, q0a.y, q1a.y, ka[t].x, ka[t].y);
-              mma_16816(sc[t], q0a.z, q1a.z, q0a.w, q1a.w, ka[t].z, ka[t].w);
-              mma_16816(sc[t], q0b.x, q1b.x, q0b.y, q1b.y, kc[t].x, kc[t].y);
-              mma_16816(sc[t], q0b.z, q1b.z, q0b.w, q1b.w, kc[t].z, kc[t].w);
+              mma_16816(sc[t], q0a.x, q1a.x, q0a.y, q1a.y, cur.ka[t].x, cur.ka[t].y);
+              mma_16816(sc[t], q0a.z, q1a.z, q0a.w, q1a.w, cur.ka[t].z, cur.ka[t].w);
+              mma_16816(sc[t], q0b.x, q1b.x, q0b.y, q1b.y, cur.kc[t].x, cur.kc[t].y);
+              mma_16816(sc[t], q0b.z, q1b.z, q0b.w, q1b.w, cur.kc[t].z, cur.kc[t].w);
             }
             float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
@@ -475,46 +513,88 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
-              const uint32_t v0 = (&vv[0].x)[j >> 1], v1 = (&vv[1].x)[j >> 1], v2 = (&vv[2].x)[j >> 1], v3 = (&vv[3].x)[j >> 1];
+              const uint32_t v0 = (&cur.vv[0].x)[j >> 1], v1 = (&cur.vv[1].x)[j >> 1], v2 = (&cur.vv[2].x)[j >> 1], v3 = (&cur.vv[3].x)[j >> 1];
               mma_16816(o[j], pf[0], pf[1], pf[2], pf[3], prmt(v0, v1, sel), prmt(v2, v3, sel));
             }
+            cur = nxt;
           }
           l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
           l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
           l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
           l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
         }
-        // ---- merge the eight warps of this CTA (shared-memory reductions), then the four CTAs (DSMEM) ----
+        // ---- merge the eight warps of this CTA, then the four CTAs ----
+        // Warps 4-7 hand their flash state (m, l, O) to warps 0-3 through shared memory, which fold it into their own
+        // and publish the result; the sending threads below fold those four states while they read them.  (Shared-
+        // memory float atomics would be compare-and-swap loops: 10 us per layer when eight warps hit the same rows.)
         float* scr = reinterpret_cast<float*>(sm + K::S_SCR);
-        float* wm = scr + K::X_WM / 4;
-        if (q == 0) { wm[warp * 16 + g] = m0; wm[warp * 16 + g + 8] = m1; }
-        __syncthreads();
         {
-          float M0 = -INFINITY, M1 = -INFINITY;
+          float* mb = reinterpret_cast<float*>(sm + K::S_MRG) + (warp & 3) * MRG_BLK;     // [16][68] O, then [16][2] (m, l)
+          float* mlb = mb + 16 * MRG_P;
+          auto put = [&]() {
 #pragma unroll
-          for (int w = 0; w < CW; ++w) { M0 = fmaxf(M0, wm[w * 16 + g]); M1 = fmaxf(M1, wm[w * 16 + g + 8]); }
-          const float w0 = ex2w(m0, M0, sl2), w1 = ex2w(m1, M1, sl2);
-          if (m0 != -INFINITY || m1 != -INFINITY) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              atomicAdd(scr + g * 64 + 16 * q + j, o[j][0] * w0);
-              atomicAdd(scr + g * 64 + 16 * q + 8 + j, o[j][1] * w0);
-              atomicAdd(scr + (g + 8) * 64 + 16 * q + j, o[j][2] * w1);
-              atomicAdd(scr + (g + 8) * 64 + 16 * q + 8 + j, o[j][3] * w1);
+            for (int hf = 0; hf < 2; ++hf) {
+              float* r0p = mb + g * MRG_P + 16 * q + 8 * hf;
+              *reinterpret_cast<float4*>(r0p) = make_float4(o[0][hf], o[1][hf], o[2][hf], o[3][hf]);
+              *reinterpret_cast<float4*>(r0p + 4) = make_float4(o[4][hf], o[5][hf], o[6][hf], o[7][hf]);
+              float* r1p = r0p + 8 * MRG_P;
+              *reinterpret_cast<float4*>(r1p) = make_float4(o[0][2 + hf], o[1][2 + hf], o[2][2 + hf], o[3][2 + hf]);
+              *reinterpret_cast<float4*>(r1p + 4) = make_float4(o[4][2 + hf], o[5][2 + hf], o[6][2 + hf], o[7][2 + hf]);
             }
-            if (q == 0) { atomicAdd(scr + K::X_L / 4 + g, l0 * w0); atomicAdd(scr + K::X_L / 4 + g + 8, l1 * w1); }
+            if (q == 0) {
+              *reinterpret_cast<float2*>(mlb + 2 * g) = make_float2(m0, l0);
+              *reinterpret_cast<float2*>(mlb + 2 * (g + 8)) = make_float2(m1, l1);
+            }
+          };
+          if (warp >= 4) put();
+          __syncthreads();
+          if (warp < 4) {
+            const float2 p0 = *reinterpret_cast<const float2*>(mlb + 2 * g), p1 = *reinterpret_cast<const float2*>(mlb + 2 * (g + 8));
+            const float M0 = fmaxf(m0, p0.x), M1 = fmaxf(m1, p1.x);
+            const float wa0 = ex2w(m0, M0, sl2), wb0 = ex2w(p0.x, M0, sl2), wa1 = ex2w(m1, M1, sl2), wb1 = ex2w(p1.x, M1, sl2);
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              const float* r0p = mb + g * MRG_P + 16 * q + 8 * hf;
+              const float4 x0 = *reinterpret_cast<const float4*>(r0p), x1 = *reinterpret_cast<const float4*>(r0p + 4);
+              const float4 y0 = *reinterpret_cast<const float4*>(r0p + 8 * MRG_P), y1 = *reinterpret_cast<const float4*>(r0p + 8 * MRG_P + 4);
+              const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w}, ys[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                o[j][hf] = o[j][hf] * wa0 + xs[j] * wb0;
+                o[j][2 + hf] = o[j][2 + hf] * wa1 + ys[j] * wb1;
+              }
+            }
+            l0 = l0 * wa0 + p0.y * wb0; l1 = l1 * wa1 + p1.y * wb1;
+            m0 = M0; m1 = M1;
+            __syncwarp();
+            put();
           }
-          if (warp == 0 && q == 0) { scr[K::X_M / 4 + g] = M0; scr[K::X_M / 4 + g + 8] = M1; }
+          __syncthreads();
         }
-        __syncthreads();
         CL_TRACE(l, 4);
         {
           // CTA d merges the context columns [16 d, 16 d + 16): one 16-byte store per thread (row, destination, quarter)
           const int r = tid >> 4, d = (tid >> 2) & 3, qq = tid & 3;
+          const float* mb = reinterpret_cast<const float*>(sm + K::S_MRG);
+          float mv[4], lv[4], M = -INFINITY;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const float2 v = *reinterpret_cast<const float2*>(mb + b * MRG_BLK + 16 * MRG_P + 2 * r);
+            mv[b] = v.x; lv[b] = v.y;
+            M = fmaxf(M, v.x);
+          }
+          float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          float lsum = 0.f;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const float w = ex2w(mv[b], M, sl2);
+            const float4 v = *reinterpret_cast<const float4*>(mb + b * MRG_BLK + r * MRG_P + 16 * d + 4 * qq);
+            acc4.x = fmaf(v.x, w, acc4.x); acc4.y = fmaf(v.y, w, acc4.y); acc4.z = fmaf(v.z, w, acc4.z); acc4.w = fmaf(v.w, w, acc4.w);
+            lsum = fmaf(lv[b], w, lsum);
+          }
           st_cluster_v4(mapa(sb + K::S_SCR + K::X_RX2 + (uint32_t)(((rank * 16 + r) * 16 + 4 * qq) * 4), (uint32_t)d),
-                        *reinterpret_cast<const uint4*>(scr + r * 64 + 16 * d + 4 * qq));
-          if (qq == 0)
-            st_cluster_v2f(mapa(sb + K::S_SCR + K::X_ML + (uint32_t)((rank * 16 + r) * 8), (uint32_t)d), scr[K::X_M / 4 + r], scr[K::X_L / 4 + r]);
+                        make_uint4(__float_as_uint(acc4.x), __float_as_uint(acc4.y), __float_as_uint(acc4.z), __float_as_uint(acc4.w)));
+          if (qq == 0) st_cluster_v2f(mapa(sb + K::S_SCR + K::X_ML + (uint32_t)((rank * 16 + r) * 8), (uint32_t)d), M, lsum);
         }
         cluster_sync();
         CL_TRACE(l, 5);
@@ -564,6 +644,7 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
     } else {
       // ================= fc1 for the cluster's hidden units: K split over the CTAs, reduce-scatter =================
       ok = wait_piece(4 * l + 2) && ok;
+      CL_TRACE(l, 16);
       {
         float acc[2][K::NT1C][4] = {};
         uint32_t bb[K::NT1C];
@@ -612,6 +693,7 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
       CL_TRACE(l, 11);
       // ================= fc2 restricted to the cluster's hidden units: this CTA's D/4 output columns =================
       ok = wait_piece(4 * l + 3) && ok;
+      CL_TRACE(l, 17);
       if (warp * K::NT2 * 8 < K::NO) {
         float acc[2][K::NT2][4] = {};
         uint32_t bb[K::NT2];
@@ -801,7 +883,7 @@ w2vs_status_t launch_stream_cluster(const StreamFusedArgs& h, cudaStream_t st) {
 }
 
 w2vs_status_t debug_read_cluster_trace(unsigned long long* out, int n) {
-  if (n > 64 * 16) n = 64 * 16;
+  if (n > 64 * 24) n = 64 * 24;
   cudaError_t e = cudaMemcpyFromSymbol(out, g_cluster_trace, (size_t)n * 8);
   if (e != cudaSuccess) { set_error("read g_cluster_trace: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
   return W2VS_OK;
