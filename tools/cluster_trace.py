@@ -43,9 +43,9 @@ if impl == 3:
     buf = (C.c_uint64 * (64 * 24))()
     cabi.check(cabi.lib().w2vs_debug_cluster_trace(buf, len(buf)), "trace")
     t = np.frombuffer(buf, dtype=np.uint64).astype(np.int64).reshape(64, 24)[:24]
-    ev = [0, 1, 15, 2, 3, 4, 5, 6, 7, 13, 8, 9, 16, 10, 11, 17, 12, 14]
-    names = ["LN+stats", "wait weights", "QKV+scatter", "reduce+gather", "attention", "merge-send", "merge+ctx gather",
-             "out_proj", "grid barrier", "(next phase start)", "LN+stats", "wait weights", "fc1+scatter", "gelu+gather",
+    ev = [0, 18, 19, 1, 15, 2, 3, 4, 5, 6, 7, 13, 8, 20, 21, 9, 16, 10, 11, 17, 12, 14]
+    names = ["x slice + local stats", "stats exchange", "normalise", "wait weights", "QKV+scatter", "reduce+gather", "attention", "merge-send", "merge+ctx gather",
+             "out_proj", "grid barrier", "(next phase start)", "x slice + local stats", "stats exchange", "normalise", "wait weights", "fc1+scatter", "gelu+gather",
              "wait weights", "fc2", "grid barrier"]
     seq = t[:, ev]
     d = np.diff(seq, axis=1) / 1e3

@@ -101,7 +101,7 @@ struct CK {
   static constexpr int S_CTX = S_G + G_B;
   static constexpr int S_MRG = S_CTX + 16 * PO;                       // attention merge: 4 x ([16][68] O + [16][2] (m, l)) fp32
   static constexpr int S_BAR = S_MRG + 4 * MRG_BLK * 4;
-  static constexpr int S_END = S_BAR + 64;
+  static constexpr int S_END = S_BAR + 128;
   // phase A scratch after the reduce: rx2 [4][16][16], ml_rx [4][16][2]   (fp32, written by the peers)
   static constexpr int X_RX2 = 8192, X_ML = 12288;
   static_assert(D % 128 == 0 && D == 64 * H && HC % 64 == 0 && KS % 16 == 0, "model shape");
@@ -123,11 +123,16 @@ __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
 __device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t (&r)[2]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
 }
-__device__ __forceinline__ void st_cluster_v2f(uint32_t addr, float a, float b) {
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+// Remote shared-memory stores that count their bytes on an mbarrier of the DESTINATION CTA (st.async): the receiver
+// waits on its own barrier for the bytes it expects -- no fence on the sender, no cluster-wide barrier.  (With plain
+// st.shared::cluster + barrier.cluster the release fence of every barrier cost ~0.6 us: 18 % of the kernel's samples.)
+__device__ __forceinline__ void st_async_v2f(uint32_t addr, float a, float b, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1,%2}, [%3];"
+               ::"r"(addr), "f"(a), "f"(b), "r"(mbar) : "memory");
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
-  asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+__device__ __forceinline__ void st_async_v4(uint32_t addr, uint4 v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.u32 [%0], {%1,%2,%3,%4}, [%5];"
+               ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar) : "memory");
 }
 __device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
   asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
@@ -209,6 +214,9 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
   const bool two_mt = Mt > 16;
   const float sl2 = a.scale_log2;
   const uint32_t bar_slot = sb + K::S_BAR;
+  // shared-window base of every CTA of the cluster (mapa reads a special register: once, not per store)
+  const uint32_t rb0 = mapa(sb, 0), rb1 = mapa(sb, 1), rb2 = mapa(sb, 2), rb3 = mapa(sb, 3);
+  auto rbase = [&](int d) { return d == 0 ? rb0 : (d == 1 ? rb1 : (d == 2 ? rb2 : rb3)); };
   const uint8_t* wc_cta = a.W + a.wc + (size_t)gid * K::CTA_B;     // + layer * layer_stride
 
   // ---- weight pieces: piece i = 4 layer + {0 q|k, 1 v + out_proj, 2 fc1, 3 fc2} lives in slot i & 1; thread 0
@@ -243,8 +251,12 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
       else if (tid < 32 + 2) prefetch_l2(Wl + a.b1 + 4 * (cl * K::HC + rank * K::HR) + 128 * (tid - 32));
     }
   };
+  // exchange barriers (byte-counting, one use per layer): phase A statistics, partial q|k|v, gathered q|k|v, attention
+  // partials, gathered context; phase C statistics, partial hidden units, gathered hidden units
+  constexpr uint32_t XB_ASTAT = 16, XB_ARX1 = 24, XB_AG = 32, XB_ARX2 = 40, XB_ACTX = 48, XB_CSTAT = 56, XB_CRX1 = 64, XB_CG = 72;
   if (tid == 0) {
     mbar_init(bar_slot, 1); mbar_init(bar_slot + 8, 1);
+    for (uint32_t o = XB_ASTAT; o <= XB_CG; o += 8) mbar_init(bar_slot + o, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     issue_piece(0); issue_piece(1);
   }
@@ -278,8 +290,6 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
     float* Xout = a.X + (size_t)((ph + 1) % 3) * ROWS * D;
     const uint8_t* Wl = a.W + (size_t)l * a.layer_stride;
     CL_TRACE(l, pa ? 0 : 8);
-    // zero the buffer the NEXT phase accumulates into (it was last read in the previous phase)
-    a.X[(size_t)((ph + 2) % 3) * ROWS * D + gid * CT + tid] = 0.f;
     // the small parameter vectors of the NEXT phase (first touched there: a DRAM miss on its critical path otherwise)
     prefetch_params(ph + 1);
     if (pa && 16 * (cl & 1) < Mt) {
@@ -291,16 +301,42 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
       }
     }
 
+    const bool a_on = !pa || 16 * (cl & 1) < Mt;      // phase A: does this cluster's query tile exist in this step?
+    const uint32_t lpar = (uint32_t)l & 1u;           // every exchange barrier completes one phase per layer
+    if (tid == 0) {
+      if (pa) {
+        mbar_expect_tx(bar_slot + XB_ASTAT, CL * ROWS * 8);
+        if (a_on) {
+          mbar_expect_tx(bar_slot + XB_ARX1, (uint32_t)(CL * Mt * 48 * 4));
+          mbar_expect_tx(bar_slot + XB_AG, (uint32_t)(CL * Mt * 96));
+          mbar_expect_tx(bar_slot + XB_ARX2, CL * 16 * (64 + 8));
+          mbar_expect_tx(bar_slot + XB_ACTX, CL * 16 * 32);
+        }
+      } else {
+        mbar_expect_tx(bar_slot + XB_CSTAT, CL * ROWS * 8);
+        mbar_expect_tx(bar_slot + XB_CRX1, (uint32_t)(CL * Mt * K::HR * 4));
+        mbar_expect_tx(bar_slot + XB_CG, (uint32_t)(CL * Mt * K::HR * 2));
+      }
+    }
+    // The residual term of the second product (x + bias): the rows are dealt to the clusters (row r -> cluster r % NC),
+    // a cluster's CTAs split the columns: 64 float4 per CTA.  Loaded now, added at the end of the phase.
+    float4 res_x = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int res_row = cl + K::NC * (tid / (K::NO / 4)), res_col = rank * K::NO + 4 * (tid % (K::NO / 4));
+    const bool res_on = tid < 64 && res_row < Mt;
+    if (res_on) {
+      const float4 xr = __ldcg(reinterpret_cast<const float4*>(Xin + (size_t)res_row * D + res_col));
+      const float4 b = *reinterpret_cast<const float4*>(Wl + (pa ? a.bo : a.b2) + 4 * res_col);
+      res_x = make_float4(xr.x + b.x, xr.y + b.y, xr.z + b.z, xr.w + b.w);
+    }
     // ================= LayerNorm of the K slice =================
-    float4 x[4][K::NV4], gm[K::NV4], bt[K::NV4], b2v[K::NV4];
+    float4 x[4][K::NV4], gm[K::NV4], bt[K::NV4];
 #pragma unroll
     for (int j = 0; j < K::NV4; ++j) {
       const int c = 4 * lane + 128 * j;
-      gm[j] = bt[j] = b2v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      gm[j] = bt[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c < K::KS) {
         gm[j] = *reinterpret_cast<const float4*>(Wl + (pa ? a.ln1_w : a.ln2_w) + 4 * (rank * K::KS + c));
         bt[j] = *reinterpret_cast<const float4*>(Wl + (pa ? a.ln1_b : a.ln2_b) + 4 * (rank * K::KS + c));
-        b2v[j] = *reinterpret_cast<const float4*>(Wl + (pa ? a.bo : a.b2) + 4 * (rank * K::KS + c));
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -317,27 +353,24 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
       for (int j = 0; j < K::NV4; ++j) s += (x[i][j].x + x[i][j].y) + (x[i][j].z + x[i][j].w);
       const float mean = warp_sum(s) * (1.0f / K::KS);
       float d2 = 0.f;
-      const int r = 4 * warp + i;
 #pragma unroll
       for (int j = 0; j < K::NV4; ++j)
         if (4 * lane + 128 * j < K::KS) {
           const float d0 = x[i][j].x - mean, d1 = x[i][j].y - mean, d2_ = x[i][j].z - mean, d3 = x[i][j].w - mean;
           d2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2_, d2_, fmaf(d3, d3, d2))));
-          // the residual term of the second product: rows are dealt to the clusters, the CTA that holds the slice adds it
-          if (r < Mt && (r % K::NC) == cl)
-            red_add_v4(Xout + (size_t)r * D + rank * K::KS + 4 * lane + 128 * j,
-                       make_float4(x[i][j].x + b2v[j].x, x[i][j].y + b2v[j].y, x[i][j].z + b2v[j].z, x[i][j].w + b2v[j].w));
         }
       mean_i[i] = mean;
       m2_i[i] = warp_sum(d2);
     }
+    CL_TRACE(l, pa ? 18 : 20);
     if (lane < CL) {
-      const uint32_t dst = mapa(sb + K::S_STAT + (uint32_t)((rank * ROWS + 4 * warp) * 8), (uint32_t)lane);
+      const uint32_t dst = rbase(lane) + K::S_STAT + (uint32_t)((rank * ROWS + 4 * warp) * 8);
+      const uint32_t mb = rbase(lane) + K::S_BAR + (pa ? XB_ASTAT : XB_CSTAT);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) st_cluster_v2f(dst + i * 8, mean_i[i], m2_i[i]);
+      for (int i = 0; i < 4; ++i) st_async_v2f(dst + i * 8, mean_i[i], m2_i[i], mb);
     }
-    cluster_sync();
-    const bool a_on = !pa || 16 * (cl & 1) < Mt;      // phase A: does this cluster's query tile exist in this step?
+    ok = mbar_wait(bar_slot + (pa ? XB_ASTAT : XB_CSTAT), lpar) && ok;
+    CL_TRACE(l, pa ? 19 : 21);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = 4 * warp + i;
@@ -379,20 +412,21 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
           bb[nt] = n < 16 ? sb + K::S_SLOT0 + (uint32_t)(n * 8) * K::PQ : sb + K::S_SLOT1 + (uint32_t)((n - 16) * 8) * K::PQ;
         }
         mma_block<3, K::KS / 16, K::PQ, K::PQ>(sb + K::S_A, bb, acc, lane, two_mt);
-        const uint32_t dst = mapa(sb + K::S_SCR + (uint32_t)(rank * ROWS * 48 * 4), (uint32_t)(warp >> 1));
+        const uint32_t dst = rbase((warp >> 1)) + K::S_SCR + (uint32_t)(rank * ROWS * 48 * 4);
+        const uint32_t mb = rbase((warp >> 1)) + K::S_BAR + XB_ARX1;
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
           for (int nt = 0; nt < 3; ++nt) {
             const int r0 = mt * 16 + g, c = (warp & 1) * 24 + nt * 8 + 2 * q;
-            if (r0 < Mt) st_cluster_v2f(dst + (uint32_t)((r0 * 48 + c) * 4), acc[mt][nt][0], acc[mt][nt][1]);
-            if (r0 + 8 < Mt) st_cluster_v2f(dst + (uint32_t)(((r0 + 8) * 48 + c) * 4), acc[mt][nt][2], acc[mt][nt][3]);
+            if (r0 < Mt) st_async_v2f(dst + (uint32_t)((r0 * 48 + c) * 4), acc[mt][nt][0], acc[mt][nt][1], mb);
+            if (r0 + 8 < Mt) st_async_v2f(dst + (uint32_t)(((r0 + 8) * 48 + c) * 4), acc[mt][nt][2], acc[mt][nt][3], mb);
           }
+        __syncthreads();       // all warps are past their reads of the operand slice: its memory becomes the staging rows
+        ok = mbar_wait(bar_slot + XB_ARX1, lpar) && ok;
       }
-      cluster_sync();
-      // every warp of this CTA is past its reads of the q|k rows: request fc1's rows into that slot
-      if (tid == 0) issue_piece(4 * l + 2);
       CL_TRACE(l, 2);
+      if (!a_on && tid == 0) issue_piece(4 * l + 2);
       if (a_on) {
         // ---- reduce, bias, bf16, all-gather; K / V rows -> cache (by the cluster of the head's first query tile) ----
         uint32_t* stage = reinterpret_cast<uint32_t*>(sm + K::S_A);          // [32][24] bf16 pairs
@@ -410,22 +444,15 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
           stage[it] = pack_bf16x2(v0, v1);
         }
         __syncthreads();
+        // every warp of this CTA is past its reads of the q|k rows: request fc1's rows into that slot
+        if (tid == 0) issue_piece(4 * l + 2);
         for (int idx = tid; idx < Mt * 6 * CL; idx += CT) {
           const int d = idx & (CL - 1), rc_ = idx >> 2, r = rc_ / 6, ch = rc_ - 6 * r;
           const uint4 v = *reinterpret_cast<const uint4*>(sm + K::S_A + r * 96 + ch * 16);
-          st_cluster_v4(mapa(sb + K::S_G + (uint32_t)(r * K::PG + rank * 96 + ch * 16), (uint32_t)d), v);
+          st_async_v4(rbase(d) + K::S_G + (uint32_t)(r * K::PG + rank * 96 + ch * 16), v, rbase(d) + K::S_BAR + XB_AG);
         }
-        if (mtile == 0) {
-          bf16* kv_l = a.kv + (size_t)l * a.kv_layer_elems;
-          for (int idx = tid; idx < Mt * 6; idx += CT) {
-            const int r = idx / 6, ch = idx - 6 * r, col0 = 48 * rank + 8 * ch, part = col0 >> 6;
-            if (part >= 1)
-              *reinterpret_cast<uint4*>(kv_l + (size_t)(a.f0 + r) * (2 * D) + (size_t)(part - 1) * D + head * 64 + (col0 & 63)) =
-                  *reinterpret_cast<const uint4*>(sm + K::S_A + r * 96 + ch * 16);
-          }
-        }
+        ok = mbar_wait(bar_slot + XB_AG, lpar) && ok;
       }
-      cluster_sync();
       CL_TRACE(l, 3);
 
       if (a_on) {
@@ -592,11 +619,12 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
             acc4.x = fmaf(v.x, w, acc4.x); acc4.y = fmaf(v.y, w, acc4.y); acc4.z = fmaf(v.z, w, acc4.z); acc4.w = fmaf(v.w, w, acc4.w);
             lsum = fmaf(lv[b], w, lsum);
           }
-          st_cluster_v4(mapa(sb + K::S_SCR + K::X_RX2 + (uint32_t)(((rank * 16 + r) * 16 + 4 * qq) * 4), (uint32_t)d),
-                        make_uint4(__float_as_uint(acc4.x), __float_as_uint(acc4.y), __float_as_uint(acc4.z), __float_as_uint(acc4.w)));
-          if (qq == 0) st_cluster_v2f(mapa(sb + K::S_SCR + K::X_ML + (uint32_t)((rank * 16 + r) * 8), (uint32_t)d), M, lsum);
+          st_async_v4(rbase(d) + K::S_SCR + K::X_RX2 + (uint32_t)(((rank * 16 + r) * 16 + 4 * qq) * 4),
+                      make_uint4(__float_as_uint(acc4.x), __float_as_uint(acc4.y), __float_as_uint(acc4.z), __float_as_uint(acc4.w)),
+                      rbase(d) + K::S_BAR + XB_ARX2);
+          if (qq == 0) st_async_v2f(rbase(d) + K::S_SCR + K::X_ML + (uint32_t)((rank * 16 + r) * 8), M, lsum, rbase(d) + K::S_BAR + XB_ARX2);
         }
-        cluster_sync();
+        ok = mbar_wait(bar_slot + XB_ARX2, lpar) && ok;
         CL_TRACE(l, 5);
         {
           const int r = tid >> 4, cc = tid & 15;
@@ -618,10 +646,10 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
         __syncthreads();
         if (tid < 16 * 2 * CL) {
           const int r = tid >> 3, ch = (tid >> 2) & 1, d = tid & 3;
-          st_cluster_v4(mapa(sb + K::S_CTX + (uint32_t)(r * K::PO + rank * 32 + ch * 16), (uint32_t)d),
-                        *reinterpret_cast<const uint4*>(sm + K::S_A + r * 32 + ch * 16));
+          st_async_v4(rbase(d) + K::S_CTX + (uint32_t)(r * K::PO + rank * 32 + ch * 16),
+                      *reinterpret_cast<const uint4*>(sm + K::S_A + r * 32 + ch * 16), rbase(d) + K::S_BAR + XB_ACTX);
         }
-        cluster_sync();
+        ok = mbar_wait(bar_slot + XB_ACTX, lpar) && ok;
         CL_TRACE(l, 6);
         // ================= out_proj restricted to the head: this CTA's D/4 output columns, 16 rows =================
         if (warp * K::NT2 * 8 < K::NO) {
@@ -635,6 +663,15 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
             const int r0 = mtile * 16 + g, col = rank * K::NO + (warp * K::NT2 + nt) * 8 + 2 * q;
             if (r0 < Mt) red_add_v2(Xout + (size_t)r0 * D + col, acc[0][nt][0], acc[0][nt][1]);
             if (r0 + 8 < Mt) red_add_v2(Xout + (size_t)(r0 + 8) * D + col, acc[0][nt][2], acc[0][nt][3]);
+          }
+        }
+        if (mtile == 0) {
+          // this step's K / V rows of the head -> cache (every CTA holds the gathered rows: each writes a quarter)
+          bf16* kv_l = a.kv + (size_t)l * a.kv_layer_elems;
+          for (int idx = rank * CT + tid; idx < Mt * 16; idx += CL * CT) {
+            const int r = idx >> 4, ch = idx & 15;            // 16-byte chunk ch of [k | v] (8 + 8 chunks)
+            *reinterpret_cast<uint4*>(kv_l + (size_t)(a.f0 + r) * (2 * D) + (size_t)(ch >> 3) * D + head * 64 + (ch & 7) * 8) =
+                *reinterpret_cast<const uint4*>(sm + K::S_G + r * K::PG + 128 + ch * 16);
           }
         }
       }
@@ -651,18 +688,19 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
 #pragma unroll
         for (int nt = 0; nt < K::NT1C; ++nt) bb[nt] = sb + K::S_SLOT0 + (uint32_t)((warp * K::NT1C + nt) * 8) * K::PQ;
         mma_block<K::NT1C, K::KS / 16, K::PQ, K::PQ>(sb + K::S_A, bb, acc, lane, two_mt);
-        const uint32_t dst = mapa(sb + K::S_SCR + (uint32_t)(rank * ROWS * K::HR * 4), (uint32_t)(warp >> 1));
+        const uint32_t dst = rbase((warp >> 1)) + K::S_SCR + (uint32_t)(rank * ROWS * K::HR * 4);
+        const uint32_t mb = rbase((warp >> 1)) + K::S_BAR + XB_CRX1;
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
           for (int nt = 0; nt < K::NT1C; ++nt) {
             const int r0 = mt * 16 + g, c = ((warp & 1) * K::NT1C + nt) * 8 + 2 * q;
-            if (r0 < Mt) st_cluster_v2f(dst + (uint32_t)((r0 * K::HR + c) * 4), acc[mt][nt][0], acc[mt][nt][1]);
-            if (r0 + 8 < Mt) st_cluster_v2f(dst + (uint32_t)(((r0 + 8) * K::HR + c) * 4), acc[mt][nt][2], acc[mt][nt][3]);
+            if (r0 < Mt) st_async_v2f(dst + (uint32_t)((r0 * K::HR + c) * 4), acc[mt][nt][0], acc[mt][nt][1], mb);
+            if (r0 + 8 < Mt) st_async_v2f(dst + (uint32_t)(((r0 + 8) * K::HR + c) * 4), acc[mt][nt][2], acc[mt][nt][3], mb);
           }
       }
-      cluster_sync();
-      if (tid == 0) issue_piece(4 * l + 4);      // next layer's q|k rows
+      __syncthreads();         // all warps are past their reads of the operand slice: its memory becomes the staging rows
+      ok = mbar_wait(bar_slot + XB_CRX1, lpar) && ok;
       CL_TRACE(l, 10);
       // ---- reduce, bias, GELU, bf16, all-gather ----
       {
@@ -682,14 +720,15 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
           stage[it] = pack_bf16x2(gelu_tanh(v0), gelu_tanh(v1));
         }
         __syncthreads();
+        if (tid == 0) issue_piece(4 * l + 4);      // every warp is past fc1's rows: next layer's q|k rows into that slot
         constexpr int CH = K::HR * 2 / 16;       // 16-byte chunks per row
         for (int idx = tid; idx < Mt * CH * CL; idx += CT) {
           const int d = idx & (CL - 1), rc_ = idx >> 2, r = rc_ / CH, ch = rc_ - CH * r;
           const uint4 v = *reinterpret_cast<const uint4*>(sm + K::S_A + r * (K::HR * 2) + ch * 16);
-          st_cluster_v4(mapa(sb + K::S_G + (uint32_t)(r * K::PH + rank * (K::HR * 2) + ch * 16), (uint32_t)d), v);
+          st_async_v4(rbase(d) + K::S_G + (uint32_t)(r * K::PH + rank * (K::HR * 2) + ch * 16), v, rbase(d) + K::S_BAR + XB_CG);
         }
       }
-      cluster_sync();
+      ok = mbar_wait(bar_slot + XB_CG, lpar) && ok;
       CL_TRACE(l, 11);
       // ================= fc2 restricted to the cluster's hidden units: this CTA's D/4 output columns =================
       ok = wait_piece(4 * l + 3) && ok;
@@ -713,6 +752,10 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
       if (tid == 0) issue_piece(4 * l + 5);      // next layer's v + out_proj rows
       CL_TRACE(l, 12);
     }
+    // zero the buffer the NEXT phase accumulates into (it was last read in the previous phase).  Global writes sit at
+    // the end of a phase: before a cluster barrier they would hold up its release fence for an L2 round trip.
+    a.X[(size_t)((ph + 2) % 3) * ROWS * D + gid * CT + tid] = 0.f;
+    if (res_on) red_add_v4(Xout + (size_t)res_row * D + res_col, res_x);
     ok = grid_barrier(a.bar, ++nbar * G) && ok;
     CL_TRACE(l, pa ? 13 : 14);
   }
