@@ -111,7 +111,7 @@ struct CK {
 // ---- small PTX helpers ----
 __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                           uint32_t b0, uint32_t b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
@@ -150,6 +150,18 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   return r;
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// four independent warp sums in lock step (shuffles are convergent operations the compiler keeps in program order:
+// four separate warp_sum calls are twenty dependent shuffle latencies, this is five)
+__device__ __forceinline__ void warp_sum4(float (&v)[4]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float t[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t[i] = __shfl_xor_sync(0xffffffffu, v[i], o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] += t[i];
+  }
+}
 __device__ __forceinline__ float ex2w(float m, float M, float sl2) { return m == -INFINITY ? 0.f : ex2_approx((m - M) * sl2); }
 
 // Grid-wide barrier (all CTAs are co-resident: one per SM, the launcher checked the occupancy).  One arrival counter
@@ -185,17 +197,24 @@ template <int NTW, int KSTEPS, int PA, int PB>
 __device__ __forceinline__ void mma_block(uint32_t a_base, const uint32_t (&bb)[NTW], float (&acc)[2][NTW][4], int lane, bool two_mt) {
   const uint32_t a_lane = a_base + (uint32_t)(lane & 15) * PA + (uint32_t)(lane >> 4) * 16;
   const uint32_t b_lane = (uint32_t)(lane & 7) * PB + (uint32_t)((lane >> 3) & 1) * 16;
+  // the fragments of k step ks + 1 are requested before the MMAs of step ks are issued (the ldmatrix asm statements
+  // are volatile and stay in program order: without the look-ahead every step would wait for its own loads)
+  uint32_t af[2][2][4], bf[2][NTW][2];
+  auto load = [&](int ks, int buf) {
+    ldsm_x4(a_lane + ks * 32, af[buf][0]);
+    if (two_mt) ldsm_x4(a_lane + 16 * PA + ks * 32, af[buf][1]);
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt) ldsm_x2(bb[nt] + b_lane + ks * 32, bf[buf][nt]);
+  };
+  load(0, 0);
 #pragma unroll
   for (int ks = 0; ks < KSTEPS; ++ks) {
-    uint32_t af[2][4];
-    ldsm_x4(a_lane + ks * 32, af[0]);
-    if (two_mt) ldsm_x4(a_lane + 16 * PA + ks * 32, af[1]);
+    const int cur = ks & 1;
+    if (ks + 1 < KSTEPS) load(ks + 1, cur ^ 1);
 #pragma unroll
     for (int nt = 0; nt < NTW; ++nt) {
-      uint32_t bf[2];
-      ldsm_x2(bb[nt] + b_lane + ks * 32, bf);
-      mma_16816(acc[0][nt], af[0][0], af[0][1], af[0][2], af[0][3], bf[0], bf[1]);
-      if (two_mt) mma_16816(acc[1][nt], af[1][0], af[1][1], af[1][2], af[1][3], bf[0], bf[1]);
+      mma_16816(acc[0][nt], af[cur][0][0], af[cur][0][1], af[cur][0][2], af[cur][0][3], bf[cur][nt][0], bf[cur][nt][1]);
+      if (two_mt) mma_16816(acc[1][nt], af[cur][1][0], af[cur][1][1], af[cur][1][2], af[cur][1][3], bf[cur][nt][0], bf[cur][nt][1]);
     }
   }
 }
@@ -290,17 +309,6 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
     float* Xout = a.X + (size_t)((ph + 1) % 3) * ROWS * D;
     const uint8_t* Wl = a.W + (size_t)l * a.layer_stride;
     CL_TRACE(l, pa ? 0 : 8);
-    // the small parameter vectors of the NEXT phase (first touched there: a DRAM miss on its critical path otherwise)
-    prefetch_params(ph + 1);
-    if (pa && 16 * (cl & 1) < Mt) {
-      // this warp's past K / V rows of head cl / 2 -> L2 (one 128-byte line per lane: 16 keys x {K, V} per step)
-      const uint8_t* kv_h = reinterpret_cast<const uint8_t*>(a.kv + (size_t)l * a.kv_layer_elems + (cl >> 1) * 64);
-      for (int s = rank * CW + warp; 16 * s < a.f0; s += CL * CW) {
-        const int key = min(16 * s + (lane & 15), a.f0 - 1);
-        prefetch_l2(kv_h + (size_t)key * (4 * D) + (lane >> 4) * (2 * D));
-      }
-    }
-
     const bool a_on = !pa || 16 * (cl & 1) < Mt;      // phase A: does this cluster's query tile exist in this step?
     const uint32_t lpar = (uint32_t)l & 1u;           // every exchange barrier completes one phase per layer
     if (tid == 0) {
@@ -317,16 +325,6 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
         mbar_expect_tx(bar_slot + XB_CRX1, (uint32_t)(CL * Mt * K::HR * 4));
         mbar_expect_tx(bar_slot + XB_CG, (uint32_t)(CL * Mt * K::HR * 2));
       }
-    }
-    // The residual term of the second product (x + bias): the rows are dealt to the clusters (row r -> cluster r % NC),
-    // a cluster's CTAs split the columns: 64 float4 per CTA.  Loaded now, added at the end of the phase.
-    float4 res_x = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int res_row = cl + K::NC * (tid / (K::NO / 4)), res_col = rank * K::NO + 4 * (tid % (K::NO / 4));
-    const bool res_on = tid < 64 && res_row < Mt;
-    if (res_on) {
-      const float4 xr = __ldcg(reinterpret_cast<const float4*>(Xin + (size_t)res_row * D + res_col));
-      const float4 b = *reinterpret_cast<const float4*>(Wl + (pa ? a.bo : a.b2) + 4 * res_col);
-      res_x = make_float4(xr.x + b.x, xr.y + b.y, xr.z + b.z, xr.w + b.w);
     }
     // ================= LayerNorm of the K slice =================
     float4 x[4][K::NV4], gm[K::NV4], bt[K::NV4];
@@ -345,13 +343,39 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
                                         : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
+    // The residual term of the second product (x + bias): the rows are dealt to the clusters (row r -> cluster r % NC),
+    // a cluster's CTAs split the columns: 64 float4 per CTA.  Loaded now, added at the end of the phase.
+    float4 res_x = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int res_row = cl + K::NC * (tid / (K::NO / 4)), res_col = rank * K::NO + 4 * (tid % (K::NO / 4));
+    const bool res_on = tid < 64 && res_row < Mt;
+    if (res_on) {
+      const float4 xr = __ldcg(reinterpret_cast<const float4*>(Xin + (size_t)res_row * D + res_col));
+      const float4 b = *reinterpret_cast<const float4*>(Wl + (pa ? a.bo : a.b2) + 4 * res_col);
+      res_x = make_float4(xr.x + b.x, xr.y + b.y, xr.z + b.z, xr.w + b.w);
+    }
+    // the small parameter vectors of the NEXT phase (first touched there: a DRAM miss on its critical path otherwise)
+    prefetch_params(ph + 1);
+    if (pa && 16 * (cl & 1) < Mt) {
+      // this warp's past K / V rows of head cl / 2 -> L2 (one 128-byte line per lane: 16 keys x {K, V} per step)
+      const uint8_t* kv_h = reinterpret_cast<const uint8_t*>(a.kv + (size_t)l * a.kv_layer_elems + (cl >> 1) * 64);
+      for (int s = rank * CW + warp; 16 * s < a.f0; s += CL * CW) {
+        const int key = min(16 * s + (lane & 15), a.f0 - 1);
+        prefetch_l2(kv_h + (size_t)key * (4 * D) + (lane >> 4) * (2 * D));
+      }
+    }
+
     float mean_i[4], m2_i[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float s = 0.f;
 #pragma unroll
       for (int j = 0; j < K::NV4; ++j) s += (x[i][j].x + x[i][j].y) + (x[i][j].z + x[i][j].w);
-      const float mean = warp_sum(s) * (1.0f / K::KS);
+      mean_i[i] = s;
+    }
+    warp_sum4(mean_i);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float mean = mean_i[i] * (1.0f / K::KS);
       float d2 = 0.f;
 #pragma unroll
       for (int j = 0; j < K::NV4; ++j)
@@ -360,8 +384,9 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
           d2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2_, d2_, fmaf(d3, d3, d2))));
         }
       mean_i[i] = mean;
-      m2_i[i] = warp_sum(d2);
+      m2_i[i] = d2;
     }
+    warp_sum4(m2_i);
     CL_TRACE(l, pa ? 18 : 20);
     if (lane < CL) {
       const uint32_t dst = rbase(lane) + K::S_STAT + (uint32_t)((rank * ROWS + 4 * warp) * 8);
@@ -371,28 +396,40 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
     }
     ok = mbar_wait(bar_slot + (pa ? XB_ASTAT : XB_CSTAT), lpar) && ok;
     CL_TRACE(l, pa ? 19 : 21);
+    {
+      float ms[4], qs[4], mean[4], m2[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = 4 * warp + i;
-      float ms = 0.f, qs = 0.f;
-      if (lane < CL) {
-        const float2 v = *reinterpret_cast<const float2*>(sm + K::S_STAT + (lane * ROWS + r) * 8);
-        ms = v.x; qs = v.y;
-      }
-      const float mean = warp_sum(ms) * (1.0f / CL);
-      const float dev = lane < CL ? ms - mean : 0.f;
-      const float m2 = warp_sum(fmaf((float)K::KS * dev, dev, qs));
-      const float rstd = 1.0f / sqrtf(m2 * (1.0f / D) + 1e-5f);
-#pragma unroll
-      for (int j = 0; j < K::NV4; ++j)
-        if (4 * lane + 128 * j < K::KS) {
-          uint2 u = make_uint2(0u, 0u);
-          if (r < Mt) {
-            u.x = pack_bf16x2((x[i][j].x - mean) * rstd * gm[j].x + bt[j].x, (x[i][j].y - mean) * rstd * gm[j].y + bt[j].y);
-            u.y = pack_bf16x2((x[i][j].z - mean) * rstd * gm[j].z + bt[j].z, (x[i][j].w - mean) * rstd * gm[j].w + bt[j].w);
-          }
-          *reinterpret_cast<uint2*>(sm + K::S_A + r * K::PQ + 2 * (4 * lane + 128 * j)) = u;
+      for (int i = 0; i < 4; ++i) {
+        ms[i] = qs[i] = 0.f;
+        if (lane < CL) {
+          const float2 v = *reinterpret_cast<const float2*>(sm + K::S_STAT + (lane * ROWS + 4 * warp + i) * 8);
+          ms[i] = v.x; qs[i] = v.y;
         }
+        mean[i] = ms[i];
+      }
+      warp_sum4(mean);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        mean[i] *= 1.0f / CL;
+        const float dev = lane < CL ? ms[i] - mean[i] : 0.f;
+        m2[i] = fmaf((float)K::KS * dev, dev, qs[i]);
+      }
+      warp_sum4(m2);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = 4 * warp + i;
+        const float rstd = 1.0f / sqrtf(m2[i] * (1.0f / D) + 1e-5f), mu = mean[i];
+#pragma unroll
+        for (int j = 0; j < K::NV4; ++j)
+          if (4 * lane + 128 * j < K::KS) {
+            uint2 u = make_uint2(0u, 0u);
+            if (r < Mt) {
+              u.x = pack_bf16x2((x[i][j].x - mu) * rstd * gm[j].x + bt[j].x, (x[i][j].y - mu) * rstd * gm[j].y + bt[j].y);
+              u.y = pack_bf16x2((x[i][j].z - mu) * rstd * gm[j].z + bt[j].z, (x[i][j].w - mu) * rstd * gm[j].w + bt[j].w);
+            }
+            *reinterpret_cast<uint2*>(sm + K::S_A + r * K::PQ + 2 * (4 * lane + 128 * j)) = u;
+          }
+      }
     }
     __syncthreads();
     CL_TRACE(l, pa ? 1 : 9);
@@ -400,6 +437,28 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
     if (pa) {
       // ================= q | k | v of head cl / 2 (all rows): K split over the CTAs, reduce-scatter =================
       const int head = cl >> 1, mtile = cl & 1;
+      // K / V fragments of one attention step (16 keys) of this warp: key-split group grp takes steps grp, grp + 32, ...
+      struct KVF { uint4 ka[2], kc[2], vv[4]; int valid; };
+      const int grp = rank * CW + warp;
+      const int n_past = (a.f0 + 15) >> 4, n_steps = n_past + ((Mt + 15) >> 4);
+      const uint8_t* kv_h = reinterpret_cast<const uint8_t*>(a.kv + (size_t)l * a.kv_layer_elems + head * 64);
+      auto load_step = [&](int s, KVF& f) {
+        const uint8_t* kb; size_t pitch; int voff;
+        if (s < n_past) { kb = kv_h + (size_t)(16 * s) * (4 * D); pitch = 4 * D; f.valid = min(16, a.f0 - 16 * s); voff = 2 * D; }
+        else { const int t0 = 16 * (s - n_past); kb = sm + K::S_G + t0 * K::PG + 128; pitch = K::PG; f.valid = min(16, Mt - t0); voff = 128; }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const uint8_t* p = kb + (size_t)min(8 * t + g, f.valid - 1) * pitch + 32 * q;
+          f.ka[t] = *reinterpret_cast<const uint4*>(p);
+          f.kc[t] = *reinterpret_cast<const uint4*>(p + 16);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = 2 * q + (e & 1) + 8 * (e >> 1);
+          f.vv[e] = *reinterpret_cast<const uint4*>(kb + voff + (size_t)min(key, f.valid - 1) * pitch + 16 * g);
+        }
+      };
+      KVF cur, nxt;
       ok = wait_piece(4 * l) && ok;
       ok = wait_piece(4 * l + 1) && ok;
       CL_TRACE(l, 15);
@@ -422,6 +481,9 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
             if (r0 < Mt) st_async_v2f(dst + (uint32_t)((r0 * 48 + c) * 4), acc[mt][nt][0], acc[mt][nt][1], mb);
             if (r0 + 8 < Mt) st_async_v2f(dst + (uint32_t)(((r0 + 8) * 48 + c) * 4), acc[mt][nt][2], acc[mt][nt][3], mb);
           }
+        // the first attention step of this warp, if it reads the cache (rows of earlier decision steps): in flight
+        // during the reduce and gather stages
+        if (grp < n_past) load_step(grp, cur);
         __syncthreads();       // all warps are past their reads of the operand slice: its memory becomes the staging rows
         ok = mbar_wait(bar_slot + XB_ARX1, lpar) && ok;
       }
@@ -457,8 +519,6 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
 
       if (a_on) {
         // ================= attention: 16 query rows, keys split over the 32 warps of the cluster =================
-        const int grp = rank * CW + warp;
-        const int n_past = (a.f0 + 15) >> 4, n_steps = n_past + ((Mt + 15) >> 4);
         float o[8][4];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
@@ -467,29 +527,11 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
           const uint8_t* qr = sm + K::S_G + (mtile * 16 + g) * K::PG + 32 * q;
           const uint4 q0a = *reinterpret_cast<const uint4*>(qr), q0b = *reinterpret_cast<const uint4*>(qr + 16);
           const uint4 q1a = *reinterpret_cast<const uint4*>(qr + 8 * K::PG), q1b = *reinterpret_cast<const uint4*>(qr + 8 * K::PG + 16);
-          const uint8_t* kv_h = reinterpret_cast<const uint8_t*>(a.kv + (size_t)l * a.kv_layer_elems + head * 64);
-          struct KVF { uint4 ka[2], kc[2], vv[4]; int valid; };
-          auto load_step = [&](int s, KVF& f) {
-            const uint8_t* kb; size_t pitch; int voff;
-            if (s < n_past) { kb = kv_h + (size_t)(16 * s) * (4 * D); pitch = 4 * D; f.valid = min(16, a.f0 - 16 * s); voff = 2 * D; }
-            else { const int t0 = 16 * (s - n_past); kb = sm + K::S_G + t0 * K::PG + 128; pitch = K::PG; f.valid = min(16, Mt - t0); voff = 128; }
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              const uint8_t* p = kb + (size_t)min(8 * t + g, f.valid - 1) * pitch + 32 * q;
-              f.ka[t] = *reinterpret_cast<const uint4*>(p);
-              f.kc[t] = *reinterpret_cast<const uint4*>(p + 16);
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int key = 2 * q + (e & 1) + 8 * (e >> 1);
-              f.vv[e] = *reinterpret_cast<const uint4*>(kb + voff + (size_t)min(key, f.valid - 1) * pitch + 16 * g);
-            }
-          };
-          KVF cur, nxt;
-          if (grp < n_steps) load_step(grp, cur);
+          // steps on this step's own keys (the gathered k | v rows in shared memory) are loaded now
+          if (grp < n_steps && grp >= n_past) load_step(grp, cur);
 #pragma unroll 1
           for (int s = grp; s < n_steps; s += CL * CW) {
-            // the next step's fragments are in flight while this one is computed
+            // one step ahead: the next fragments are in flight while this step is computed
             if (s + CL * CW < n_steps) load_step(s + CL * CW, nxt);
             const int valid = cur.valid;
             // S = Q K^T for 16 keys (the d index is permuted identically for Q and K: lane q owns d = 16 q .. 16 q + 15)
@@ -846,10 +888,12 @@ w2vs_status_t launch_t(const ClArgs& a, cudaStream_t st) {
   bool& done = once.here();
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3((unsigned)(CL * K::NC)); lc.blockDim = dim3(CT); lc.dynamicSmemBytes = smem; lc.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  lc.attrs = attr; lc.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: the grid barriers cannot deadlock
+  attr[1].val.cooperative = 1;
+  lc.attrs = attr; lc.numAttrs = 2;
   if (!done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("stream_cluster smem attribute: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
