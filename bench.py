@@ -237,7 +237,8 @@ def stream_bench(a, kind, B, seconds):
     metric = f"p50 per-chunk latency (wav2vec-S {kind} incremental, batch {B}, {16 * a.step_blocks} frames/step)"
     config = {"workload": f"wav2vec-S {kind} incremental encoder, {B} stream(s) x {seconds} s, first chunk 24 frames, "
                           f"then {16 * a.step_blocks} frames per step, {a.dtype}"
-                          + (", persistent step kernel" if a.step_impl == 2 else ""), "name": a.workload,
+                          + {0: "", 1: ", operator chain", 2: ", first persistent step kernel", 3: ""}[a.step_impl],
+              "step_impl": a.step_impl, "name": a.workload,
               "chunks": len(bounds), "l2_policy": "weights (613 MB bf16) exceed the 126 MB L2"}
     if a.impl == "reference":
         import warnings
@@ -426,7 +427,7 @@ def main():
     ap.add_argument("--cpu-sample-batch", type=int, default=4,
                     help="utterances per step of the CPU reference arm (a bounded sample of the workload's batch)")
     ap.add_argument("--step-blocks", type=int, default=1, help="streaming workloads: blocks of 16 frames per decision step")
-    ap.add_argument("--step-impl", type=int, default=0, help="streaming workloads: 0 = operator chain (default), 2 = persistent step kernel")
+    ap.add_argument("--step-impl", type=int, default=0, help="streaming workloads: 0 = automatic (cluster step kernel for one stream of the large model, else the operator chain), 1 = operator chain, 2 = first persistent step kernel")
     a = ap.parse_args()
     if a.workload.startswith("stream_"):
         kind, B, seconds = WORKLOADS[a.workload]

@@ -73,10 +73,12 @@ typedef struct {
   int32_t conv_pos_groups;             /* 16 */
   int32_t seq_multiple;                /* required_seq_len_multiple (2) */
   int32_t sin_rows;                    /* rows of the sinusoidal table handed to pack (>= T+2) */
-  int32_t stream_step_impl;            /* incremental mode: 0 = default = 1 = the kernel-per-operator chain with
-                                          programmatic dependent launches; 2 = one persistent cooperative kernel per
-                                          decision step where it applies (bf16, <= 32 tokens per step; parity-tested,
-                                          measured slower than the chain so far: DESIGN.md section 5) */
+  int32_t stream_step_impl;            /* incremental mode: 0 = automatic: one kernel of thread-block clusters per decision
+                                          step (k_stream_cluster.cu) for one stream of a pre-LN bf16 model of an
+                                          instantiated shape with <= 32 tokens per step, else the chain; 1 = the
+                                          kernel-per-operator chain with programmatic dependent launches; 2 = the first
+                                          persistent cooperative kernel (bf16, <= 32 tokens per step; slower than the
+                                          chain, kept for comparison); 3 = same choice as 0 */
   int32_t io_dtype;                    /* 0 = outputs in `dtype`; W2VS_F16 = the model was given in fp16 (`.half()`, as
                                           the reference trainer does under --fp16, fairseq/fairseq/trainer.py:86-90):
                                           encoder outputs are written as fp16.  Arithmetic is that of dtype = BF16:

@@ -118,8 +118,8 @@ def test_base_2x15s_ragged_vs_oracle(dtype):
     assert e2 < BF16_TOL and err < BF16_TOL_FP32_WEIGHTS
 
 
-@pytest.mark.parametrize("dtype,step_impl", [(torch.float32, 0), (torch.bfloat16, 0), (torch.bfloat16, 2), (torch.bfloat16, 3)],
-                         ids=["fp32", "bf16", "bf16-persistent-kernel", "bf16-cluster-kernel"])
+@pytest.mark.parametrize("dtype,step_impl", [(torch.float32, 0), (torch.bfloat16, 1), (torch.bfloat16, 2), (torch.bfloat16, 0)],
+                         ids=["fp32", "bf16-chain", "bf16-persistent-kernel", "bf16-default-cluster-kernel"])
 def test_incremental_large_30s_vs_oracle_offline_rows(dtype, step_impl):
     """configs[3]: large, chunk by chunk (first chunk 24 frames = 7760 samples, then 16 frames = 5120 samples) with
     cached left context over 30 s; every emitted frame against the oracle's OFFLINE row of the complete utterance

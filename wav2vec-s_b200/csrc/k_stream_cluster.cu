@@ -879,37 +879,47 @@ pack_cluster_kernel(const bf16* __restrict__ wqkv, const bf16* __restrict__ wo, 
 }
 
 template <int D, int F, int H>
-w2vs_status_t launch_t(const ClArgs& a, cudaStream_t st) {
+void launch_config(cudaLaunchConfig_t& lc, cudaLaunchAttribute (&attr)[2], cudaStream_t st) {
   using K = CK<D, F, H>;
-  auto kern = stream_cluster_kernel<D, F, H>;
-  const size_t smem = K::S_END + 128;
-  static PerDeviceOnce once;
-  static int max_clusters[kMaxDevices];
-  bool& done = once.here();
-  cudaLaunchConfig_t lc = {};
-  lc.gridDim = dim3((unsigned)(CL * K::NC)); lc.blockDim = dim3(CT); lc.dynamicSmemBytes = smem; lc.stream = st;
-  cudaLaunchAttribute attr[2];
+  lc = cudaLaunchConfig_t{};
+  lc.gridDim = dim3((unsigned)(CL * K::NC)); lc.blockDim = dim3(CT); lc.dynamicSmemBytes = K::S_END + 128; lc.stream = st;
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: the grid barriers cannot deadlock
   attr[1].val.cooperative = 1;
   lc.attrs = attr; lc.numAttrs = 2;
-  if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("stream_cluster smem attribute: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
-    int n = 0;
-    e = cudaOccupancyMaxActiveClusters(&n, kern, &lc);
-    if (e != cudaSuccess) { set_error("stream_cluster occupancy query: %s", cudaGetErrorString(e)); cudaGetLastError(); return W2VS_CUDA_ERROR; }
-    max_clusters[current_device()] = n;
-    done = true;
+}
+
+// Clusters of this kernel the current device holds at a time (the grid barriers need all 2 H of them resident; how
+// many fit depends on how the SMs of the part are spread over its GPCs).  Cached per device; -1 on a CUDA error.
+template <int D, int F, int H>
+int resident_clusters() {
+  using K = CK<D, F, H>;
+  static int cached[kMaxDevices];     // 0 = not asked yet
+  int& n = cached[current_device()];
+  if (n == 0) {
+    auto kern = stream_cluster_kernel<D, F, H>;
+    cudaLaunchConfig_t lc; cudaLaunchAttribute attr[2];
+    launch_config<D, F, H>(lc, attr, nullptr);
+    int v = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::S_END + 128) != cudaSuccess ||
+        cudaOccupancyMaxActiveClusters(&v, kern, &lc) != cudaSuccess) { cudaGetLastError(); v = -1; }
+    n = v == 0 ? -1 : v;
   }
-  // the grid barriers spin: every cluster of the grid has to be resident at the same time
-  if (max_clusters[current_device()] < K::NC) {
-    set_error("unsupported: this device holds %d clusters of %d CTAs at a time, the cluster step kernel needs %d",
-              max_clusters[current_device()], CL, K::NC);
+  return n;
+}
+
+template <int D, int F, int H>
+w2vs_status_t launch_t(const ClArgs& a, cudaStream_t st) {
+  using K = CK<D, F, H>;
+  const int nres = resident_clusters<D, F, H>();
+  if (nres < K::NC) {
+    set_error("unsupported: this device holds %d clusters of %d CTAs at a time, the cluster step kernel needs %d", nres, CL, K::NC);
     return W2VS_UNSUPPORTED;
   }
-  cudaError_t e = cudaLaunchKernelEx(&lc, kern, a);
+  cudaLaunchConfig_t lc; cudaLaunchAttribute attr[2];
+  launch_config<D, F, H>(lc, attr, st);
+  cudaError_t e = cudaLaunchKernelEx(&lc, stream_cluster_kernel<D, F, H>, a);
   if (e != cudaSuccess) { set_error("stream_cluster_kernel launch: %s", cudaGetErrorString(e)); cudaGetLastError(); return W2VS_CUDA_ERROR; }
   W2VS_CHECK_LAUNCH("stream_cluster_kernel");
   return W2VS_OK;
@@ -936,7 +946,11 @@ size_t stream_cluster_layer_bytes(const w2vs_config* cfg) {
 }
 
 bool stream_cluster_applicable(const w2vs_config* cfg, int B, int ntok) {
-  return stream_cluster_layer_bytes(cfg) != 0 && B == 1 && ntok >= 1 && ntok <= ROWS;
+  if (stream_cluster_layer_bytes(cfg) == 0 || B != 1 || ntok < 1 || ntok > ROWS) return false;
+#define X(D_, F_, H_) if (cfg->embed_dim == D_ && cfg->ffn_dim == F_ && cfg->heads == H_) return resident_clusters<D_, F_, H_>() >= CK<D_, F_, H_>::NC;
+  W2VS_CLUSTER_SHAPES(X)
+#undef X
+  return false;
 }
 
 w2vs_status_t launch_pack_cluster(const w2vs_config* cfg, const void* wqkv, const void* wo, const void* w1,

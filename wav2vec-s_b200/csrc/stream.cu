@@ -146,9 +146,10 @@ w2vs_status_t block_step(const w2vs_config* cfg, const WeightLayout& wl, const S
   void* ctx = at<void>(d_ws, L.ctx);
   void* h = at<void>(d_ws, L.h);
   const bool pre_ln = cfg->layer_norm_first != 0;
-  if (cfg->stream_step_impl == 3 && cfg->io_dtype == 0 && stream_cluster_applicable(cfg, B, ntok)) {
-    // opt-in (stream_step_impl = 3; one stream, pre-LN bf16 models, at most 32 tokens per step): the whole step as
-    // one kernel of thread-block clusters, one cluster per attention head
+  if ((cfg->stream_step_impl == 0 || cfg->stream_step_impl == 3) && cfg->io_dtype == 0 && stream_cluster_applicable(cfg, B, ntok)) {
+    // default where it applies (one stream, pre-LN bf16 model of an instantiated shape, at most 32 tokens per step, a
+    // device that holds all clusters at once): the whole step as one kernel of thread-block clusters, two per
+    // attention head; everything else takes the operator chain below
     StreamFusedArgs fa{};
     fa.cfg = cfg; fa.wl = &wl; fa.W = W;
     fa.B = B; fa.ntok = ntok; fa.n_main = n_main; fa.f0 = f0;

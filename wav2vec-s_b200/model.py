@@ -508,8 +508,9 @@ class EncoderStream:
         self.rc = model.encoder.right_context if right_context is None else right_context
         self.max_frames, self.max_new = int(max_frames), int(max_new_samples)
         ccfg, self.packed = model._ensure_packed(self.max_frames + 2)
-        # step_impl (w2vs_config.stream_step_impl): 0 / 1 = the kernel-per-operator chain (default), 2 = one persistent
-        # cooperative kernel per decision step where it applies (bf16, <= 32 tokens per step)
+        # step_impl (w2vs_config.stream_step_impl): 0 = automatic (one kernel of thread-block clusters per decision step
+        # for one stream of a pre-LN bf16 model of an instantiated shape, else the operator chain), 1 = the
+        # kernel-per-operator chain, 2 = the first persistent cooperative kernel (bf16, <= 32 tokens per step)
         self.ccfg = cabi.Config.from_buffer_copy(ccfg)
         self.ccfg.stream_step_impl = int(step_impl)
         lib = cabi.lib()
