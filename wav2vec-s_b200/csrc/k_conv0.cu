@@ -205,7 +205,14 @@ conv0_gn_finalize_kernel(float* __restrict__ gn_stats, const float* __restrict__
 template <typename TIn, typename TOut, int NI, int MODE>
 static w2vs_status_t launch_one(const Conv0Args& a, cudaStream_t st) {
   constexpr int C = NI * 64, KW = 10;
-  const int frames_per_cta = kFramesPerCta;
+  // 256 frames per CTA amortise the tap / parameter loads over a long utterance; a decision step of the incremental
+  // mode has ~1000 frames in all, which would be four CTAs: spread those over the SMs (multiples of 16 frames = one
+  // pass of the 8 warps).  The GroupNorm passes keep 256 (their partial-statistics layout is sized by it).
+  int frames_per_cta = kFramesPerCta;
+  if (MODE == C0_PLAIN || MODE == C0_LN) {
+    const int64_t per_cta = ceil_div64((int64_t)a.T0 * a.B, 2 * num_sms());
+    if (per_cta < kFramesPerCta) frames_per_cta = (int)((per_cta + 15) / 16 * 16);
+  }
   W2VS_REQUIRE(a.stride >= 1 && a.stride <= 8, "first conv stride must be <= 8");
   size_t smem = (size_t)(KW * C + 3 * C + ((kFramesPerCta - 1) * 8 + KW + 3) / 4 * 4) * sizeof(float);
   if (MODE == C0_GN_STATS) smem += (size_t)8 * 2 * C * sizeof(float);
