@@ -21,13 +21,25 @@ impl = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 torch.manual_seed(0)
 m = W.BlockWiseWav2Vec2Model(LARGE).to("cuda", torch.bfloat16).eval()
 L = int(seconds * 16000)
-wav = torch.randn(1, L + 5120 * 8).cuda()
+wav = torch.randn(1, L + 5120 * 16).cuda()
 st = m.open_stream(B=1, max_seconds=seconds + 5, max_new_samples=7760 + 400, step_impl=impl)
 pos = 0
 while pos < L:
     n = 7760 if pos == 0 else 5120
     st.step(wav[:, pos:pos + n])
     pos += n
+lat0 = []
+for _ in range(6):                      # untraced steps first: the stamps cost the kernel a few percent
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    st.step(wav[:, pos:pos + 5120])
+    e1.record()
+    torch.cuda.synchronize()
+    lat0.append(round(e0.elapsed_time(e1), 4))
+    pos += 5120
+print(f"step latency without stamps (ms): {lat0}")
+cabi.check(cabi.lib().w2vs_debug_cluster_trace(None, 1), "trace on")
 lat = []
 for _ in range(6):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -439,7 +439,8 @@ w2vs_status_t w2vs_debug_fused_trace(uint64_t* out, int32_t n) {
 }
 
 w2vs_status_t w2vs_debug_cluster_trace(uint64_t* out, int32_t n) {
-  W2VS_REQUIRE(out != nullptr && n >= 0, "out / n");
+  if (out == nullptr) { debug_cluster_trace_enable(n != 0); return W2VS_OK; }      // (NULL, on): switch the stamps on / off
+  W2VS_REQUIRE(n >= 0, "n");
   return debug_read_cluster_trace(reinterpret_cast<unsigned long long*>(out), n);
 }
 

@@ -68,8 +68,9 @@ struct ClArgs {
   float* X;                            // residual stream, 3 x [32][D] fp32
   bf16* kv; long long kv_layer_elems;  // cache [layers][kv_rows][2D]
   bf16* out;                           // [n_main][D]
-  unsigned long long* bar;             // [0] arrivals, [1] departures (both zero between launches)
+  unsigned long long* bar;             // [0..3] arrivals per cluster rank, [4] departures (all zero between launches)
   float scale_log2;
+  int trace;                           // write the phase timestamps (tools/cluster_trace.py); off by default
 };
 
 template <int D, int F, int H>
@@ -164,25 +165,32 @@ __device__ __forceinline__ void warp_sum4(float (&v)[4]) {
 }
 __device__ __forceinline__ float ex2w(float m, float M, float sl2) { return m == -INFINITY ? 0.f : ex2_approx((m - M) * sl2); }
 
-// Grid-wide barrier (all CTAs are co-resident: one per SM, the launcher checked the occupancy).  One arrival counter
-// in global memory, monotonically increasing inside a launch; the last CTA to leave the kernel resets it.
-__device__ __forceinline__ bool grid_barrier(unsigned long long* bar, unsigned long long target) {
+// Grid barrier (all CTAs are co-resident: cooperative launch).  One arrival counter PER CLUSTER RANK in global memory,
+// monotonically increasing inside a launch; the last CTA to leave the kernel resets them.  Between two phases a CTA
+// of rank j only depends on the rank-j CTAs of the other clusters (they own the same quarter of the feature
+// dimension: the columns its second product adds into are the K slice its next first product reads), so it waits for
+// its own rank's counter only -- a quarter of the arrivals on the line it polls, and no waiting for stragglers of the
+// other ranks; `all` = wait for every rank (after the embedding and before the final LayerNorm, which touch whole rows).
+__device__ __forceinline__ bool grid_barrier(unsigned long long* bar, int rank, unsigned long long target, bool all) {
   __shared__ int s_ok;
   __syncthreads();
   if (threadIdx.x == 0) {
     // release at gpu scope: this CTA's writes and reductions of the phase (ordered before this thread by the
     // bar.sync above) are visible to whoever observes the arrival
-    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(bar), "l"(1ull) : "memory");
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(bar + rank), "l"(1ull) : "memory");
     unsigned long long v, t0 = 0;
     unsigned spins = 0;
     int ok = 1;
-    for (;;) {
-      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
-      if (v >= target) break;
-      if ((++spins & 0x3ff) == 0) {
-        const unsigned long long now = global_ns();
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > CL_TIMEOUT_NS) { atomicExch(&g_cluster_fault, 1); ok = 0; break; }
+    for (int k = 0; k < (all ? CL : 1) && ok; ++k) {
+      const unsigned long long* p = bar + (all ? k : rank);
+      for (;;) {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        if (v >= target) break;
+        if ((++spins & 0x3ff) == 0) {
+          const unsigned long long now = global_ns();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > CL_TIMEOUT_NS) { atomicExch(&g_cluster_fault, 1); ok = 0; break; }
+        }
       }
     }
     s_ok = ok;
@@ -282,7 +290,7 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
   // gather targets start as zeros (rows past the step's tokens are multiplied, never stored)
   for (int i = tid; i < (K::G_B + 16 * K::PO) / 16; i += CT) reinterpret_cast<uint4*>(sm + K::S_G)[i] = make_uint4(0u, 0u, 0u, 0u);
 
-  const bool tr = gid == 0 && tid == 0;
+  const bool tr = a.trace != 0 && gid == 0 && tid == 0;
 #define CL_TRACE(l_, ev_) do { if (tr && (l_) < 64) g_cluster_trace[l_][ev_] = global_ns(); } while (0)
 
   // ---- embed: X[0] = projected frame + sinusoidal position (absolute index frame + 2); X[1] = 0 ----
@@ -299,7 +307,7 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
   prefetch_params(0);
   cluster_sync();                          // mbarrier inits and zeroed buffers before any remote traffic
   unsigned long long nbar = 0;
-  bool ok = grid_barrier(a.bar, ++nbar * G);
+  bool ok = grid_barrier(a.bar, rank, ++nbar * K::NC, true);
 
 #pragma unroll 1
   for (int ph = 0; ph < 2 * a.layers && ok; ++ph) {
@@ -796,9 +804,10 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
     }
     // zero the buffer the NEXT phase accumulates into (it was last read in the previous phase).  Global writes sit at
     // the end of a phase: before a cluster barrier they would hold up its release fence for an L2 round trip.
-    a.X[(size_t)((ph + 2) % 3) * ROWS * D + gid * CT + tid] = 0.f;
+    // (this CTA's share of that buffer lies in its rank's columns, like everything else it writes: see grid_barrier)
+    if (tid < 64) *reinterpret_cast<float4*>(a.X + (size_t)((ph + 2) % 3) * ROWS * D + (size_t)res_row * D + res_col) = make_float4(0.f, 0.f, 0.f, 0.f);
     if (res_on) red_add_v4(Xout + (size_t)res_row * D + res_col, res_x);
-    ok = grid_barrier(a.bar, ++nbar * G) && ok;
+    ok = grid_barrier(a.bar, rank, ++nbar * K::NC, ph + 1 == 2 * a.layers) && ok;
     CL_TRACE(l, pa ? 13 : 14);
   }
 
@@ -840,9 +849,8 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
   cluster_sync();
   if (tid == 0) {
     __threadfence();
-    if (atomicAdd(a.bar + 1, 1ull) == (unsigned long long)G - 1) {
-      a.bar[0] = 0ull;
-      a.bar[1] = 0ull;
+    if (atomicAdd(a.bar + CL, 1ull) == (unsigned long long)G - 1) {
+      for (int k = 0; k <= CL; ++k) a.bar[k] = 0ull;
       __threadfence();
     }
   }
@@ -934,6 +942,8 @@ w2vs_status_t pack_t(const void* wqkv, const void* wo, const void* w1, const voi
 
 }  // namespace
 
+static int g_cluster_trace_on = 0;    // process-wide debug switch (w2vs_debug_cluster_trace with n < 0 toggles it)
+
 // The shapes this kernel is instantiated for: the released large model and the tiny model of the parity tests.
 #define W2VS_CLUSTER_SHAPES(X) X(1024, 4096, 16) X(128, 256, 2)
 
@@ -976,12 +986,15 @@ w2vs_status_t launch_stream_cluster(const StreamFusedArgs& h, cudaStream_t st) {
   a.kv = (bf16*)h.kv; a.kv_layer_elems = h.kv_layer_elems;
   a.out = (bf16*)h.out; a.bar = h.bar;
   a.scale_log2 = 0.125f * 1.4426950408889634f;
+  a.trace = g_cluster_trace_on;
 #define X(D_, F_, H_) if (cfg->embed_dim == D_ && cfg->ffn_dim == F_ && cfg->heads == H_) return launch_t<D_, F_, H_>(a, st);
   W2VS_CLUSTER_SHAPES(X)
 #undef X
   set_error("unsupported: no cluster step kernel for this model shape");
   return W2VS_UNSUPPORTED;
 }
+
+void debug_cluster_trace_enable(int on) { g_cluster_trace_on = on; }
 
 w2vs_status_t debug_read_cluster_trace(unsigned long long* out, int n) {
   if (n > 64 * 24) n = 64 * 24;

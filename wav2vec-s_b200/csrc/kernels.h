@@ -144,6 +144,7 @@ w2vs_status_t launch_pack_cluster(const w2vs_config* cfg, const void* wqkv, cons
                                   const void* w2, void* dst, cudaStream_t st);
 w2vs_status_t debug_read_cluster_fault(int* out);
 w2vs_status_t debug_read_cluster_trace(unsigned long long* out, int n);
+void debug_cluster_trace_enable(int on);
 
 // ---- positional conv + weight packing -----------------------------------------------------------------
 struct PosConvArgs {
