@@ -64,6 +64,8 @@ if impl == 3:
     print("CTA 0, mean over layers (us):")
     for n, v in zip(names, d.mean(0)):
         print(f"  {n:20s} {v:6.2f}")
+    print(f"  phase C grid barrier: bar.sync {(t[:, 22] - t[:, 12]).mean() / 1e3:.2f}, release + arrive {(t[:, 23] - t[:, 22]).mean() / 1e3:.2f}, "
+          f"poll + bar.sync {(t[:, 14] - t[:, 23]).mean() / 1e3:.2f} us")
     print(f"  layer total {(seq[:, -1] - seq[:, 0]).mean() / 1e3:.2f} us; all layers {(t[23, 14] - t[0, 0]) / 1e3:.1f} us")
 flags = C.c_int32(0)
 cabi.check(cabi.lib().w2vs_debug_fault_flags(C.byref(flags)), "faults")

@@ -171,13 +171,16 @@ __device__ __forceinline__ float ex2w(float m, float M, float sl2) { return m ==
 // dimension: the columns its second product adds into are the K slice its next first product reads), so it waits for
 // its own rank's counter only -- a quarter of the arrivals on the line it polls, and no waiting for stragglers of the
 // other ranks; `all` = wait for every rank (after the embedding and before the final LayerNorm, which touch whole rows).
-__device__ __forceinline__ bool grid_barrier(unsigned long long* bar, int rank, unsigned long long target, bool all) {
+__device__ __forceinline__ bool grid_barrier(unsigned long long* bar, int rank, unsigned long long target, bool all,
+                                             unsigned long long* stamps = nullptr) {
   __shared__ int s_ok;
   __syncthreads();
   if (threadIdx.x == 0) {
+    if (stamps) stamps[0] = global_ns();
     // release at gpu scope: this CTA's writes and reductions of the phase (ordered before this thread by the
     // bar.sync above) are visible to whoever observes the arrival
     asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(bar + rank), "l"(1ull) : "memory");
+    if (stamps) stamps[1] = global_ns();
     unsigned long long v, t0 = 0;
     unsigned spins = 0;
     int ok = 1;
@@ -807,7 +810,7 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
     // (this CTA's share of that buffer lies in its rank's columns, like everything else it writes: see grid_barrier)
     if (tid < 64) *reinterpret_cast<float4*>(a.X + (size_t)((ph + 2) % 3) * ROWS * D + (size_t)res_row * D + res_col) = make_float4(0.f, 0.f, 0.f, 0.f);
     if (res_on) red_add_v4(Xout + (size_t)res_row * D + res_col, res_x);
-    ok = grid_barrier(a.bar, rank, ++nbar * K::NC, ph + 1 == 2 * a.layers) && ok;
+    ok = grid_barrier(a.bar, rank, ++nbar * K::NC, ph + 1 == 2 * a.layers, tr && !pa && l < 64 ? &g_cluster_trace[l][22] : nullptr) && ok;
     CL_TRACE(l, pa ? 13 : 14);
   }
 
