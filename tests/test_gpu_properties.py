@@ -85,11 +85,12 @@ def test_incremental_equals_full_utterance_at_30s(model):
     assert tuple(y.shape) == tuple(ref.shape)
     err = (y.float() - ref.float()).abs().max() / ref.float().abs().max()
     assert err < 2e-2, float(err)
-    # A second stream over the same audio.  The default path of one large-model stream (the cluster step kernel) adds the
-    # partial products of its clusters into the residual stream with fp32 reductions at L2, whose order varies from run
-    # to run: the two streams agree to rounding (1e-3 of the output range, far inside the 2e-2 parity bar).  The operator
-    # chain (step_impl = 1) gives the same bits every time: its split-key attention merges its partial states in a
-    # fixed order, the completion counters only elect the CTA that does it.
+    # A second stream over the same audio.  The default path of one large-model stream (the cluster step kernel) adds
+    # the partial products of its clusters into the residual stream with fp32 reductions at L2, in whatever order
+    # they arrive: the sums differ in the last bit, a bf16 rounding flips somewhere in the 24 layers and two runs differ
+    # by a bf16 step or two at the output (measured 7e-3 of the output range) -- both inside the parity bar.  The
+    # operator chain (step_impl = 1) gives the same bits every time: its split-key attention merges its partial
+    # states in a fixed order, the completion counters only elect the CTA that does it.
     def again(step_impl):
         st2 = model.open_stream(B=1, max_seconds=31, max_new_samples=7760 + 400, step_impl=step_impl)
         outs2, pos = [], 0
@@ -98,8 +99,10 @@ def test_incremental_equals_full_utterance_at_30s(model):
             outs2.append(st2.step(wav[:, pos:pos + n], EncoderStream.FINAL if pos + n >= L else EncoderStream.NONE))
             pos += n
         return torch.cat(outs2, 0)
+    scale = ref.float().abs().max()
     y2 = again(0)
-    assert float((y2.float() - y.float()).abs().max() / ref.float().abs().max()) < 1e-3
+    assert float((y2.float() - ref.float()).abs().max() / scale) < 2e-2
+    assert float((y2.float() - y.float()).abs().max() / scale) < 1.5e-2
     c1, c2 = again(1), again(1)
     assert torch.equal(c1, c2)
-    assert float((c1.float() - ref.float()).abs().max() / ref.float().abs().max()) < 2e-2
+    assert float((c1.float() - ref.float()).abs().max() / scale) < 2e-2

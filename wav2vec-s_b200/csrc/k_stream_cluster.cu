@@ -24,8 +24,12 @@
 //      memory into registers, flash-style partial states merged through shared memory and DSMEM);
 //   4. multiplies the gathered rows with its 1/8 of the OUTPUT columns of the second weight matrix (out_proj rows
 //      restricted to head h's 64 inputs, fc2 rows restricted to the cluster's hidden units) and adds the partial
-//      result into the next residual buffer with fp32 reductions at L2 (red.global.add.v2.f32; 16 additions per
-//      element and phase, so results differ from run to run in the last bits).
+//      result into the next residual buffer with fp32 reductions at L2 (red.global.add.v2.f32; 16 to 32 additions per
+//      element and phase in whatever order they arrive: the fp32 sums differ in the last bit from run to run, and
+//      after 24 layers of bf16 roundings two runs over the same audio differ by up to two bf16 steps at the output.
+//      Accumulating in 64-bit fixed point (red.global.add.u64) makes the step bit-reproducible -- built, tested and
+//      measured at 30.6 instead of 24.2 us per layer (64-bit reductions and the loads behind them are that much
+//      slower at L2), so it is not used; stream_step_impl = 1, the operator chain, gives the same bits every time).
 // The residual stream rotates through three buffers: phase p reads X[p % 3], accumulates into X[(p + 1) % 3] (the
 // rows' old values + bias are added by the CTA that holds them anyway) and zeroes X[(p + 2) % 3] for the phase after.
 // Weights: a second copy in the packed blob (LayerW::wc) holds, per layer and CTA, the four operand pieces exactly as
