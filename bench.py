@@ -350,8 +350,10 @@ def incremental_probe(model, cfg, dev, B=1, seconds=30):
     while bounds[-1] + 5120 < L:
         bounds.append(bounds[-1] + 5120)
     bounds.append(L)
-    lats = []
+    from wav2vec_s_b200 import cabi
+    lats, launches = [], 0
     for rep in range(3):
+        cabi.launch_count(reset=True)
         st = sm.open_stream(B=B, max_seconds=seconds + 1, max_new_samples=7760 + 400)
         pos, lat = 0, []
         for n in bounds:
@@ -363,6 +365,7 @@ def incremental_probe(model, cfg, dev, B=1, seconds=30):
             torch.cuda.synchronize()
             lat.append(e0.elapsed_time(e1))
             pos = n
+        launches = cabi.launch_count(reset=True) / len(bounds)
         if rep > 0:
             lats += lat[1:-1]
     lats.sort()
@@ -373,7 +376,10 @@ def incremental_probe(model, cfg, dev, B=1, seconds=30):
     pk, pk_kind = peaks()
     ach = (wbytes + kvbytes) / (p50 / 1e3) / 1e9
     return {"metric": f"p50 per-chunk latency (wav2vec-S large incremental, {B} stream(s), 16 frames/step)",
-            "streams": B, "p50_ms": p50, "p90_ms": lats[int(0.9 * len(lats))], "unit": "ms", "steps": len(lats),
+            "streams": B, "launches_per_step": round(launches, 1),
+            "path": "one kernel of thread-block clusters per step (k_stream_cluster.cu) behind the conv-stack launches"
+                    if launches < 60 else "kernel-per-operator chain with programmatic dependent launches",
+            "p50_ms": p50, "p90_ms": lats[int(0.9 * len(lats))], "unit": "ms", "steps": len(lats),
             "realtime_factor": 0.32 / (p50 / 1e3),
             "roofline": {"bound": "hbm", "kernel": "one decision step (weights streamed once + cached K/V)",
                          "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
