@@ -115,6 +115,18 @@ w2vs_status_t launch_concat_wav(float* dst, int64_t dst_bs, const float* srcA, i
 w2vs_status_t launch_kv_append(const void* qkv, void* cache, int64_t cache_rows, int row0, int n_tok, int D,
                                int elem_bytes, int B, cudaStream_t st);
 
+// ---- one conv block of the feature extractor on the new rows of a decision step, one launch (k_conv_step.cu):
+// [carry rows | new rows] -> Conv1d(C, C, k, s) + bias -> LayerNorm -> GELU -> out; the rows the next step needs again
+// are copied to carry_out.  One stream, bf16, C in {512, 64}, k in {2, 3}, s = 2.
+struct ConvStepArgs {
+  const void* carry; int n_carry; const void* fresh; int n_fresh;
+  const void* W; const float *bias, *gamma, *beta;
+  void* out; int n_out; void* carry_out;
+  int k, s, C;
+};
+bool conv_step_applicable(const ConvStepArgs& a);
+w2vs_status_t launch_conv_step(const ConvStepArgs& a, cudaStream_t st);
+
 // ---- fused incremental step (k_stream_fused.cu): embed -> all layers -> final LayerNorm in one cooperative kernel ----
 struct WeightLayout;
 struct StreamFusedArgs {

@@ -396,6 +396,24 @@ w2vs_status_t w2vs_stream_step(const w2vs_config* cfg, const void* d_packed, voi
       const int cur = hs->cur[i], nxt = cur ^ 1;
       void* dst = at<void>(d_state, L.in[i][nxt]);
       const void* old = at<void>(d_state, L.in[i][cur]);
+      if (i > 0 && B == 1 && adt == W2VS_BF16 && cfg->stream_step_impl != 1 && conv_has_ln(cfg, i) && cin == cout && n_o[i] > 0) {
+        // one stream: the whole block (carry + new rows -> conv -> LayerNorm -> GELU, next carry) as one launch
+        ConvStepArgs ca{};
+        ca.carry = reinterpret_cast<const uint8_t*>(old) + (size_t)hs->carry_off[i] * cin * as; ca.n_carry = hs->carry[i];
+        ca.fresh = prev_out; ca.n_fresh = added;
+        ca.W = at<void>(W, wl.conv[i].w); ca.bias = at<float>(W, wl.conv[i].bias);
+        ca.gamma = at<float>(W, wl.conv[i].norm_w); ca.beta = at<float>(W, wl.conv[i].norm_b);
+        ca.out = at<void>(d_ws, L.out[i & 1]); ca.n_out = n_o[i]; ca.carry_out = dst; ca.k = k; ca.s = s; ca.C = cout;
+        if (conv_step_applicable(ca)) {
+          W2VS_TRY(launch_conv_step(ca, st));
+          hs->cur[i] = nxt;
+          hs->carry_off[i] = 0;
+          hs->carry[i] = n_in[i] - n_o[i] * s;
+          prev_out = ca.out;
+          prev_cap = L.out_cap[i];
+          continue;
+        }
+      }
       if (i == 0) {
         W2VS_TRY(launch_concat_wav((float*)dst, L.cap_in[0], (const float*)old, L.cap_in[0], hs->carry_off[0],
                                    hs->carry[0], d_new, wav_dtype, n_new, n_new, B, st));
