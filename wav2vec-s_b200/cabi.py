@@ -98,7 +98,7 @@ PROTOTYPES = {
 # kernel name -> class reported by bench.py
 KERNEL_CLASS = {"gemm_tc_kernel": "gemm", "gemm_tc2_kernel": "gemm", "gemm_simt_kernel": "gemm_simt", "attn_mma_kernel": "attention", "attn_tc_kernel": "attention",
                 "attn_simt_kernel": "attention", "conv0_kernel": "conv0", "stream_fused_kernel": "stream_fused",
-                "stream_cluster_kernel": "stream_cluster", "conv_step_kernel": "conv_step"}
+                "stream_cluster_kernel": "stream_cluster", "conv_step_kernel": "conv_step", "feat_proj_kernel": "conv_step"}
 
 _lib = None
 

@@ -291,7 +291,135 @@ w2vs_status_t launch_c(const CsArgs& a, cudaStream_t st) {
   return W2VS_OK;
 }
 
+// ---- feature LayerNorm + post_extract_proj + append to the stream's frame buffer, one launch ----------------------
+// (wav2vec2.py:566-569 on the new frames of a decision step; the chain: LayerNorm launch, weight-streaming GEMM, row
+// copy).  One CTA per 8 output columns, 8 warps split K: every CTA normalises the (at most 64) new rows itself into
+// shared memory -- 16 KB of L2 reads -- while its 8 weight rows, requested before griddepcontrol.wait, are in flight;
+// mma.sync.m16n8k16 with the k index of a 32-wide block permuted identically for both operands (lane (g, q) takes the
+// 8 consecutive elements 32 b + 8 q ..: 16-byte accesses, no ldmatrix), fixed-order reduction of the 8 partial sums.
+constexpr int FP_MAX_MT = 4;
+
+template <int MT, int KB>      // m16 tiles of rows; 32-wide k blocks per warp (K = 256 KB)
+__global__ void __launch_bounds__(CS_THREADS)
+feat_proj_kernel(const bf16* __restrict__ x, int rows, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 const bf16* __restrict__ W, const float* __restrict__ bias, float* __restrict__ out, int N) {
+  constexpr int K = 256 * KB, PA = K * 2 + 16;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sa = smem_raw;                                             // normalised rows [MT * 16][PA] bf16
+  float* part = reinterpret_cast<float*>(smem_raw + MT * 16 * PA);    // [8 warps][MT * 16][8]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  const int n0 = blockIdx.x * 8;
+  pdl_launch_dependents();
+  const int kbeg = warp * (K / CS_WARPS) + 8 * q;
+  uint4 wv[KB];
+#pragma unroll
+  for (int b = 0; b < KB; ++b) wv[b] = __ldg(reinterpret_cast<const uint4*>(W + (size_t)(n0 + g) * K + kbeg + 32 * b));
+  pdl_wait();
+  // LayerNorm: one warp per row, the row in registers (K / 32 elements per lane, 16-byte loads)
+  constexpr int VPL = K / 256;                  // uint4 per lane and row
+  for (int r = warp; r < MT * 16; r += CS_WARPS) {
+    uint4 u[VPL];
+    float v[VPL][8], s = 0.f;
+    if (r < rows) {
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        u[j] = *reinterpret_cast<const uint4*>(x + (size_t)r * K + (j * 32 + lane) * 8);
+        const float2 a0 = unpack_bf16x2(u[j].x), a1 = unpack_bf16x2(u[j].y), a2 = unpack_bf16x2(u[j].z), a3 = unpack_bf16x2(u[j].w);
+        v[j][0] = a0.x; v[j][1] = a0.y; v[j][2] = a1.x; v[j][3] = a1.y; v[j][4] = a2.x; v[j][5] = a2.y; v[j][6] = a3.x; v[j][7] = a3.y;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += v[j][e];
+      }
+    }
+    const float mean = warp_sum(s) * (1.0f / K);
+    float qq = 0.f;
+    if (r < rows) {
+#pragma unroll
+      for (int j = 0; j < VPL; ++j)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float d = v[j][e] - mean; qq = fmaf(d, d, qq); }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(qq) * (1.0f / K) + 1e-5f);
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (r < rows) {
+        const int c = (j * 32 + lane) * 8;
+        float gg[8], bb[8], y[8];
+        load8(gamma + c, gg);
+        load8(beta + c, bb);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = (v[j][e] - mean) * rstd * gg[e] + bb[e];
+        o = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+      }
+      *reinterpret_cast<uint4*>(sa + r * PA + (j * 32 + lane) * 16) = o;
+    }
+  }
+  __syncthreads();
+  float acc[MT][4] = {};
+#pragma unroll
+  for (int b = 0; b < KB; ++b) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const uint4 lo = *reinterpret_cast<const uint4*>(sa + (mt * 16 + g) * PA + (kbeg + 32 * b) * 2);
+      const uint4 hi = *reinterpret_cast<const uint4*>(sa + (mt * 16 + g + 8) * PA + (kbeg + 32 * b) * 2);
+      const uint32_t a0[4] = {lo.x, hi.x, lo.y, hi.y}, a1[4] = {lo.z, hi.z, lo.w, hi.w};
+      const uint32_t b0[2] = {wv[b].x, wv[b].y}, b1[2] = {wv[b].z, wv[b].w};
+      cs_mma(acc[mt], a0, b0);
+      cs_mma(acc[mt], a1, b1);
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    float* p = part + ((size_t)warp * MT * 16 + mt * 16 + g) * 8 + 2 * q;
+    p[0] = acc[mt][0]; p[1] = acc[mt][1]; p[64] = acc[mt][2]; p[65] = acc[mt][3];
+  }
+  __syncthreads();
+  for (int o = tid; o < rows * 8; o += CS_THREADS) {
+    const int r = o >> 3, c = o & 7;
+    float v = bias != nullptr ? bias[n0 + c] : 0.f;
+#pragma unroll
+    for (int w = 0; w < CS_WARPS; ++w) v += part[((size_t)w * MT * 16 + r) * 8 + c];      // fixed order
+    out[(size_t)r * N + n0 + c] = v;
+  }
+}
+
+template <int KB>
+w2vs_status_t launch_fp(const FeatProjArgs& a, cudaStream_t st) {
+  const int mt = (a.rows + 15) / 16;
+  constexpr int K = 256 * KB;
+  const size_t smem = (size_t)mt * 16 * (K * 2 + 16) + (size_t)CS_WARPS * mt * 16 * 8 * 4;
+  const dim3 grid((unsigned)(a.N / 8));
+#define W2VS_FP_CASE(MT_)                                                                                         \
+  {                                                                                                               \
+    static PerDeviceOnce once;                                                                                    \
+    if (!once.here()) {                                                                                           \
+      cudaFuncSetAttribute(feat_proj_kernel<MT_, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FP_MAX_MT * 16 * (K * 2 + 16) + CS_WARPS * FP_MAX_MT * 16 * 8 * 4)); \
+      once.here() = true;                                                                                         \
+    }                                                                                                             \
+    launch_pdl(feat_proj_kernel<MT_, KB>, grid, dim3(CS_THREADS), smem, st, (const bf16*)a.x, a.rows, a.gamma, a.beta, \
+               (const bf16*)a.W, a.bias, a.out, a.N);                                                             \
+  }
+  switch (mt) {
+    case 1: W2VS_FP_CASE(1) break;
+    case 2: W2VS_FP_CASE(2) break;
+    case 3: W2VS_FP_CASE(3) break;
+    default: W2VS_FP_CASE(4) break;
+  }
+#undef W2VS_FP_CASE
+  W2VS_CHECK_LAUNCH("feat_proj_kernel");
+  return W2VS_OK;
+}
+
 }  // namespace
+
+bool feat_proj_applicable(const FeatProjArgs& a) {
+  return (a.K == 512 || a.K == 256) && a.rows >= 1 && a.rows <= 16 * FP_MAX_MT && a.N % 8 == 0 && a.gamma != nullptr && a.beta != nullptr;
+}
+
+w2vs_status_t launch_feat_proj(const FeatProjArgs& a, cudaStream_t st) {
+  W2VS_REQUIRE(feat_proj_applicable(a), "feature projection step: configuration not supported");
+  return a.K == 512 ? launch_fp<2>(a, st) : launch_fp<1>(a, st);
+}
 
 bool conv_step_applicable(const ConvStepArgs& h) {
   return (h.C == 512 || h.C == 64) && h.k >= 2 && h.k <= 3 && h.s == 2 && h.n_out >= 1 && h.n_carry >= 0 && h.n_fresh >= 0 &&

@@ -127,6 +127,14 @@ struct ConvStepArgs {
 bool conv_step_applicable(const ConvStepArgs& a);
 w2vs_status_t launch_conv_step(const ConvStepArgs& a, cudaStream_t st);
 
+// feature LayerNorm + post_extract_proj + append of a step's new frames, one launch (k_conv_step.cu): x [rows][K] bf16
+// -> LN(gamma, beta) -> . W[N][K]^T + bias -> out [rows][N] fp32 (rows <= 64, K in {256, 512})
+struct FeatProjArgs {
+  const void* x; int rows, K; const float *gamma, *beta; const void* W; const float* bias; float* out; int N;
+};
+bool feat_proj_applicable(const FeatProjArgs& a);
+w2vs_status_t launch_feat_proj(const FeatProjArgs& a, cudaStream_t st);
+
 // ---- fused incremental step (k_stream_fused.cu): embed -> all layers -> final LayerNorm in one cooperative kernel ----
 struct WeightLayout;
 struct StreamFusedArgs {

@@ -470,7 +470,20 @@ w2vs_status_t w2vs_stream_step(const w2vs_config* cfg, const void* d_packed, voi
     la.x = conv_out; la.in_dtype = adt; la.ldx = CL;
     la.gamma = at<float>(W, wl.feat_ln_w); la.beta = at<float>(W, wl.feat_ln_b);
     la.rows = rows; la.N = CL; la.gelu = 0; la.ldo = CL; la.act_dtype = adt;
-    if (CL != D) {
+    bool fused_proj = false;
+    if (CL != D && B == 1 && adt == W2VS_BF16 && cfg->stream_step_impl != 1) {
+      // one stream: LayerNorm + projection + append to the frame buffer as one launch
+      FeatProjArgs fp{};
+      fp.x = conv_out; fp.rows = f_new; fp.K = CL; fp.gamma = la.gamma; fp.beta = la.beta;
+      fp.W = at<void>(W, wl.proj_w); fp.bias = at<float>(W, wl.proj_b);
+      fp.out = at<float>(d_state, L.fbuf) + (size_t)hs->frames_total * D; fp.N = D;
+      if (feat_proj_applicable(fp)) {
+        W2VS_TRY(launch_feat_proj(fp, st));
+        fused_proj = true;
+      }
+    }
+    if (fused_proj) {
+    } else if (CL != D) {
       void* normed = at<void>(d_ws, L.normed);
       la.out_f32 = nullptr; la.out_act = normed;
       W2VS_TRY(launch_layernorm(la, st));
@@ -484,6 +497,7 @@ w2vs_status_t w2vs_stream_step(const w2vs_config* cfg, const void* d_packed, voi
       W2VS_TRY(launch_layernorm(la, st));
     }
     float* fbuf = at<float>(d_state, L.fbuf);
+    if (!fused_proj)
     W2VS_TRY(launch_concat_rows(fbuf + (size_t)hs->frames_total * D, (int64_t)L.fcap * D * 4, feats_tmp, 0, 0, 0,
                                 feats_tmp, (int64_t)ocap * D * 4, f_new, D * 4, B, st));
   }
