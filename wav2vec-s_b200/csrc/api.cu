@@ -140,9 +140,14 @@ w2vs_status_t w2vs_weights_pack(const w2vs_config* cfg, const void* const* d_ref
     W2VS_TRY(copy_f32(l.b2, D));
     W2VS_TRY(copy_f32(l.ln2_w, D));
     W2VS_TRY(copy_f32(l.ln2_b, D));
-    if (l.wc != kNone)   // per-CTA operand pieces of the cluster incremental step, from the bf16 matrices just packed
-      W2VS_TRY(launch_pack_cluster(cfg, at<void>(d_packed, l.wqkv), at<void>(d_packed, l.wo), at<void>(d_packed, l.w1),
-                                   at<void>(d_packed, l.w2), at<void>(d_packed, l.wc), st));
+    if (l.wc != kNone) {   // per-CTA operand pieces + LayerNorm fold vectors of the cluster incremental step, from the tensors just packed
+      ClusterPackArgs cp{};
+      cp.wqkv = at<void>(d_packed, l.wqkv); cp.wo = at<void>(d_packed, l.wo); cp.w1 = at<void>(d_packed, l.w1); cp.w2 = at<void>(d_packed, l.w2);
+      cp.ln1_w = at<float>(d_packed, l.ln1_w); cp.ln1_b = at<float>(d_packed, l.ln1_b); cp.bqkv = at<float>(d_packed, l.bqkv);
+      cp.ln2_w = at<float>(d_packed, l.ln2_w); cp.ln2_b = at<float>(d_packed, l.ln2_b); cp.b1 = at<float>(d_packed, l.b1);
+      cp.dst = at<void>(d_packed, l.wc);
+      W2VS_TRY(launch_pack_cluster(cfg, cp, st));
+    }
   }
   W2VS_TRY(copy_f32(wl.enc_ln_w, D));
   W2VS_TRY(copy_f32(wl.enc_ln_b, D));

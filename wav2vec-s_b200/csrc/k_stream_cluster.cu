@@ -105,10 +105,17 @@ struct CK {
   static constexpr int G_B = cmax(ROWS * PG, ROWS * PH);
   static constexpr int S_CTX = S_G + G_B;
   static constexpr int S_MRG = S_CTX + 16 * PO;                       // attention merge: 4 x ([16][68] O + [16][2] (m, l)) fp32
-  static constexpr int S_BAR = S_MRG + 4 * MRG_BLK * 4;
+  static constexpr int S_FIN = S_MRG + 4 * MRG_BLK * 4;            // [32 rows][8]: rstd, m_j - mean (j < 4) of the folded LayerNorm
+  static constexpr int S_BAR = S_FIN + ROWS * 32;
   static constexpr int S_END = S_BAR + 128;
   // phase A scratch after the reduce: rx2 [4][16][16], ml_rx [4][16][2]   (fp32, written by the peers)
   static constexpr int X_RX2 = 8192, X_ML = 12288;
+  // behind the CTA blocks of a layer: the vectors that fold the LayerNorm into the first products (fp32)
+  //   sq [4][3D], bq [3D]: s_j[n] = sum over K slice j of gamma_k W[n][k], b[n] = bias[n] + sum_k beta_k W[n][k]   (q|k|v rows)
+  //   s1 [4][F],  b1 [F]:  the same for fc1
+  static constexpr size_t FOLD_OFF = (size_t)CL * NC * CTA_B;
+  static constexpr size_t F_SQ = FOLD_OFF, F_BQ = F_SQ + (size_t)CL * 3 * D * 4, F_S1 = F_BQ + (size_t)3 * D * 4,
+                          F_B1 = F_S1 + (size_t)CL * F * 4, LAYER_B = F_B1 + (size_t)F * 4;
   static_assert(D % 128 == 0 && D == 64 * H && HC % 64 == 0 && KS % 16 == 0, "model shape");
   static_assert(S_END + 128 <= 232448, "shared memory");
 };
@@ -276,13 +283,19 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
     const uint8_t* Wl = a.W + (size_t)l * a.layer_stride;
     const bool pa_ = (p & 1) == 0;
     constexpr int LPV = (K::KS * 4 + 127) / 128;          // 128-byte lines per vector slice
-    if (tid < 3 * LPV) {
+    if (tid < 2 * LPV) {                                  // LayerNorm weight and the second product's bias over the K slice
       const int v = tid / LPV, i = tid - v * LPV;
-      const unsigned long long off = pa_ ? (v == 0 ? a.ln1_w : (v == 1 ? a.ln1_b : a.bo)) : (v == 0 ? a.ln2_w : (v == 1 ? a.ln2_b : a.b2));
+      const unsigned long long off = pa_ ? (v == 0 ? a.ln1_w : a.bo) : (v == 0 ? a.ln2_w : a.b2);
       prefetch_l2(Wl + off + 4 * (rank * K::KS) + 128 * i);
-    } else if (tid >= 32 && tid < 32 + 6) {
-      if (pa_) prefetch_l2(Wl + a.bqkv + 4 * (((tid - 32) >> 1) * D + (cl >> 1) * 64) + 128 * ((tid - 32) & 1));
-      else if (tid < 32 + 2) prefetch_l2(Wl + a.b1 + 4 * (cl * K::HC + rank * K::HR) + 128 * (tid - 32));
+    } else if (tid >= 64 && tid < 64 + 5 * 6) {           // fold vectors (4 x s_j, b) over the columns this CTA reduces
+      const int v = (tid - 64) / 6, i = (tid - 64) % 6;
+      if (pa_) {        // q|k|v rows of the head: three runs of 64 floats (two lines each)
+        const size_t base = v < 4 ? K::F_SQ + (size_t)v * 3 * D * 4 : K::F_BQ;
+        prefetch_l2(Wl + a.wc + base + 4 * ((i >> 1) * D + (cl >> 1) * 64) + 128 * (i & 1));
+      } else if (i < 2) {
+        const size_t base = v < 4 ? K::F_S1 + (size_t)v * F * 4 : K::F_B1;
+        prefetch_l2(Wl + a.wc + base + 4 * (cl * K::HC + rank * K::HR) + 128 * i);
+      }
     }
   };
   // exchange barriers (byte-counting, one use per layer): phase A statistics, partial q|k|v, gathered q|k|v, attention
@@ -341,16 +354,17 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
         mbar_expect_tx(bar_slot + XB_CG, (uint32_t)(CL * Mt * K::HR * 2));
       }
     }
-    // ================= LayerNorm of the K slice =================
-    float4 x[4][K::NV4], gm[K::NV4], bt[K::NV4];
+    // ================= operand rows of the first product: the K slice, centred and scaled =================
+    // LayerNorm is folded into the product (see the reduce stages): the operand is bf16((x - m_j) gamma) with m_j the
+    // row's mean over THIS slice -- known after one warp sum, no exchange -- so the product starts an exchange and a
+    // normalisation pass earlier; centring on the slice mean keeps the rounding as fine as that of the normalised
+    // row (rounding x gamma itself would lose |mean| / std in accuracy).
+    float4 x[4][K::NV4], gm[K::NV4];
 #pragma unroll
     for (int j = 0; j < K::NV4; ++j) {
       const int c = 4 * lane + 128 * j;
-      gm[j] = bt[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c < K::KS) {
-        gm[j] = *reinterpret_cast<const float4*>(Wl + (pa ? a.ln1_w : a.ln2_w) + 4 * (rank * K::KS + c));
-        bt[j] = *reinterpret_cast<const float4*>(Wl + (pa ? a.ln1_b : a.ln2_b) + 4 * (rank * K::KS + c));
-      }
+      gm[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < K::KS) gm[j] = *reinterpret_cast<const float4*>(Wl + (pa ? a.ln1_w : a.ln2_w) + 4 * (rank * K::KS + c));
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = 4 * warp + i;
@@ -390,6 +404,7 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
     warp_sum4(mean_i);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
+      const int r = 4 * warp + i;
       const float mean = mean_i[i] * (1.0f / K::KS);
       float d2 = 0.f;
 #pragma unroll
@@ -397,57 +412,49 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
         if (4 * lane + 128 * j < K::KS) {
           const float d0 = x[i][j].x - mean, d1 = x[i][j].y - mean, d2_ = x[i][j].z - mean, d3 = x[i][j].w - mean;
           d2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2_, d2_, fmaf(d3, d3, d2))));
+          uint2 u = make_uint2(0u, 0u);
+          if (r < Mt) {
+            u.x = pack_bf16x2(d0 * gm[j].x, d1 * gm[j].y);
+            u.y = pack_bf16x2(d2_ * gm[j].z, d3 * gm[j].w);
+          }
+          *reinterpret_cast<uint2*>(sm + K::S_A + r * K::PQ + 2 * (4 * lane + 128 * j)) = u;
         }
       mean_i[i] = mean;
       m2_i[i] = d2;
     }
-    warp_sum4(m2_i);
     CL_TRACE(l, pa ? 18 : 20);
+    // the statistics of the slice (mean, centred sum of squares) for the reduce stage of every CTA of the cluster
+    warp_sum4(m2_i);
     if (lane < CL) {
       const uint32_t dst = rbase(lane) + K::S_STAT + (uint32_t)((rank * ROWS + 4 * warp) * 8);
       const uint32_t mb = rbase(lane) + K::S_BAR + (pa ? XB_ASTAT : XB_CSTAT);
 #pragma unroll
       for (int i = 0; i < 4; ++i) st_async_v2f(dst + i * 8, mean_i[i], m2_i[i], mb);
     }
-    ok = mbar_wait(bar_slot + (pa ? XB_ASTAT : XB_CSTAT), lpar) && ok;
     CL_TRACE(l, pa ? 19 : 21);
-    {
-      float ms[4], qs[4], mean[4], m2[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        ms[i] = qs[i] = 0.f;
-        if (lane < CL) {
-          const float2 v = *reinterpret_cast<const float2*>(sm + K::S_STAT + (lane * ROWS + 4 * warp + i) * 8);
-          ms[i] = v.x; qs[i] = v.y;
-        }
-        mean[i] = ms[i];
-      }
-      warp_sum4(mean);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        mean[i] *= 1.0f / CL;
-        const float dev = lane < CL ? ms[i] - mean[i] : 0.f;
-        m2[i] = fmaf((float)K::KS * dev, dev, qs[i]);
-      }
-      warp_sum4(m2);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = 4 * warp + i;
-        const float rstd = 1.0f / sqrtf(m2[i] * (1.0f / D) + 1e-5f), mu = mean[i];
-#pragma unroll
-        for (int j = 0; j < K::NV4; ++j)
-          if (4 * lane + 128 * j < K::KS) {
-            uint2 u = make_uint2(0u, 0u);
-            if (r < Mt) {
-              u.x = pack_bf16x2((x[i][j].x - mu) * rstd * gm[j].x + bt[j].x, (x[i][j].y - mu) * rstd * gm[j].y + bt[j].y);
-              u.y = pack_bf16x2((x[i][j].z - mu) * rstd * gm[j].z + bt[j].z, (x[i][j].w - mu) * rstd * gm[j].w + bt[j].w);
-            }
-            *reinterpret_cast<uint2*>(sm + K::S_A + r * K::PQ + 2 * (4 * lane + 128 * j)) = u;
-          }
-      }
-    }
     __syncthreads();
     CL_TRACE(l, pa ? 1 : 9);
+    // The folded LayerNorm, applied where the partial products are reduced:
+    //   y[r][n] = rstd_r (sum_j P_j[r][n] + sum_j (m_j[r] - mean_r) s_j[n]) + b[n]
+    // with P_j the product of slice j's operand rows, (m_j, M2_j) the slice statistics every CTA has received, mean and
+    // variance of the row by Chan's combination, s_j / b the vectors packed with the weights.  One thread per row
+    // leaves rstd and the four offsets in shared memory.
+    auto fold_stats = [&]() {
+      if (tid < ROWS) {
+        const float2* st = reinterpret_cast<const float2*>(sm + K::S_STAT);
+        float mj[CL], mean = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < CL; ++j) { mj[j] = st[j * ROWS + tid].x; mean += mj[j]; }
+        mean *= 1.0f / CL;
+#pragma unroll
+        for (int j = 0; j < CL; ++j) { const float dv = mj[j] - mean; m2 += st[j * ROWS + tid].y + (float)K::KS * dv * dv; }
+        float* fin = reinterpret_cast<float*>(sm + K::S_FIN) + tid * 8;
+        fin[0] = 1.0f / sqrtf(m2 * (1.0f / D) + 1e-5f);
+#pragma unroll
+        for (int j = 0; j < CL; ++j) fin[1 + j] = mj[j] - mean;
+      }
+      __syncthreads();
+    };
 
     if (pa) {
       // ================= q | k | v of head cl / 2 (all rows): K split over the CTAs, reduce-scatter =================
@@ -508,17 +515,23 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
         // ---- reduce, bias, bf16, all-gather; K / V rows -> cache (by the cluster of the head's first query tile) ----
         uint32_t* stage = reinterpret_cast<uint32_t*>(sm + K::S_A);          // [32][24] bf16 pairs
         const float* rx = reinterpret_cast<const float*>(sm + K::S_SCR);
-        const float* bq = reinterpret_cast<const float*>(Wl + a.bqkv);
+        ok = mbar_wait(bar_slot + XB_ASTAT, lpar) && ok;
+        fold_stats();
+        const float* sq = reinterpret_cast<const float*>(Wl + a.wc + K::F_SQ);
+        const float* bq = reinterpret_cast<const float*>(Wl + a.wc + K::F_BQ);
         for (int it = tid; it < Mt * 24; it += CT) {
           const int r = it / 24, cp = it - r * 24, col = 48 * rank + 2 * cp;
-          const float2 b = *reinterpret_cast<const float2*>(bq + (col >> 6) * D + head * 64 + (col & 63));
-          float v0 = b.x, v1 = b.y;
+          const int n = (col >> 6) * D + head * 64 + (col & 63);
+          const float* fin = reinterpret_cast<const float*>(sm + K::S_FIN) + r * 8;
+          float v0 = 0.f, v1 = 0.f;
 #pragma unroll
           for (int s = 0; s < CL; ++s) {
             const float2 p = *reinterpret_cast<const float2*>(rx + (s * ROWS + r) * 48 + 2 * cp);
-            v0 += p.x; v1 += p.y;
+            const float2 sj = *reinterpret_cast<const float2*>(sq + (size_t)s * 3 * D + n);
+            v0 += p.x + fin[1 + s] * sj.x; v1 += p.y + fin[1 + s] * sj.y;
           }
-          stage[it] = pack_bf16x2(v0, v1);
+          const float2 b = *reinterpret_cast<const float2*>(bq + n);
+          stage[it] = pack_bf16x2(fmaf(fin[0], v0, b.x), fmaf(fin[0], v1, b.y));
         }
         __syncthreads();
         // every warp of this CTA is past its reads of the q|k rows: request fc1's rows into that slot
@@ -763,18 +776,23 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
       {
         uint32_t* stage = reinterpret_cast<uint32_t*>(sm + K::S_A);          // [32][HR / 2] bf16 pairs
         const float* rx = reinterpret_cast<const float*>(sm + K::S_SCR);
-        const float* b1 = reinterpret_cast<const float*>(Wl + a.b1) + cl * K::HC + rank * K::HR;
+        ok = mbar_wait(bar_slot + XB_CSTAT, lpar) && ok;
+        fold_stats();
+        const float* s1 = reinterpret_cast<const float*>(Wl + a.wc + K::F_S1) + cl * K::HC + rank * K::HR;
+        const float* b1 = reinterpret_cast<const float*>(Wl + a.wc + K::F_B1) + cl * K::HC + rank * K::HR;
         constexpr int HP = K::HR / 2;
         for (int it = tid; it < Mt * HP; it += CT) {
           const int r = it / HP, cp = it - r * HP;
-          const float2 b = *reinterpret_cast<const float2*>(b1 + 2 * cp);
-          float v0 = b.x, v1 = b.y;
+          const float* fin = reinterpret_cast<const float*>(sm + K::S_FIN) + r * 8;
+          float v0 = 0.f, v1 = 0.f;
 #pragma unroll
           for (int s = 0; s < CL; ++s) {
             const float2 p = *reinterpret_cast<const float2*>(rx + (s * ROWS + r) * K::HR + 2 * cp);
-            v0 += p.x; v1 += p.y;
+            const float2 sj = *reinterpret_cast<const float2*>(s1 + (size_t)s * F + 2 * cp);
+            v0 += p.x + fin[1 + s] * sj.x; v1 += p.y + fin[1 + s] * sj.y;
           }
-          stage[it] = pack_bf16x2(gelu_tanh(v0), gelu_tanh(v1));
+          const float2 b = *reinterpret_cast<const float2*>(b1 + 2 * cp);
+          stage[it] = pack_bf16x2(gelu_tanh(fmaf(fin[0], v0, b.x)), gelu_tanh(fmaf(fin[0], v1, b.y)));
         }
         __syncthreads();
         if (tid == 0) issue_piece(4 * l + 4);      // every warp is past fc1's rows: next layer's q|k rows into that slot
@@ -893,6 +911,41 @@ pack_cluster_kernel(const bf16* __restrict__ wqkv, const bf16* __restrict__ wo, 
   }
 }
 
+// fold vectors of one layer: one warp per weight row n (q|k|v rows, then fc1 rows)
+template <int D, int F, int H>
+__global__ void __launch_bounds__(256)
+pack_fold_kernel(const bf16* __restrict__ wqkv, const bf16* __restrict__ w1, const float* __restrict__ ln1_w,
+                 const float* __restrict__ ln1_b, const float* __restrict__ bqkv, const float* __restrict__ ln2_w,
+                 const float* __restrict__ ln2_b, const float* __restrict__ b1, uint8_t* __restrict__ dst) {
+  using K = CK<D, F, H>;
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= 3 * D + F) return;
+  const bool qkv = n < 3 * D;
+  const int m = qkv ? n : n - 3 * D;
+  const bf16* w = (qkv ? wqkv : w1) + (size_t)m * D;
+  const float* gm = qkv ? ln1_w : ln2_w;
+  const float* bt = qkv ? ln1_b : ln2_b;
+  float sj[CL] = {}, sb = 0.f;
+#pragma unroll
+  for (int j = 0; j < CL; ++j)
+    for (int k = j * K::KS + lane; k < (j + 1) * K::KS; k += 32) {
+      const float wv = __bfloat162float(w[k]);
+      sj[j] = fmaf(gm[k], wv, sj[j]);
+      sb = fmaf(bt[k], wv, sb);
+    }
+#pragma unroll
+  for (int j = 0; j < CL; ++j) sj[j] = warp_sum(sj[j]);
+  sb = warp_sum(sb);
+  if (lane == 0) {
+    float* sv = reinterpret_cast<float*>(dst + (qkv ? K::F_SQ : K::F_S1));
+    float* bv = reinterpret_cast<float*>(dst + (qkv ? K::F_BQ : K::F_B1));
+    const int N = qkv ? 3 * D : F;
+#pragma unroll
+    for (int j = 0; j < CL; ++j) sv[(size_t)j * N + m] = sj[j];
+    bv[m] = (qkv ? bqkv[m] : b1[m]) + sb;
+  }
+}
+
 template <int D, int F, int H>
 void launch_config(cudaLaunchConfig_t& lc, cudaLaunchAttribute (&attr)[2], cudaStream_t st) {
   using K = CK<D, F, H>;
@@ -941,9 +994,11 @@ w2vs_status_t launch_t(const ClArgs& a, cudaStream_t st) {
 }
 
 template <int D, int F, int H>
-w2vs_status_t pack_t(const void* wqkv, const void* wo, const void* w1, const void* w2, void* dst, cudaStream_t st) {
-  pack_cluster_kernel<D, F, H><<<CL * CK<D, F, H>::NC, 256, 0, st>>>((const bf16*)wqkv, (const bf16*)wo, (const bf16*)w1, (const bf16*)w2, (uint8_t*)dst);
+w2vs_status_t pack_t(const ClusterPackArgs& p, cudaStream_t st) {
+  pack_cluster_kernel<D, F, H><<<CL * CK<D, F, H>::NC, 256, 0, st>>>((const bf16*)p.wqkv, (const bf16*)p.wo, (const bf16*)p.w1, (const bf16*)p.w2, (uint8_t*)p.dst);
   W2VS_CHECK_LAUNCH("pack_cluster_kernel");
+  pack_fold_kernel<D, F, H><<<(3 * D + F + 7) / 8, 256, 0, st>>>((const bf16*)p.wqkv, (const bf16*)p.w1, p.ln1_w, p.ln1_b, p.bqkv, p.ln2_w, p.ln2_b, p.b1, (uint8_t*)p.dst);
+  W2VS_CHECK_LAUNCH("pack_fold_kernel");
   return W2VS_OK;
 }
 
@@ -956,7 +1011,7 @@ static int g_cluster_trace_on = 0;    // process-wide debug switch (w2vs_debug_c
 
 size_t stream_cluster_layer_bytes(const w2vs_config* cfg) {
   if (!stream_cluster_model(cfg)) return 0;
-#define X(D_, F_, H_) if (cfg->embed_dim == D_ && cfg->ffn_dim == F_ && cfg->heads == H_) return (size_t)CL * CK<D_, F_, H_>::NC * CK<D_, F_, H_>::CTA_B;
+#define X(D_, F_, H_) if (cfg->embed_dim == D_ && cfg->ffn_dim == F_ && cfg->heads == H_) return CK<D_, F_, H_>::LAYER_B;
   W2VS_CLUSTER_SHAPES(X)
 #undef X
   return 0;
@@ -970,9 +1025,8 @@ bool stream_cluster_applicable(const w2vs_config* cfg, int B, int ntok) {
   return false;
 }
 
-w2vs_status_t launch_pack_cluster(const w2vs_config* cfg, const void* wqkv, const void* wo, const void* w1,
-                                  const void* w2, void* dst, cudaStream_t st) {
-#define X(D_, F_, H_) if (cfg->embed_dim == D_ && cfg->ffn_dim == F_ && cfg->heads == H_) return pack_t<D_, F_, H_>(wqkv, wo, w1, w2, dst, st);
+w2vs_status_t launch_pack_cluster(const w2vs_config* cfg, const ClusterPackArgs& p, cudaStream_t st) {
+#define X(D_, F_, H_) if (cfg->embed_dim == D_ && cfg->ffn_dim == F_ && cfg->heads == H_) return pack_t<D_, F_, H_>(p, st);
   W2VS_CLUSTER_SHAPES(X)
 #undef X
   set_error("unsupported: no cluster step kernel for this model shape");

@@ -160,8 +160,12 @@ constexpr int kStreamClusterSize = 4;
 size_t stream_cluster_layer_bytes(const w2vs_config* cfg);      // bytes of LayerW::wc per layer, 0 = kernel not available
 bool stream_cluster_applicable(const w2vs_config* cfg, int B, int ntok);
 w2vs_status_t launch_stream_cluster(const StreamFusedArgs& a, cudaStream_t st);
-w2vs_status_t launch_pack_cluster(const w2vs_config* cfg, const void* wqkv, const void* wo, const void* w1,
-                                  const void* w2, void* dst, cudaStream_t st);
+struct ClusterPackArgs {      // packed tensors of one layer (device pointers into the blob) -> its LayerW::wc region
+  const void *wqkv, *wo, *w1, *w2;
+  const float *ln1_w, *ln1_b, *bqkv, *ln2_w, *ln2_b, *b1;
+  void* dst;
+};
+w2vs_status_t launch_pack_cluster(const w2vs_config* cfg, const ClusterPackArgs& p, cudaStream_t st);
 w2vs_status_t debug_read_cluster_fault(int* out);
 w2vs_status_t debug_read_cluster_trace(unsigned long long* out, int n);
 void debug_cluster_trace_enable(int on);
