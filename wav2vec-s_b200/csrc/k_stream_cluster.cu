@@ -481,6 +481,7 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
         }
       };
       KVF cur, nxt;
+      float2 fsj[CL], fb = make_float2(0.f, 0.f);
       ok = wait_piece(4 * l) && ok;
       ok = wait_piece(4 * l + 1) && ok;
       CL_TRACE(l, 15);
@@ -506,6 +507,15 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
         // the first attention step of this warp, if it reads the cache (rows of earlier decision steps): in flight
         // during the reduce and gather stages
         if (grp < n_past) load_step(grp, cur);
+        // the reduce stage below: thread = (column pair cp of the 24 this CTA owns, rows rg, rg + 10, rg + 20); its fold
+        // vector entries are requested now and arrive while the partial sums are still in flight
+        if (tid < 240) {
+          const int cp = tid % 24, col = 48 * rank + 2 * cp, n = (col >> 6) * D + head * 64 + (col & 63);
+          const float* sq = reinterpret_cast<const float*>(Wl + a.wc + K::F_SQ);
+#pragma unroll
+          for (int s = 0; s < CL; ++s) fsj[s] = *reinterpret_cast<const float2*>(sq + (size_t)s * 3 * D + n);
+          fb = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(Wl + a.wc + K::F_BQ) + n);
+        }
         __syncthreads();       // all warps are past their reads of the operand slice: its memory becomes the staging rows
         ok = mbar_wait(bar_slot + XB_ARX1, lpar) && ok;
       }
@@ -517,21 +527,18 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
         const float* rx = reinterpret_cast<const float*>(sm + K::S_SCR);
         ok = mbar_wait(bar_slot + XB_ASTAT, lpar) && ok;
         fold_stats();
-        const float* sq = reinterpret_cast<const float*>(Wl + a.wc + K::F_SQ);
-        const float* bq = reinterpret_cast<const float*>(Wl + a.wc + K::F_BQ);
-        for (int it = tid; it < Mt * 24; it += CT) {
-          const int r = it / 24, cp = it - r * 24, col = 48 * rank + 2 * cp;
-          const int n = (col >> 6) * D + head * 64 + (col & 63);
-          const float* fin = reinterpret_cast<const float*>(sm + K::S_FIN) + r * 8;
-          float v0 = 0.f, v1 = 0.f;
+        if (tid < 240) {
+          const int cp = tid % 24;
+          for (int r = tid / 24; r < Mt; r += 10) {
+            const float* fin = reinterpret_cast<const float*>(sm + K::S_FIN) + r * 8;
+            float v0 = 0.f, v1 = 0.f;
 #pragma unroll
-          for (int s = 0; s < CL; ++s) {
-            const float2 p = *reinterpret_cast<const float2*>(rx + (s * ROWS + r) * 48 + 2 * cp);
-            const float2 sj = *reinterpret_cast<const float2*>(sq + (size_t)s * 3 * D + n);
-            v0 += p.x + fin[1 + s] * sj.x; v1 += p.y + fin[1 + s] * sj.y;
+            for (int s = 0; s < CL; ++s) {
+              const float2 p = *reinterpret_cast<const float2*>(rx + (s * ROWS + r) * 48 + 2 * cp);
+              v0 += p.x + fin[1 + s] * fsj[s].x; v1 += p.y + fin[1 + s] * fsj[s].y;
+            }
+            stage[r * 24 + cp] = pack_bf16x2(fmaf(fin[0], v0, fb.x), fmaf(fin[0], v1, fb.y));
           }
-          const float2 b = *reinterpret_cast<const float2*>(bq + n);
-          stage[it] = pack_bf16x2(fmaf(fin[0], v0, b.x), fmaf(fin[0], v1, b.y));
         }
         __syncthreads();
         // every warp of this CTA is past its reads of the q|k rows: request fc1's rows into that slot
@@ -769,6 +776,17 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
             if (r0 + 8 < Mt) st_async_v2f(dst + (uint32_t)(((r0 + 8) * K::HR + c) * 4), acc[mt][nt][2], acc[mt][nt][3], mb);
           }
       }
+      // the reduce stage below: thread = (column pair cp of the HR / 2 this CTA owns, rows rg, rg + 256 / HP, ...); its
+      // fold vector entries are requested now
+      constexpr int HP = K::HR / 2, RSTEP = CT / HP;
+      float2 fsj[CL], fb;
+      {
+        const int cp = tid % HP;
+        const float* s1 = reinterpret_cast<const float*>(Wl + a.wc + K::F_S1) + cl * K::HC + rank * K::HR;
+#pragma unroll
+        for (int s = 0; s < CL; ++s) fsj[s] = *reinterpret_cast<const float2*>(s1 + (size_t)s * F + 2 * cp);
+        fb = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(Wl + a.wc + K::F_B1) + cl * K::HC + rank * K::HR + 2 * cp);
+      }
       __syncthreads();         // all warps are past their reads of the operand slice: its memory becomes the staging rows
       ok = mbar_wait(bar_slot + XB_CRX1, lpar) && ok;
       CL_TRACE(l, 10);
@@ -778,21 +796,18 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
         const float* rx = reinterpret_cast<const float*>(sm + K::S_SCR);
         ok = mbar_wait(bar_slot + XB_CSTAT, lpar) && ok;
         fold_stats();
-        const float* s1 = reinterpret_cast<const float*>(Wl + a.wc + K::F_S1) + cl * K::HC + rank * K::HR;
-        const float* b1 = reinterpret_cast<const float*>(Wl + a.wc + K::F_B1) + cl * K::HC + rank * K::HR;
-        constexpr int HP = K::HR / 2;
-        for (int it = tid; it < Mt * HP; it += CT) {
-          const int r = it / HP, cp = it - r * HP;
-          const float* fin = reinterpret_cast<const float*>(sm + K::S_FIN) + r * 8;
-          float v0 = 0.f, v1 = 0.f;
+        {
+          const int cp = tid % HP;
+          for (int r = tid / HP; r < Mt; r += RSTEP) {
+            const float* fin = reinterpret_cast<const float*>(sm + K::S_FIN) + r * 8;
+            float v0 = 0.f, v1 = 0.f;
 #pragma unroll
-          for (int s = 0; s < CL; ++s) {
-            const float2 p = *reinterpret_cast<const float2*>(rx + (s * ROWS + r) * K::HR + 2 * cp);
-            const float2 sj = *reinterpret_cast<const float2*>(s1 + (size_t)s * F + 2 * cp);
-            v0 += p.x + fin[1 + s] * sj.x; v1 += p.y + fin[1 + s] * sj.y;
+            for (int s = 0; s < CL; ++s) {
+              const float2 p = *reinterpret_cast<const float2*>(rx + (s * ROWS + r) * K::HR + 2 * cp);
+              v0 += p.x + fin[1 + s] * fsj[s].x; v1 += p.y + fin[1 + s] * fsj[s].y;
+            }
+            stage[r * HP + cp] = pack_bf16x2(gelu_tanh(fmaf(fin[0], v0, fb.x)), gelu_tanh(fmaf(fin[0], v1, fb.y)));
           }
-          const float2 b = *reinterpret_cast<const float2*>(b1 + 2 * cp);
-          stage[it] = pack_bf16x2(gelu_tanh(fmaf(fin[0], v0, b.x)), gelu_tanh(fmaf(fin[0], v1, b.y)));
         }
         __syncthreads();
         if (tid == 0) issue_piece(4 * l + 4);      // every warp is past fc1's rows: next layer's q|k rows into that slot
