@@ -250,7 +250,7 @@ int64_t w2vs_prof_collect(char* buf, int64_t capacity);
  * w2vs_debug_fault_flags: bit 0 tcgen05 GEMM, bit 1 tcgen05 attention, bit 2 fused step kernel, bit 3 cluster step kernel -- set when a
  *   pipeline / barrier wait timed out inside a kernel (a bug; the kernels end instead of hanging). */
 w2vs_status_t w2vs_debug_fused_trace(uint64_t* out, int32_t n);
-/* same for the cluster step kernel: CTA 0, [64 layers][24 events].  The stamps are off by default:
+/* same for the cluster step kernel: CTA 0, [64 layers][32 events].  The stamps are off by default:
  * w2vs_debug_cluster_trace(NULL, 1) switches them on for the process, (NULL, 0) off. */
 w2vs_status_t w2vs_debug_cluster_trace(uint64_t* out, int32_t n);
 w2vs_status_t w2vs_debug_fault_flags(int32_t* flags);

@@ -52,9 +52,9 @@ for _ in range(6):
     pos += 5120
 print(f"step latency (ms): {lat}; left context {pos / 16000:.1f} s")
 if impl == 3:
-    buf = (C.c_uint64 * (64 * 24))()
+    buf = (C.c_uint64 * (64 * 32))()
     cabi.check(cabi.lib().w2vs_debug_cluster_trace(buf, len(buf)), "trace")
-    t = np.frombuffer(buf, dtype=np.uint64).astype(np.int64).reshape(64, 24)[:24]
+    t = np.frombuffer(buf, dtype=np.uint64).astype(np.int64).reshape(64, 32)[:24]
     ev = [0, 18, 19, 1, 15, 2, 3, 4, 5, 6, 7, 13, 8, 20, 21, 9, 16, 10, 11, 17, 12, 14]
     names = ["x slice + local stats", "stats exchange", "normalise", "wait weights", "QKV+scatter", "reduce+gather", "attention", "merge-send", "merge+ctx gather",
              "out_proj", "grid barrier", "(next phase start)", "x slice + local stats", "stats exchange", "normalise", "wait weights", "fc1+scatter", "gelu+gather",
@@ -66,6 +66,8 @@ if impl == 3:
         print(f"  {n:20s} {v:6.2f}")
     print(f"  phase C grid barrier: bar.sync {(t[:, 22] - t[:, 12]).mean() / 1e3:.2f}, release + arrive {(t[:, 23] - t[:, 22]).mean() / 1e3:.2f}, "
           f"poll + bar.sync {(t[:, 14] - t[:, 23]).mean() / 1e3:.2f} us")
+    print(f"  QKV stage: product {(t[:, 24] - t[:, 15]).mean() / 1e3:.2f}, sends {(t[:, 25] - t[:, 24]).mean() / 1e3:.2f}, "
+          f"early loads + sync + wait for the peers {(t[:, 2] - t[:, 25]).mean() / 1e3:.2f} us")
     print(f"  layer total {(seq[:, -1] - seq[:, 0]).mean() / 1e3:.2f} us; all layers {(t[23, 14] - t[0, 0]) / 1e3:.1f} us")
 flags = C.c_int32(0)
 cabi.check(cabi.lib().w2vs_debug_fault_flags(C.byref(flags)), "faults")

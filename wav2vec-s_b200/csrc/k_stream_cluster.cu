@@ -45,7 +45,7 @@
 
 namespace w2vs {
 __device__ int g_cluster_fault = 0;                       // a barrier / pipeline wait timed out (diagnostics)
-__device__ unsigned long long g_cluster_trace[64][24];    // globaltimer stamps of CTA 0, [layer][event]
+__device__ unsigned long long g_cluster_trace[64][32];    // globaltimer stamps of CTA 0, [layer][event]
 }
 #define W2VS_TC_FAULT_FLAG (&::w2vs::g_cluster_fault)
 #include "tc_common.cuh"
@@ -486,6 +486,9 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
       ok = wait_piece(4 * l + 1) && ok;
       CL_TRACE(l, 15);
       if (a_on) {
+        // (eight warps x three n tiles: the product is bound by the issue rate of mma.sync -- 768 HMMA.16816 per CTA at one
+        //  per ~12 cycles and SM sub-partition = 1.15 us measured; four warps x six n tiles, which re-read the operand
+        //  tile from shared memory half as often, take 1.6 us)
         float acc[2][3][4] = {};
         uint32_t bb[3];
 #pragma unroll
@@ -494,6 +497,7 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
           bb[nt] = n < 16 ? sb + K::S_SLOT0 + (uint32_t)(n * 8) * K::PQ : sb + K::S_SLOT1 + (uint32_t)((n - 16) * 8) * K::PQ;
         }
         mma_block<3, K::KS / 16, K::PQ, K::PQ>(sb + K::S_A, bb, acc, lane, two_mt);
+        CL_TRACE(l, 24);
         const uint32_t dst = rbase((warp >> 1)) + K::S_SCR + (uint32_t)(rank * ROWS * 48 * 4);
         const uint32_t mb = rbase((warp >> 1)) + K::S_BAR + XB_ARX1;
 #pragma unroll
@@ -506,6 +510,7 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
           }
         // the first attention step of this warp, if it reads the cache (rows of earlier decision steps): in flight
         // during the reduce and gather stages
+        CL_TRACE(l, 25);
         if (grp < n_past) load_step(grp, cur);
         // the reduce stage below: thread = (column pair cp of the 24 this CTA owns, rows rg, rg + 10, rg + 20); its fold
         // vector entries are requested now and arrive while the partial sums are still in flight
@@ -1073,7 +1078,7 @@ w2vs_status_t launch_stream_cluster(const StreamFusedArgs& h, cudaStream_t st) {
 void debug_cluster_trace_enable(int on) { g_cluster_trace_on = on; }
 
 w2vs_status_t debug_read_cluster_trace(unsigned long long* out, int n) {
-  if (n > 64 * 24) n = 64 * 24;
+  if (n > 64 * 32) n = 64 * 32;
   cudaError_t e = cudaMemcpyFromSymbol(out, g_cluster_trace, (size_t)n * 8);
   if (e != cudaSuccess) { set_error("read g_cluster_trace: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
   return W2VS_OK;
