@@ -24,7 +24,10 @@
 //                          commits the MMAs that read a ring slot, so it knows when the slot is free.  The refills
 //                          are deferred by one step -- K's slot of S(g+1) after PV(g) has been issued, V's slot of
 //                          PV(g-1) at the start of tile g, the next Q after the item's last S -- so the thread never
-//                          waits for an MMA it has just issued)
+//                          waits for an MMA it has just issued).  The role is entered through elect_one(): behind
+//                          `lane == 0` ptxas wrapped every UTCHMMA / UTMALDG in an ELECT + R2UR.BROADCAST + BRA.U.ANY
+//                          loop and this thread needed 500 cycles to issue four MMAs -- its loop, 2500 cycles per
+//                          tile, was the kernel's period (clock64 trace); now 160 cycles per four MMAs.
 //                          S = Q K^T  (tcgen05.mma M=128,N=64,K=64: A,B K-major from smem -> TMEM cols 0..63)
 //                          O += P V   (M=128,N=64,K=64: A = bf16 P K-major from smem, B = V MN-major from smem
 //                          -> TMEM cols 64..127); owns the TMEM allocation.
@@ -255,7 +258,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // The thread that issues the MMAs also knows when each ring slot becomes free (it commits the MMAs that
     // read them), so it issues the TMA loads in its idle time: after S(g+1) is issued it waits for that MMA
     // (it would be waiting for P(g) anyway) and loads K(g+1+NS); after PV(g) it loads V(g+NS).
-    if (lane == 0) {
+    if (elect_one()) {
       // D=f32, A=B=bf16; QK: both K-major, N=64; PV: A K-major (P), B MN-major (bit 16), N=64; M=128
       constexpr uint32_t idesc_qk = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KT >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
       constexpr uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) |
@@ -453,7 +456,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       float m_ref = -INFINITY;
       uint64_t l2a = pack2(0.f, 0.f), l2b = pack2(0.f, 0.f);   // row sum (four accumulators)
       // the P buffer doubles as this warp's output staging tile: the previous item's TMA store must have read it
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the thread that issues the stores
       __syncwarp();
 
       for (int it = 0; it < n_kt && ok; ++it) {
@@ -647,7 +650,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           tma_store_2d_(&tmCtx, sP + (uint32_t)quarter * 32 * 128, out_col, out_row0);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -675,7 +678,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc_fence_before();   // orders these TMEM reads before this warp's next p_full arrive (next item overwrites O)
       TRACE(0, gt - 1, 13);
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging must outlive its last store
+    if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging must outlive its last store
   }
 
   tc_fence_before();

@@ -138,7 +138,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp == PRODUCER_WARP) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    // (single-thread roles are entered through elect_one(), see tc_common.cuh: behind `lane == 0` every TMA / MMA
+    //  instruction is wrapped in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop)
+    if (elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
       const uint32_t full_leader = mapa(bar_full, 0);
@@ -161,7 +163,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == MMA_WARP) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
+    if (leader && elect_one()) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=256 (cta_group::2)
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                  ((uint32_t)((2 * BM) >> 4) << 24);
@@ -212,7 +214,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
       for (int i = lane; i < CPW; i += 32) bs[i] = (bias != nullptr && colw + i < N) ? bias[bt * N + colw + i] : 0.f;
       // residual chunk 0 prefetch (overlaps the wait for the accumulator)
-      if (SLOTS == 2 && !kTmaReduce && has_residual && lane == 0) {
+      if (SLOTS == 2 && !kTmaReduce && has_residual && elect_one()) {
         bulk_wait_read<0>();                           // earlier stores from slot 0/1 have been read out
         mbar_expect_tx(my_res_bar, C2::kSlotBytes);
         tma_load_2d(slot0, &tmC, my_res_bar, colw, row0);
@@ -230,7 +232,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (SLOTS == 1) {
           // single slot: wait until the previous store has read it, then fetch this chunk's residual into it (the
           // accumulator load and the bias arithmetic below run while it is in flight)
-          if (lane == 0) {
+          if (elect_one()) {
             bulk_wait_read<0>();
             if (!kTmaReduce && has_residual) {
               mbar_expect_tx(my_res_bar, C2::kSlotBytes);
@@ -238,12 +240,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
         } else if (!kTmaReduce && has_residual) {
-          if (c + 1 < C2::kChunksPerWarp && lane == 0) {
+          if (c + 1 < C2::kChunksPerWarp && elect_one()) {
             bulk_wait_read<0>();                       // the store that used the other slot has drained it
             mbar_expect_tx(my_res_bar + 8 * (sl ^ 1), C2::kSlotBytes);
             tma_load_2d(slot0 + (sl ^ 1) * C2::kSlotBytes, &tmC, my_res_bar + 8 * (sl ^ 1), colw + (c + 1) * CHUNK, row0);
           }
-        } else if (lane == 0) {
+        } else if (elect_one()) {
           bulk_wait_read<1>();                         // the store issued two chunks ago (same slot) is done
         }
         uint32_t r[CHUNK];
@@ -288,7 +290,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         fence_async_smem();                            // generic-proxy writes -> visible to the TMA engine
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           if (kTmaReduce && has_residual) tma_reduce_add_2d(&tmC, slot, colw + c * CHUNK, row0);
           else if (n_batch > 1) tma_store_3d(&tmC, slot, colw + c * CHUNK, bt, row0);   // {column, product, row}: clipped at N
           else tma_store_2d(&tmC, slot, colw + c * CHUNK, row0);
@@ -301,7 +303,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * as);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-    if (lane == 0) bulk_wait_read<0>();                // smem must stay valid until the last store has read it
+    if (elect_one()) bulk_wait_read<0>();              // smem must stay valid until the last store has read it
   }
 
   tc_fence_before();

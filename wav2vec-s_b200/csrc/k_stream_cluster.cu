@@ -305,8 +305,11 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
     mbar_init(bar_slot, 1); mbar_init(bar_slot + 8, 1);
     for (uint32_t o = XB_ASTAT; o <= XB_CG; o += 8) mbar_init(bar_slot + o, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    issue_piece(0); issue_piece(1);
   }
+  // (bulk copies are issued inside an elect_one() region, see tc_common.cuh: behind `tid == 0` every UBLKCP sits in an
+  //  ELECT + R2UR.BROADCAST + BRA.U.ANY loop)
+  __syncwarp();
+  if (warp == 0 && elect_one()) { issue_piece(0); issue_piece(1); }
   // gather targets start as zeros (rows past the step's tokens are multiplied, never stored)
   for (int i = tid; i < (K::G_B + 16 * K::PO) / 16; i += CT) reinterpret_cast<uint4*>(sm + K::S_G)[i] = make_uint4(0u, 0u, 0u, 0u);
 
@@ -525,7 +528,7 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
         ok = mbar_wait(bar_slot + XB_ARX1, lpar) && ok;
       }
       CL_TRACE(l, 2);
-      if (!a_on && tid == 0) issue_piece(4 * l + 2);
+      if (!a_on && warp == 0 && elect_one()) issue_piece(4 * l + 2);
       if (a_on) {
         // ---- reduce, bias, bf16, all-gather; K / V rows -> cache (by the cluster of the head's first query tile) ----
         uint32_t* stage = reinterpret_cast<uint32_t*>(sm + K::S_A);          // [32][24] bf16 pairs
@@ -547,7 +550,7 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
         }
         __syncthreads();
         // every warp of this CTA is past its reads of the q|k rows: request fc1's rows into that slot
-        if (tid == 0) issue_piece(4 * l + 2);
+        if (warp == 0 && elect_one()) issue_piece(4 * l + 2);
         for (int idx = tid; idx < Mt * 6 * CL; idx += CT) {
           const int d = idx & (CL - 1), rc_ = idx >> 2, r = rc_ / 6, ch = rc_ - 6 * r;
           const uint4 v = *reinterpret_cast<const uint4*>(sm + K::S_A + r * 96 + ch * 16);
@@ -758,7 +761,7 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
         }
       }
       __syncthreads();
-      if (tid == 0) issue_piece(4 * l + 3);
+      if (warp == 0 && elect_one()) issue_piece(4 * l + 3);
       CL_TRACE(l, 7);
     } else {
       // ================= fc1 for the cluster's hidden units: K split over the CTAs, reduce-scatter =================
@@ -815,7 +818,7 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
           }
         }
         __syncthreads();
-        if (tid == 0) issue_piece(4 * l + 4);      // every warp is past fc1's rows: next layer's q|k rows into that slot
+        if (warp == 0 && elect_one()) issue_piece(4 * l + 4);      // every warp is past fc1's rows: next layer's q|k rows into that slot
         constexpr int CH = K::HR * 2 / 16;       // 16-byte chunks per row
         for (int idx = tid; idx < Mt * CH * CL; idx += CT) {
           const int d = idx & (CL - 1), rc_ = idx >> 2, r = rc_ / CH, ch = rc_ - CH * r;
@@ -844,7 +847,7 @@ stream_cluster_kernel(const __grid_constant__ ClArgs a) {
           }
       }
       __syncthreads();
-      if (tid == 0) issue_piece(4 * l + 5);      // next layer's v + out_proj rows
+      if (warp == 0 && elect_one()) issue_piece(4 * l + 5);      // next layer's v + out_proj rows
       CL_TRACE(l, 12);
     }
     // zero the buffer the NEXT phase accumulates into (it was last read in the previous phase).  Global writes sit at

@@ -139,6 +139,16 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N> __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
+// One thread of the (converged) warp.  A single-thread role must be entered through this and not through `lane == 0`:
+// inside an elect.sync region ptxas knows that one thread is active and issues UTCHMMA / UTMALDG with their operands
+// moved to uniform registers once; behind `lane == 0` it wraps EVERY such instruction in a loop of ELECT +
+// R2UR.BROADCAST + BRA.U.ANY (~100 cycles per instruction: the attention kernel's MMA thread took 500 cycles to issue
+// four MMAs and paced the whole kernel).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
