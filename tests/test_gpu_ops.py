@@ -28,7 +28,11 @@ def _gemm_ref(A, W, bias, res, gelu):
 
 @pytest.mark.parametrize("impl", [cabi.GEMM_TCGEN05_2CTA, cabi.GEMM_SIMT])
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 128, 192), (1000, 512, 1536), (257, 3072, 1024),
-                                   (4096, 1024, 4096), (24, 384, 128), (130, 64, 128), (5000, 768, 512)])
+                                   (4096, 1024, 4096), (24, 384, 128), (130, 64, 128), (5000, 768, 512),
+                                   # a few hundred rows (a batch of incremental streams): the in-place fp32 products
+                                   # run split over K with L2 reductions (uneven last range: 17 K blocks in two ranges)
+                                   (384, 1024, 4096), (384, 1024, 1024), (96, 1024, 4096), (200, 512, 2048),
+                                   (384, 1024, 1088)])
 def test_gemm_bf16(impl, M, N, K):
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N + K)
     A = (torch.randn(M, K, generator=g) * 0.5).to(DEV, torch.bfloat16)

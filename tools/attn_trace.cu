@@ -4,6 +4,8 @@
 //        wav2vec-s_b200/csrc/layout.cu && ./attn_trace
 #include <vector>
 #include <cstdio>
+#include <cstring>
+#include <cmath>
 #include "../wav2vec-s_b200/csrc/k_attn_tc.cu"
 
 int main() {
@@ -37,6 +39,11 @@ int main() {
   cudaDeviceSynchronize();
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   printf("attn_tc: %.1f us per launch (B=%d)  err=%s\n", ms * 100, B, cudaGetErrorString(cudaGetLastError()));
+  { std::vector<uint16_t> o((size_t)B * M * D);
+    cudaMemcpy(o.data(), ctx, o.size() * 2, cudaMemcpyDeviceToHost);
+    double sum = 0, asum = 0; unsigned long long x = 0;
+    for (size_t i = 0; i < o.size(); ++i) { uint32_t u = (uint32_t)o[i] << 16; float f; memcpy(&f, &u, 4); sum += f; asum += fabs(f); x = x * 1315423911ull + o[i]; }
+    printf("ctx checksum: sum %.6f abs %.6f hash %016llx\n", sum, asum, x); }
 #ifdef W2VS_ATTN_TRACE
   static long long tr[2][64][16];
   cudaMemcpyFromSymbol(tr, g_attn_trace, sizeof(tr));

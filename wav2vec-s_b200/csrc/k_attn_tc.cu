@@ -57,10 +57,20 @@ constexpr int QT = 128, KT = 64, HD = 64;
 constexpr int Q_BYTES = QT * HD * 2;         // 16 KB
 constexpr int KV_BYTES = KT * HD * 2;        // 8 KB: K or V tile
 constexpr int P_BYTES = QT * KT * 2;         // 16 KB: bf16 P (A operand of PV), reused as the output staging tile
-constexpr int NS = 2;                        // K ring and V ring depth
+// Ring depth and CTAs per SM as macros for the A/B harness (tools/build_attn_variants.sh).  Measured per layer call
+// at cfg3 (round 2, same box): 2 slots x 3 CTAs 466 us; 1 slot x 3 CTAs 500 us; 1 slot x 4 CTAs (96 registers,
+// 572 bytes of spills in the tile loop) 1066 us.  F2FP packing is not on the MUFU pipe (tools/mufu_bw.cu: ex2 alone
+// 16 / clk / SM, with one bf16x2 pack per two ex2 still 16), and cutting P to bf16 with PRMT instead changes nothing.
+#ifndef W2VS_ATTN_NS
+#define W2VS_ATTN_NS 2
+#endif
+#ifndef W2VS_ATTN_CTAS
+#define W2VS_ATTN_CTAS 3
+#endif
+constexpr int NS = W2VS_ATTN_NS;             // K ring and V ring depth
 constexpr int N_SOFTMAX_WARPS = 4;
 constexpr int N_THREADS = 160;               // warps 0-3 softmax, warp 4 MMA
-constexpr int CTAS_PER_SM = 3;
+constexpr int CTAS_PER_SM = W2VS_ATTN_CTAS;
 constexpr int SMEM_BYTES = Q_BYTES + 2 * NS * KV_BYTES + P_BYTES + 256 /*barriers*/ + 256 /*item ring*/ + 1024 /*align*/;
 constexpr uint32_t TMEM_COLS = 128, S_COL = 0, O_COL = 64;
 // barrier waits per role: parked (suspend-time hint) or spinning, see tc_common.cuh

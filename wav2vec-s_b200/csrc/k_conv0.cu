@@ -23,10 +23,16 @@ namespace w2vs {
 enum { C0_PLAIN = 0, C0_LN = 1, C0_GN_STATS = 2, C0_GN_APPLY = 3 };
 
 constexpr int kFramesPerCta = 256;
-constexpr int FPI = 4;   // frames per warp iteration
+#ifndef W2VS_CONV0_FPI
+#define W2VS_CONV0_FPI 4
+#endif
+#ifndef W2VS_CONV0_CTAS
+#define W2VS_CONV0_CTAS 2
+#endif
+constexpr int FPI = W2VS_CONV0_FPI;   // frames per warp iteration
 
 template <typename TIn, typename TOut, int NI, int KW, int MODE>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, W2VS_CONV0_CTAS)
 conv0_kernel(const TIn* __restrict__ wav, int64_t wav_ld, const float* __restrict__ w,
              const float* __restrict__ bias, const float* __restrict__ gamma,
              const float* __restrict__ beta, TOut* __restrict__ out, int rows_per_utt, int T0,

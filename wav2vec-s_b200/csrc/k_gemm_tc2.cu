@@ -85,12 +85,19 @@ template <int BN, typename TC, int SLOTS = 2, int EW = 8> struct Cfg2 {
 
 using namespace tc;
 
-template <int BN, typename TC, int SLOTS, int EW>
+// RED (split-K for the in-place fp32 products of a few hundred rows, the incremental steps of a batch of streams):
+// the tile index also walks `ksplit` K ranges, every range's partial tile goes into C through the TMA reduction path
+// (fp32 adds at L2, so C += sum of the partials in whatever order they arrive; the bias rides on range 0).  A
+// 384 x 1024 product has 32 cluster tiles for 74 clusters, each streaming its whole K through one SM pair; split
+// four ways every SM pair has a tile and a quarter of the K loop.
+template <int BN, typename TC, int SLOTS, int EW, bool RED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * EW + 64, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int has_residual,
-                int M, int N, int K, int a_row_len, int gelu, int n_batch, int a_batch_rows, int w_batch_rows) {
+                int M, int N, int K, int a_row_len, int gelu, int n_batch, int a_batch_rows, int w_batch_rows,
+                int ksplit) {
   using C2 = Cfg2<BN, TC, SLOTS, EW>;
+  constexpr bool kTmaReduce = w2vs::kTmaReduce || RED;
   constexpr int S = C2::kStages;
   constexpr bool kF32 = sizeof(TC) == 4;
   constexpr int N_EPI_WARPS = EW, PRODUCER_WARP = EW, MMA_WARP = EW + 1, CPW = C2::kColsPerWarp;
@@ -115,8 +122,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
   const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + 2 * BM - 1) / (2 * BM);
   const int tiles_pb = tiles_m * tiles_n;          // tiles per product; n_batch > 1: the tile index also walks the batch
-  const int n_tiles = tiles_pb * n_batch;
+  const int n_tiles = tiles_pb * (RED ? ksplit : n_batch);   // RED: the slow index is the K range, not the product
   const int num_kb = (K + BK - 1) / BK;
+  const int kb_per = RED ? (num_kb + ksplit - 1) / ksplit : num_kb;   // K blocks per range
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -148,10 +156,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t phase = 0;
       bool ok = true;
       for (int tile = cluster_id; tile < n_tiles && ok; tile += n_clusters) {
-        const int bt = tile / tiles_pb, rem = tile - bt * tiles_pb;
+        const int hi = tile / tiles_pb, rem = tile - hi * tiles_pb;
+        const int bt = RED ? 0 : hi;
         const int m0 = (rem / tiles_n) * (2 * BM) + (int)rank * BM + bt * a_batch_rows;
         const int n0 = (rem % tiles_n) * BN + (int)rank * (BN / 2) + bt * w_batch_rows;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = RED ? hi * kb_per : 0, kb1 = RED ? min(kb0 + kb_per, num_kb) : num_kb;
+        for (int kb = kb0; kb < kb1; ++kb) {
           if (!(ok = mbar_wait(bar_empty + 8 * stage, phase ^ 1))) break;
           if (leader) mbar_expect_tx(bar_full + 8 * stage, 2 * C2::kStageBytes);
           const int kk = kb * BK;
@@ -174,14 +184,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (!(ok = mbar_wait_cluster(bar_tempty + 8 * as, aphase ^ 1))) break;   // peer CTA's epilogue arrives here
         tc_fence_after();
         const uint32_t tmem_c = tmem_base + (uint32_t)(as * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = RED ? (tile / tiles_pb) * kb_per : 0, kb1 = RED ? min(kb0 + kb_per, num_kb) : num_kb;
+        for (int kb = kb0; kb < kb1; ++kb) {
           if (!(ok = mbar_wait(bar_full + 8 * stage, phase))) break;
           tc_fence_after();
           const uint32_t a_addr = sA + stage * A_STAGE_BYTES, b_addr = sB + stage * C2::kBStageBytes;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             umma_bf16_2sm(tmem_c, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                          (kb > 0 || k > 0) ? 1u : 0u);
+                          (kb > kb0 || k > 0) ? 1u : 0u);
           tc_commit_2sm(bar_empty + 8 * stage);   // both CTAs may refill this stage once the MMAs retire
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
@@ -203,7 +214,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t aphase = 0;
     bool ok = true;
     for (int tile = cluster_id; tile < n_tiles && ok; tile += n_clusters) {
-      const int bt = tile / tiles_pb, rem = tile - bt * tiles_pb;
+      const int hi = tile / tiles_pb, rem = tile - hi * tiles_pb;
+      const int bt = RED ? 0 : hi;
       const int m0 = (rem / tiles_n) * (2 * BM) + (int)rank * BM;
       const int n0 = (rem % tiles_n) * BN;
       const int row0 = m0 + quarter * 32;
@@ -212,7 +224,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       float* bs = bias_s + e * CPW;
       __syncwarp();
 #pragma unroll
-      for (int i = lane; i < CPW; i += 32) bs[i] = (bias != nullptr && colw + i < N) ? bias[bt * N + colw + i] : 0.f;
+      for (int i = lane; i < CPW; i += 32) bs[i] = (bias != nullptr && colw + i < N && !(RED && hi > 0)) ? bias[bt * N + colw + i] : 0.f;
       // residual chunk 0 prefetch (overlaps the wait for the accumulator)
       if (SLOTS == 2 && !kTmaReduce && has_residual && elect_one()) {
         bulk_wait_read<0>();                           // earlier stores from slot 0/1 have been read out
@@ -316,8 +328,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-template <int BN, typename TC, int SLOTS = 2, int EW = 8>
-w2vs_status_t launch_bn(const GemmArgs& g, cudaStream_t st) {
+template <int BN, typename TC, int SLOTS = 2, int EW = 8, bool RED = false>
+w2vs_status_t launch_bn(const GemmArgs& g, cudaStream_t st, int ksplit = 1) {
   using C2 = Cfg2<BN, TC, SLOTS, EW>;
   alignas(64) CUtensorMap tmA, tmB, tmC;
   const int64_t a_row_len = g.lda;
@@ -346,23 +358,24 @@ w2vs_status_t launch_bn(const GemmArgs& g, cudaStream_t st) {
   static PerDeviceOnce attr_once;   // the attribute belongs to the current device's copy of the kernel
   bool& attr_done = attr_once.here();
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, TC, SLOTS, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, TC, SLOTS, EW, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C2::kSmemBytes);
     if (e != cudaSuccess) { set_error("gemm_tc2 smem attribute: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
     attr_done = true;
   }
-  const int tiles = (int)(ceil_div64(g.M, 2 * BM) * ceil_div64(g.N, BN)) * n_batch;
+  const int tiles = (int)(ceil_div64(g.M, 2 * BM) * ceil_div64(g.N, BN)) * (RED ? ksplit : n_batch);
   const int max_clusters = num_sms() / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   // plain stream launch: as a programmatic dependent (PDL) this kernel's 200 KB CTAs cannot become resident early
   // anyway, and 16-stream incremental steps measured 7 % slower with it
-  gemm_tc2_kernel<BN, TC, SLOTS, EW><<<2 * clusters, 32 * EW + 64, C2::kSmemBytes, st>>>(
+  gemm_tc2_kernel<BN, TC, SLOTS, EW, RED><<<2 * clusters, 32 * EW + 64, C2::kSmemBytes, st>>>(
       tmA, tmB, tmC, g.bias, g.residual != nullptr ? 1 : 0, g.M, g.N, g.K, (int)a_row_len,
-      (g.flags & W2VS_EPI_GELU) ? 1 : 0, n_batch, (int)g.a_batch_rows, (int)g.w_batch_rows);
+      (g.flags & W2VS_EPI_GELU) ? 1 : 0, n_batch, (int)g.a_batch_rows, (int)g.w_batch_rows, ksplit);
   if (g_prof_on) {
     char name[96];
     char bat[24] = "";
     if (n_batch > 1) snprintf(bat, sizeof(bat), ",batch=%d", n_batch);
+    if (RED) snprintf(bat, sizeof(bat), ",ksplit=%d", ksplit);
     snprintf(name, sizeof(name), "gemm_tc2_kernel[M=%d,N=%d,K=%d,lda=%lld,%s%s%s%s]", g.M, g.N, g.K, (long long)g.lda,
              sizeof(TC) == 4 ? "f32" : "bf16", g.residual ? ",res" : "", (g.flags & W2VS_EPI_GELU) ? ",gelu" : "", bat);
     W2VS_CHECK_LAUNCH(name);
@@ -396,9 +409,27 @@ w2vs_status_t launch_typed(const GemmArgs& g, cudaStream_t st) {
   if (W2VS_GEMM_BF16_EPI_WARPS == 16 && sizeof(TC) == 2 && (g.flags & W2VS_EPI_GELU) && g.N % 256 == 0 &&
       m_tiles * (g.N / 256) >= clusters)
     return launch_bn<256, TC, 1, 16>(g, st);
+#ifndef W2VS_GEMM_WIDE_FILL_NUM
+#define W2VS_GEMM_WIDE_FILL_NUM 3      // quarters of the clusters a wider tile must still fill (4 = the round-1 rule)
+#endif
+#ifndef W2VS_GEMM_SPLITK
+#define W2VS_GEMM_SPLITK 1
+#endif
+  // in-place fp32 product with fewer 64-wide tiles than half the SM pairs: split K (see RED above)
+  if (W2VS_GEMM_SPLITK && sizeof(TC) == 4 && g.residual != nullptr && g.batch <= 1 && g.N % 64 == 0 && g.K % BK == 0 &&
+      g.K <= g.lda && m_tiles * (g.N / 64) * 2 <= clusters) {
+    const int64_t t64 = m_tiles * (g.N / 64);
+    int ks = (int)(clusters / t64);                       // ranges that still give every cluster at most one tile
+    const int num_kb = g.K / BK;
+    while (ks > 1 && num_kb / ks < 4) --ks;               // at least four K blocks per range
+    if (ks > 1) return launch_bn<64, TC, 2, 8, true>(g, st, ks);
+  }
   if (g.N <= 64) return launch_bn<64, TC>(g, st);   // one group of the positional conv (N = D / groups = 48 or 64)
-  if (g.N % 256 == 0 && (m_tiles * (g.N / 256) >= clusters || g.N % 128 != 0)) return launch_bn<256, TC>(g, st);
-  if (g.N % 128 == 0 && (m_tiles * (g.N / 128) >= clusters || g.N % 64 != 0)) return launch_bn<128, TC>(g, st);
+  // (three quarters of the clusters busy for one wave beat 1.7 waves of tiles half as wide: fc1 of 16 streams,
+  //  384 x 4096, has 64 tiles of 128 columns for 74 clusters)
+  const int64_t enough = (int64_t)clusters * W2VS_GEMM_WIDE_FILL_NUM / 4;
+  if (g.N % 256 == 0 && (m_tiles * (g.N / 256) >= enough || g.N % 128 != 0)) return launch_bn<256, TC>(g, st);
+  if (g.N % 128 == 0 && (m_tiles * (g.N / 128) >= enough || g.N % 64 != 0)) return launch_bn<128, TC>(g, st);
   if (g.N % 64 == 0) return launch_bn<64, TC>(g, st);
   return launch_bn<256, TC>(g, st);
 }
