@@ -333,7 +333,10 @@ w2vs_status_t launch_attention_mma(const AttnArgs& a, cudaStream_t st) {
     int splits = 1;
     if (a.step_partials != nullptr && a.step_counters != nullptr) {
       // ... as long as the streams and heads alone do not fill the GPU (measured: 16 streams are slower split)
-      const int fill = 296 / (a.B * a.heads * nt);
+#ifndef W2VS_ATTN_STEP_FILL
+#define W2VS_ATTN_STEP_FILL 296
+#endif
+      const int fill = W2VS_ATTN_STEP_FILL / (a.B * a.heads * nt);
       splits = n_kt / 2 < fill ? n_kt / 2 : fill;
       splits = splits < 1 ? 1 : (splits > kAttnStepMaxSplits ? kAttnStepMaxSplits : splits);
     }
