@@ -32,7 +32,7 @@ def _gemm_ref(A, W, bias, res, gelu):
                                    # a few hundred rows (a batch of incremental streams): the in-place fp32 products
                                    # run split over K with L2 reductions (uneven last range: 17 K blocks in two ranges)
                                    (384, 1024, 4096), (384, 1024, 1024), (96, 1024, 4096), (200, 512, 2048),
-                                   (384, 1024, 1088)])
+                                   (384, 1024, 1088), (100, 256, 4672)])
 def test_gemm_bf16(impl, M, N, K):
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N + K)
     A = (torch.randn(M, K, generator=g) * 0.5).to(DEV, torch.bfloat16)

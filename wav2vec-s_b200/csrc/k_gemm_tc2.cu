@@ -143,6 +143,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync();          // the peer's barriers are initialised and its TMEM is allocated
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // launched as a programmatic dependent (GemmArgs::pdl) everything above overlaps the predecessor; a no-op otherwise.
+  // (No griddepcontrol.launch_dependents here: releasing this kernel's successors early -- the step attention / the
+  //  LayerNorm of an incremental step -- measured 2.36 -> 2.8 ms per 16-stream step.)
+  // The weights do not depend on the predecessor: the producer requests the W half of the first ring stages before
+  // it waits.
+  if (warp != PRODUCER_WARP) pdl_wait();
 
   if (warp == PRODUCER_WARP) {
     // ===================== TMA producer (both CTAs) =====================
@@ -155,6 +161,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
+      int pre = 0;     // leading ring stages (first uses, first tile) that are armed and whose W half is in flight
+      if (cluster_id < n_tiles) {
+        const int hi = cluster_id / tiles_pb, rem = cluster_id - hi * tiles_pb;
+        const int n0 = (rem % tiles_n) * BN + (int)rank * (BN / 2) + (RED ? 0 : hi) * w_batch_rows;
+        const int kb0 = RED ? hi * kb_per : 0, kb1 = RED ? min(kb0 + kb_per, num_kb) : num_kb;
+        pre = min(S, kb1 - kb0);
+        for (int i = 0; i < pre; ++i) {
+          if (leader) mbar_expect_tx(bar_full + 8 * i, 2 * C2::kStageBytes);
+          tma_load_2d_2sm(sB + i * C2::kBStageBytes, &tmB, full_leader + 8 * i, (kb0 + i) * BK, n0);
+        }
+      }
+      pdl_wait();
       for (int tile = cluster_id; tile < n_tiles && ok; tile += n_clusters) {
         const int hi = tile / tiles_pb, rem = tile - hi * tiles_pb;
         const int bt = RED ? 0 : hi;
@@ -162,11 +180,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int n0 = (rem % tiles_n) * BN + (int)rank * (BN / 2) + bt * w_batch_rows;
         const int kb0 = RED ? hi * kb_per : 0, kb1 = RED ? min(kb0 + kb_per, num_kb) : num_kb;
         for (int kb = kb0; kb < kb1; ++kb) {
-          if (!(ok = mbar_wait(bar_empty + 8 * stage, phase ^ 1))) break;
-          if (leader) mbar_expect_tx(bar_full + 8 * stage, 2 * C2::kStageBytes);
           const int kk = kb * BK;
+          if (pre > 0) {
+            --pre;
+          } else {
+            if (!(ok = mbar_wait(bar_empty + 8 * stage, phase ^ 1))) break;
+            if (leader) mbar_expect_tx(bar_full + 8 * stage, 2 * C2::kStageBytes);
+            tma_load_2d_2sm(sB + stage * C2::kBStageBytes, &tmB, full_leader + 8 * stage, kk, n0);
+          }
           tma_load_2d_2sm(sA + stage * A_STAGE_BYTES, &tmA, full_leader + 8 * stage, kk % a_row_len, m0 + kk / a_row_len);
-          tma_load_2d_2sm(sB + stage * C2::kBStageBytes, &tmB, full_leader + 8 * stage, kk, n0);
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
       }
@@ -368,6 +390,11 @@ w2vs_status_t launch_bn(const GemmArgs& g, cudaStream_t st, int ksplit = 1) {
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   // plain stream launch: as a programmatic dependent (PDL) this kernel's 200 KB CTAs cannot become resident early
   // anyway, and 16-stream incremental steps measured 7 % slower with it
+  if (g.pdl && g_pdl_on)
+    launch_pdl(gemm_tc2_kernel<BN, TC, SLOTS, EW, RED>, dim3(2 * clusters), dim3(32 * EW + 64), (size_t)C2::kSmemBytes, st,
+               tmA, tmB, tmC, g.bias, g.residual != nullptr ? 1 : 0, g.M, g.N, g.K, (int)a_row_len,
+               (g.flags & W2VS_EPI_GELU) ? 1 : 0, n_batch, (int)g.a_batch_rows, (int)g.w_batch_rows, ksplit);
+  else
   gemm_tc2_kernel<BN, TC, SLOTS, EW, RED><<<2 * clusters, 32 * EW + 64, C2::kSmemBytes, st>>>(
       tmA, tmB, tmC, g.bias, g.residual != nullptr ? 1 : 0, g.M, g.N, g.K, (int)a_row_len,
       (g.flags & W2VS_EPI_GELU) ? 1 : 0, n_batch, (int)g.a_batch_rows, (int)g.w_batch_rows, ksplit);
@@ -421,7 +448,7 @@ w2vs_status_t launch_typed(const GemmArgs& g, cudaStream_t st) {
     const int64_t t64 = m_tiles * (g.N / 64);
     int ks = (int)(clusters / t64);                       // ranges that still give every cluster at most one tile
     const int num_kb = g.K / BK;
-    while (ks > 1 && num_kb / ks < 4) --ks;               // at least four K blocks per range
+    while (ks > 1 && (num_kb / ks < 4 || (ks - 1) * ((num_kb + ks - 1) / ks) >= num_kb)) --ks;   // at least four K blocks per range, none empty
     if (ks > 1) return launch_bn<64, TC, 2, 8, true>(g, st, ks);
   }
   if (g.N <= 64) return launch_bn<64, TC>(g, st);   // one group of the positional conv (N = D / groups = 48 or 64)

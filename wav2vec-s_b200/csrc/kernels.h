@@ -74,6 +74,9 @@ struct GemmArgs {
   // a_batch_rows rows (of lda) after A of b - 1, W w_batch_rows rows after, C c_batch_stride elements after, bias N
   // floats after; no residual.  The groups of the positional conv.
   int batch; int64_t a_batch_rows, w_batch_rows, c_batch_stride;
+  // pdl: the predecessor in the stream is a small row kernel (a LayerNorm of an incremental step): launch the tcgen05
+  // kernel as its programmatic dependent, so that barrier set-up, TMEM allocation and the cluster handshake overlap it
+  int pdl;
 };
 w2vs_status_t launch_gemm_simt(const GemmArgs& g, cudaStream_t st);
 w2vs_status_t launch_gemm_tc2(const GemmArgs& g, cudaStream_t st);   // CTA-pair tcgen05, TMA-store epilogue

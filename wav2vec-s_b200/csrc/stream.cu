@@ -194,8 +194,13 @@ w2vs_status_t block_step(const w2vs_config* cfg, const WeightLayout& wl, const S
     la.rows = tokens; la.N = D; la.gelu = 0;
     return launch_layernorm(la, st);
   };
-  auto gemm = [&](const void* A, int K, size_t w, size_t b, const float* res, void* C, int N, int cdt, int flags) {
+#ifndef W2VS_STREAM_GEMM_PDL
+#define W2VS_STREAM_GEMM_PDL 2      // 0 off, 1 only behind a LayerNorm, 2 every product of a layer
+#endif
+  auto gemm = [&](const void* A, int K, size_t w, size_t b, const float* res, void* C, int N, int cdt, int flags,
+                  bool after_ln = false) {
     GemmArgs ga{};
+    ga.pdl = (W2VS_STREAM_GEMM_PDL == 2 || (W2VS_STREAM_GEMM_PDL == 1 && after_ln)) ? 1 : 0;
     ga.A = A; ga.lda = K; ga.a_rows = tokens; ga.W = at<void>(W, w); ga.bias = at<float>(W, b);
     ga.residual = res; ga.C = C; ga.ldc = N; ga.M = tokens; ga.N = N; ga.K = K;
     ga.dtype_ab = adt; ga.dtype_c = cdt; ga.flags = flags;
@@ -205,7 +210,7 @@ w2vs_status_t block_step(const w2vs_config* cfg, const WeightLayout& wl, const S
     const LayerW lw = layer_at(wl, l);
     void* cache = at<void>(d_state, L.kv + (size_t)l * L.kv_layer_bytes);
     if (pre_ln) W2VS_TRY(layer_norm(lw.ln1_w, lw.ln1_b, false));
-    W2VS_TRY(gemm(Xa, D, lw.wqkv, lw.bqkv, nullptr, qkv, 3 * D, adt, 0));
+    W2VS_TRY(gemm(Xa, D, lw.wqkv, lw.bqkv, nullptr, qkv, 3 * D, adt, 0, pre_ln));
     // (bf16: the step attention kernel appends this step's K / V to the cache itself)
     if (adt != W2VS_BF16) W2VS_TRY(launch_kv_append(qkv, cache, L.kv_rows, f0, ntok, D, (int)as, B, st));
     {
@@ -218,7 +223,7 @@ w2vs_status_t block_step(const w2vs_config* cfg, const WeightLayout& wl, const S
     W2VS_TRY(gemm(ctx, D, lw.wo, lw.bo, X, X, D, W2VS_F32, 0));
     if (pre_ln) W2VS_TRY(layer_norm(lw.ln2_w, lw.ln2_b, false));
     else W2VS_TRY(layer_norm(lw.ln1_w, lw.ln1_b, true));
-    W2VS_TRY(gemm(Xa, D, lw.w1, lw.b1, nullptr, h, F, adt, W2VS_EPI_GELU));
+    W2VS_TRY(gemm(Xa, D, lw.w1, lw.b1, nullptr, h, F, adt, W2VS_EPI_GELU, true));
     W2VS_TRY(gemm(h, F, lw.w2, lw.b2, X, X, D, W2VS_F32, 0));
     if (!pre_ln) W2VS_TRY(layer_norm(lw.ln2_w, lw.ln2_b, true));
   }
