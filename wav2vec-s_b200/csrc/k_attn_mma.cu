@@ -320,6 +320,268 @@ attn_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ keypad
     }
   }
 }
+// Step mode with at most 32 query tokens per stream (a decision step has main + rc = 24): the four warps share the
+// QUERY rows and split the KEYS of every tile instead (16 each), so a tile costs a warp 32 MMAs instead of 64 (and none
+// of them on the 40 padding rows of a 64-row query tile) -- the kernel is a serial walk over up to 24 key tiles per
+// (stream, head) at one or two CTAs per SM, so the length of that per-tile chain is its run time.  Every warp keeps its
+// own running (max, sum, O) over its quarter of the keys; the four states are merged through shared memory at the end,
+// then either written out or handed to the cross-CTA merge of the split-key scheme (same partial-state layout as
+// attn_mma_kernel).
+constexpr int SQ = 32;                 // query rows per CTA
+constexpr int OP_LD = 68;              // floats per row of a warp's partial O in shared memory
+__global__ void __launch_bounds__(128)
+attn_step32_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T2, int M, int D, float scale_log2,
+                   const bf16* __restrict__ kv_cache, int64_t kv_rows, int n_splits, float* __restrict__ partials,
+                   unsigned* __restrict__ counters) {
+  __shared__ __align__(128) uint8_t sm_raw[(1 + 4) * TILE_ELEMS * 2];      // Q tile | K,V x 2 stages; later 4 x O partial
+  __shared__ float s_ml[4][SQ][2];
+  __shared__ int s_last;
+  bf16* Qs = reinterpret_cast<bf16*>(sm_raw);
+  bf16* KVs = Qs + TILE_ELEMS;                                             // [buf][K | V][64 x 64]
+  float* Op = reinterpret_cast<float*>(sm_raw);                            // [4 warps][SQ][OP_LD]
+  static_assert(4 * SQ * OP_LD * 4 <= (int)sizeof(sm_raw), "partial O does not fit");
+  pdl_prologue();
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int h = blockIdx.y, b = blockIdx.z, split = blockIdx.x;
+  const int64_t rs = 3 * (int64_t)D, krs = 2 * (int64_t)D;
+  const bf16* qbase = qkv + (size_t)b * M * rs + (size_t)h * HD;
+  const bf16* kbase = kv_cache + (size_t)b * kv_rows * krs + (size_t)h * HD;
+  const bf16* vbase = kbase + D;
+  const int f0 = T2 - M;               // keys at or past f0 are this step's own tokens (read from qkv)
+  if (blockIdx.x == 0) {               // append this step's K / V to the cache for later steps
+    bf16* cache = const_cast<bf16*>(kv_cache) + (size_t)b * kv_rows * krs + (size_t)h * HD;
+    for (int i = tid; i < M * 16; i += 128) {
+      const int row = i >> 4, part = (i >> 3) & 1, chunk = i & 7;
+      const uint4 v = *reinterpret_cast<const uint4*>(qbase + (size_t)row * rs + (1 + part) * D + chunk * 8);
+      *reinterpret_cast<uint4*>(cache + (size_t)(f0 + row) * krs + part * D + chunk * 8) = v;
+    }
+  }
+  const int n_kt = (T2 + KT - 1) / KT;
+  int it_begin = 0, it_end = n_kt;
+  if (n_splits > 1) {
+    const int per = (n_kt + n_splits - 1) / n_splits;
+    it_begin = min(split * per, n_kt);
+    it_end = min(it_begin + per, n_kt);
+  }
+  auto issue_tile = [&](int it, int buf) {
+    const int k0 = it * KT, cnt = min(KT, T2 - k0);
+    load_tile_async(KVs + (buf * 2 + 0) * TILE_ELEMS, kbase, krs, k0, cnt, tid, qbase + D, rs, f0);
+    load_tile_async(KVs + (buf * 2 + 1) * TILE_ELEMS, vbase, krs, k0, cnt, tid, qbase + 2 * D, rs, f0);
+  };
+  load_tile_async(Qs, qbase, rs, 0, M, tid);
+  if (it_begin < it_end) issue_tile(it_begin, 0);
+  cp_async_commit();
+
+  uint32_t qf[2][4][4];
+  float o[2][8][4];
+#pragma unroll
+  for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o[rb][j][0] = o[rb][j][1] = o[rb][j][2] = o[rb][j][3] = 0.f; }
+  float m[4], l[4];                    // rows g, g + 8, 16 + g, 24 + g
+#pragma unroll
+  for (int r = 0; r < 4; ++r) { m[r] = -INFINITY; l[r] = 0.f; }
+
+  for (int it = it_begin; it < it_end; ++it) {
+    const int buf = (it - it_begin) & 1;
+    if (it + 1 < it_end) {
+      issue_tile(it + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (it == it_begin) {
+#pragma unroll
+      for (int rb = 0; rb < 2; ++rb) {
+        const int row = rb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) ldsm_x4(smem_addr(Qs + sw(row, kk * 2 + (lane >> 4))), qf[rb][kk]);
+      }
+    }
+    const int cnt = min(KT, T2 - it * KT);
+    if (warp * 16 < cnt) {             // this warp's 16 keys of the tile: 16 * warp ..
+      const bf16* Kt = KVs + (buf * 2 + 0) * TILE_ELEMS;
+      const bf16* Vt = KVs + (buf * 2 + 1) * TILE_ELEMS;
+      float sc[2][2][4];
+#pragma unroll
+      for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) { sc[rb][nb][0] = sc[rb][nb][1] = sc[rb][nb][2] = sc[rb][nb][3] = 0.f; }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t kf[4];
+        const int mi = lane >> 3;
+        const int row = warp * 16 + (lane & 7) + (mi >> 1) * 8;
+        ldsm_x4(smem_addr(Kt + sw(row, kk * 2 + (mi & 1))), kf);
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb) {
+          mma_bf16(sc[rb][0], qf[rb][kk], kf[0], kf[1]);
+          mma_bf16(sc[rb][1], qf[rb][kk], kf[2], kf[3]);
+        }
+      }
+      // ---- keys past the end of the cache are masked; online softmax per row over this warp's keys
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const bool vis = warp * 16 + nb * 8 + 2 * t4 + (e & 1) < cnt;
+            sc[rb][nb][e] = vis ? sc[rb][nb][e] : -INFINITY;
+            mx[rb * 2 + (e >> 1)] = fmaxf(mx[rb * 2 + (e >> 1)], sc[rb][nb][e]);
+          }
+      float al[4], ms[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        const float mn = fmaxf(m[r], mx[r]);
+        ms[r] = mn == -INFINITY ? 0.f : mn * scale_log2;
+        al[r] = exp2f(m[r] * scale_log2 - ms[r]);
+        m[r] = mn;
+      }
+      uint32_t af[2][4];
+#pragma unroll
+      for (int rb = 0; rb < 2; ++rb) {
+        float p[2][4], sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+          p[nb][0] = exp2f(fmaf(sc[rb][nb][0], scale_log2, -ms[rb * 2]));
+          p[nb][1] = exp2f(fmaf(sc[rb][nb][1], scale_log2, -ms[rb * 2]));
+          p[nb][2] = exp2f(fmaf(sc[rb][nb][2], scale_log2, -ms[rb * 2 + 1]));
+          p[nb][3] = exp2f(fmaf(sc[rb][nb][3], scale_log2, -ms[rb * 2 + 1]));
+          sum0 += p[nb][0] + p[nb][1];
+          sum1 += p[nb][2] + p[nb][3];
+        }
+        l[rb * 2] = l[rb * 2] * al[rb * 2] + sum0;
+        l[rb * 2 + 1] = l[rb * 2 + 1] * al[rb * 2 + 1] + sum1;
+        af[rb][0] = pack_bf16x2(p[0][0], p[0][1]); af[rb][1] = pack_bf16x2(p[0][2], p[0][3]);
+        af[rb][2] = pack_bf16x2(p[1][0], p[1][1]); af[rb][3] = pack_bf16x2(p[1][2], p[1][3]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          o[rb][j][0] *= al[rb * 2]; o[rb][j][1] *= al[rb * 2];
+          o[rb][j][2] *= al[rb * 2 + 1]; o[rb][j][3] *= al[rb * 2 + 1];
+        }
+      }
+      // ---- O += P V over this warp's 16 keys (one k16 step)
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        uint32_t vf[4];
+        const int mi = lane >> 3;
+        const int row = warp * 16 + (lane & 7) + (mi & 1) * 8;
+        ldsm_x4_trans(smem_addr(Vt + sw(row, jp * 2 + (mi >> 1))), vf);
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb) {
+          mma_bf16(o[rb][2 * jp], af[rb], vf[0], vf[1]);
+          mma_bf16(o[rb][2 * jp + 1], af[rb], vf[2], vf[3]);
+        }
+      }
+    }
+    __syncthreads();  // tile `buf` fully consumed before the next iteration's prefetch overwrites it
+  }
+  cp_async_wait<0>();
+  __syncthreads();    // (an empty key range never entered the loop) nobody reads Q / K / V any more: Op may overwrite them
+
+  // ---- the four warps' states -> shared memory -> one state per row
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+    l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+  }
+  float* myO = Op + (size_t)warp * SQ * OP_LD;
+#pragma unroll
+  for (int rb = 0; rb < 2; ++rb) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      *reinterpret_cast<float2*>(myO + (rb * 16 + g) * OP_LD + j * 8 + 2 * t4) = make_float2(o[rb][j][0], o[rb][j][1]);
+      *reinterpret_cast<float2*>(myO + (rb * 16 + g + 8) * OP_LD + j * 8 + 2 * t4) = make_float2(o[rb][j][2], o[rb][j][3]);
+    }
+    if (t4 == 0) {
+      s_ml[warp][rb * 16 + g][0] = m[rb * 2]; s_ml[warp][rb * 16 + g][1] = l[rb * 2];
+      s_ml[warp][rb * 16 + g + 8][0] = m[rb * 2 + 1]; s_ml[warp][rb * 16 + g + 8][1] = l[rb * 2 + 1];
+    }
+  }
+  __syncthreads();
+  const int row = tid >> 2, c0 = (tid & 3) * 16;      // 32 rows x 4 column quarters
+  float mxr = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) mxr = fmaxf(mxr, s_ml[w][row][0]);
+  float acc[16], lsum = 0.f;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const float mw = s_ml[w][row][0];
+    if (mw == -INFINITY) continue;
+    const float wgt = exp2f((mw - mxr) * scale_log2);
+    lsum = fmaf(s_ml[w][row][1], wgt, lsum);
+    const float* src = Op + ((size_t)w * SQ + row) * OP_LD + c0;
+#pragma unroll
+    for (int c = 0; c < 16; c += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(src + c);
+      acc[c] = fmaf(v.x, wgt, acc[c]); acc[c + 1] = fmaf(v.y, wgt, acc[c + 1]);
+      acc[c + 2] = fmaf(v.z, wgt, acc[c + 2]); acc[c + 3] = fmaf(v.w, wgt, acc[c + 3]);
+    }
+  }
+  if (n_splits == 1) {
+    if (row < M) {
+      const float inv = lsum > 0.f ? 1.0f / lsum : 0.f;
+      bf16* dst = ctx + ((size_t)b * M + row) * D + (size_t)h * HD + c0;
+#pragma unroll
+      for (int c = 0; c < 16; c += 8) {
+        uint4 v;
+        v.x = pack_bf16x2(acc[c] * inv, acc[c + 1] * inv); v.y = pack_bf16x2(acc[c + 2] * inv, acc[c + 3] * inv);
+        v.z = pack_bf16x2(acc[c + 4] * inv, acc[c + 5] * inv); v.w = pack_bf16x2(acc[c + 6] * inv, acc[c + 7] * inv);
+        *reinterpret_cast<uint4*>(dst + c) = v;
+      }
+    }
+    return;
+  }
+  // ---- split keys over CTAs: this CTA's state per row (layout of attn_mma_kernel: 64 rows x 66 floats per split);
+  //      the CTA of this (stream, head) that finishes last merges the splits in a fixed order
+  const size_t grp = (size_t)b * gridDim.y + h;
+  float* P = partials + (grp * n_splits + split) * (size_t)(QT * 66);
+#pragma unroll
+  for (int c = 0; c < 16; c += 2) *reinterpret_cast<float2*>(P + row * 66 + c0 + c) = make_float2(acc[c], acc[c + 1]);
+  if ((tid & 3) == 0) *reinterpret_cast<float2*>(P + row * 66 + 64) = make_float2(mxr, lsum);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(counters + grp, 1u) == (unsigned)n_splits - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* P0 = partials + grp * n_splits * (size_t)(QT * 66);
+  for (int idx = tid; idx < M * 8; idx += 128) {
+    const int r = idx >> 3, chunk = idx & 7;
+    float mx = -INFINITY;
+    for (int sp = 0; sp < n_splits; ++sp) mx = fmaxf(mx, __ldcg(P0 + (size_t)sp * QT * 66 + r * 66 + 64));
+    float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ls = 0.f;
+    for (int sp = 0; sp < n_splits; ++sp) {
+      const float* pr = P0 + (size_t)sp * QT * 66 + r * 66;
+      const float2 ml = __ldcg(reinterpret_cast<const float2*>(pr + 64));
+      if (ml.x == -INFINITY) continue;
+      const float w = exp2f((ml.x - mx) * scale_log2);
+      ls = fmaf(ml.y, w, ls);
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) {
+        const float2 ov = __ldcg(reinterpret_cast<const float2*>(pr + chunk * 8 + e));
+        a8[e] = fmaf(ov.x, w, a8[e]);
+        a8[e + 1] = fmaf(ov.y, w, a8[e + 1]);
+      }
+    }
+    const float inv = ls > 0.f ? 1.0f / ls : 0.f;
+    uint4 v;
+    v.x = pack_bf16x2(a8[0] * inv, a8[1] * inv); v.y = pack_bf16x2(a8[2] * inv, a8[3] * inv);
+    v.z = pack_bf16x2(a8[4] * inv, a8[5] * inv); v.w = pack_bf16x2(a8[6] * inv, a8[7] * inv);
+    *reinterpret_cast<uint4*>(ctx + ((size_t)b * M + r) * D + (size_t)h * HD + chunk * 8) = v;
+  }
+  if (tid == 0) counters[grp] = 0u;            // ready for the next launch (stream order)
+}
 }  // namespace
 
 w2vs_status_t launch_attention_mma(const AttnArgs& a, cudaStream_t st) {
@@ -339,6 +601,17 @@ w2vs_status_t launch_attention_mma(const AttnArgs& a, cudaStream_t st) {
       const int fill = W2VS_ATTN_STEP_FILL / (a.B * a.heads * nt);
       splits = n_kt / 2 < fill ? n_kt / 2 : fill;
       splits = splits < 1 ? 1 : (splits > kAttnStepMaxSplits ? kAttnStepMaxSplits : splits);
+    }
+#ifndef W2VS_ATTN_STEP32
+#define W2VS_ATTN_STEP32 1
+#endif
+    if (W2VS_ATTN_STEP32 && a.n_step_q <= SQ) {     // the usual decision step: keys split over the warps of a CTA
+      dim3 grid32((unsigned)splits, (unsigned)a.heads, (unsigned)a.B);
+      launch_pdl(attn_step32_kernel, grid32, dim3(128), 0, st, (const bf16*)a.qkv, (bf16*)a.ctx, a.n_step_keys,
+                 a.n_step_q, a.D, scale_log2, (const bf16*)a.kv_cache, a.kv_rows, splits, a.step_partials,
+                 a.step_counters);
+      W2VS_CHECK_LAUNCH("attn_step32_kernel");
+      return W2VS_OK;
     }
     dim3 grid((unsigned)(nt * splits), (unsigned)a.heads, (unsigned)a.B);
     launch_pdl(attn_mma_kernel, grid, dim3(128), 0, st, (const bf16*)a.qkv, (const uint8_t*)nullptr, (bf16*)a.ctx,
