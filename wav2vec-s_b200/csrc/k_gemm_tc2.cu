@@ -437,23 +437,30 @@ w2vs_status_t launch_typed(const GemmArgs& g, cudaStream_t st) {
       m_tiles * (g.N / 256) >= clusters)
     return launch_bn<256, TC, 1, 16>(g, st);
 #ifndef W2VS_GEMM_WIDE_FILL_NUM
-#define W2VS_GEMM_WIDE_FILL_NUM 3      // quarters of the clusters a wider tile must still fill (4 = the round-1 rule)
+#define W2VS_GEMM_WIDE_FILL_NUM 2      // quarters of the clusters a wider tile must still fill (4 = the round-1 rule; 16 streams: 4 / 3 / 2 -> 2.40 / 2.36 ms, then 1.90 / 1.81)
 #endif
 #ifndef W2VS_GEMM_SPLITK
 #define W2VS_GEMM_SPLITK 1
 #endif
-  // in-place fp32 product with fewer 64-wide tiles than half the SM pairs: split K (see RED above)
+  // in-place fp32 product with fewer 64-wide tiles than half the SM pairs: split K (see RED above).  Tile width 64 or
+  // 128, whichever leaves the shorter K range per cluster (the chain of dependent TMA stages is what these products
+  // cost): out_proj / fc2 of 16 streams run as 16 tiles of 128 columns x 4 ranges.
   if (W2VS_GEMM_SPLITK && sizeof(TC) == 4 && g.residual != nullptr && g.batch <= 1 && g.N % 64 == 0 && g.K % BK == 0 &&
       g.K <= g.lda && m_tiles * (g.N / 64) * 2 <= clusters) {
-    const int64_t t64 = m_tiles * (g.N / 64);
-    int ks = (int)(clusters / t64);                       // ranges that still give every cluster at most one tile
     const int num_kb = g.K / BK;
-    while (ks > 1 && (num_kb / ks < 4 || (ks - 1) * ((num_kb + ks - 1) / ks) >= num_kb)) --ks;   // at least four K blocks per range, none empty
-    if (ks > 1) return launch_bn<64, TC, 2, 8, true>(g, st, ks);
+    auto ranges = [&](int64_t tiles) {
+      int ks = (int)(clusters / tiles);                   // ranges that still give every cluster at most one tile
+      while (ks > 1 && (num_kb / ks < 4 || (ks - 1) * ((num_kb + ks - 1) / ks) >= num_kb)) --ks;   // >= 4 K blocks each, none empty
+      return ks;
+    };
+    const int ks64 = ranges(m_tiles * (g.N / 64));
+    const int ks128 = g.N % 128 == 0 ? ranges(m_tiles * (g.N / 128)) : 1;
+    if (ks128 > 1 && (num_kb + ks128 - 1) / ks128 < (num_kb + ks64 - 1) / ks64) return launch_bn<128, TC, 2, 8, true>(g, st, ks128);
+    if (ks64 > 1) return launch_bn<64, TC, 2, 8, true>(g, st, ks64);
   }
   if (g.N <= 64) return launch_bn<64, TC>(g, st);   // one group of the positional conv (N = D / groups = 48 or 64)
-  // (three quarters of the clusters busy for one wave beat 1.7 waves of tiles half as wide: fc1 of 16 streams,
-  //  384 x 4096, has 64 tiles of 128 columns for 74 clusters)
+  // (half of the clusters busy for one wave beat 1.3 - 1.7 waves of tiles half as wide: of 16 streams, fc1, 384 x 4096,
+  //  has 64 tiles of 128 columns for 74 clusters, QKV 48)
   const int64_t enough = (int64_t)clusters * W2VS_GEMM_WIDE_FILL_NUM / 4;
   if (g.N % 256 == 0 && (m_tiles * (g.N / 256) >= enough || g.N % 128 != 0)) return launch_bn<256, TC>(g, st);
   if (g.N % 128 == 0 && (m_tiles * (g.N / 128) >= enough || g.N % 64 != 0)) return launch_bn<128, TC>(g, st);
