@@ -211,6 +211,10 @@ typedef enum {
   W2VS_GEMM_SKINNY = 4         /* M <= 64: weight-streaming mma.sync kernel (default for incremental steps) */
 } w2vs_gemm_impl_t;
 #define W2VS_EPI_GELU 1
+#define W2VS_EPI_SPLITK 2   /* in-place fp32 product of a few hundred rows: the kernel may split K over several CTA pairs and
+                              add the partial tiles at L2 (sums in arrival order: reproducible to rounding, not bit for
+                              bit).  Set by the incremental steps of a batch of streams only; the full-utterance
+                              forward keeps fixed reduction orders. */
 /* C[M,N] = A[M,K] . W[N,K]^T + bias (+GELU) (+residual fp32, may alias C when C is fp32).
  * dtype_ab = dtype of A and W; dtype_c = dtype of C. lda/ldc in elements; lda may be < K*...
  * (overlapping rows: the strided-conv-as-GEMM view). */

@@ -44,6 +44,11 @@ def test_gemm_bf16(impl, M, N, K):
         ref = _gemm_ref(A, W, bias, res if use_res else None, gelu)
         tol = 1e-2 if odt == torch.bfloat16 else 2e-5 * max(1, K // 512) + 1e-5
         assert rel(y, ref) < tol, (impl, M, N, K, gelu, use_res)
+        if use_res:
+            # fixed reduction order unless the caller allows split-K (the incremental steps of a batch of streams do)
+            assert torch.equal(y, ops.gemm(A, W, bias, res, out_dtype=odt, impl=impl))
+            ys = ops.gemm(A, W, bias, res, out_dtype=odt, impl=impl, splitk=True)
+            assert rel(ys, ref) < tol, (impl, M, N, K, "split-K")
 
 
 @pytest.mark.parametrize("M", [1, 7, 16, 24, 33, 48, 64])

@@ -19,6 +19,7 @@ POS_SIN, POS_CONV = 0, 1
 LAYOUT_BTD, LAYOUT_TBD = 0, 1
 GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05_2CTA, GEMM_SKINNY = 0, 1, 3, 4
 EPI_GELU = 1
+EPI_SPLITK = 2    # in-place fp32 product of a few hundred rows may split K with L2 reductions (w2vs.h)
 
 
 class W2vsError(RuntimeError):

@@ -329,22 +329,28 @@ attn_mma_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ keypad
 // attn_mma_kernel).
 constexpr int SQ = 32;                 // query rows per CTA
 constexpr int OP_LD = 68;              // floats per row of a warp's partial O in shared memory
-__global__ void __launch_bounds__(128)
+// NG groups of four warps walk the key tiles in turns (group q takes tiles q, q + NG, ...), each with its own two-stage
+// K/V ring, so NG tiles are in flight per CTA; all 4 * NG warp states are merged at the end.  NG = 2 keeps the Q
+// fragments in shared memory (128 registers per thread for two CTAs of 256 threads per SM).
+template <int NG>
+__global__ void __launch_bounds__(128 * NG, NG == 1 ? 3 : 2)
 attn_step32_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T2, int M, int D, float scale_log2,
                    const bf16* __restrict__ kv_cache, int64_t kv_rows, int n_splits, float* __restrict__ partials,
                    unsigned* __restrict__ counters) {
-  __shared__ __align__(128) uint8_t sm_raw[(1 + 4) * TILE_ELEMS * 2];      // Q tile | K,V x 2 stages; later 4 x O partial
-  __shared__ float s_ml[4][SQ][2];
+  extern __shared__ __align__(128) uint8_t sm_raw[];                      // Q tile | [group][stage][K | V]; later the O partials
+  __shared__ float s_ml[4 * NG][SQ][2];
   __shared__ int s_last;
   bf16* Qs = reinterpret_cast<bf16*>(sm_raw);
-  bf16* KVs = Qs + TILE_ELEMS;                                             // [buf][K | V][64 x 64]
-  float* Op = reinterpret_cast<float*>(sm_raw);                            // [4 warps][SQ][OP_LD]
-  static_assert(4 * SQ * OP_LD * 4 <= (int)sizeof(sm_raw), "partial O does not fit");
+  float* Op = reinterpret_cast<float*>(sm_raw);                            // [4 * NG warps][SQ][OP_LD]
+  static_assert(4 * NG * SQ * OP_LD * 4 <= (1 + 4 * NG) * TILE_ELEMS * 2, "partial O does not fit");
   pdl_prologue();
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, wall = tid >> 5, lane = tid & 31;
+  const int grp = wall >> 2, warp = wall & 3, gtid = tid & 127;      // tile group, key quarter inside a tile
   const int g = lane >> 2, t4 = lane & 3;
   const int h = blockIdx.y, b = blockIdx.z, split = blockIdx.x;
+  bf16* KVs = Qs + TILE_ELEMS + (size_t)grp * 4 * TILE_ELEMS;          // this group's [stage][K | V][64 x 64]
+  auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); };
   const int64_t rs = 3 * (int64_t)D, krs = 2 * (int64_t)D;
   const bf16* qbase = qkv + (size_t)b * M * rs + (size_t)h * HD;
   const bf16* kbase = kv_cache + (size_t)b * kv_rows * krs + (size_t)h * HD;
@@ -352,7 +358,7 @@ attn_step32_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T2,
   const int f0 = T2 - M;               // keys at or past f0 are this step's own tokens (read from qkv)
   if (blockIdx.x == 0) {               // append this step's K / V to the cache for later steps
     bf16* cache = const_cast<bf16*>(kv_cache) + (size_t)b * kv_rows * krs + (size_t)h * HD;
-    for (int i = tid; i < M * 16; i += 128) {
+    for (int i = tid; i < M * 16; i += 128 * NG) {
       const int row = i >> 4, part = (i >> 3) & 1, chunk = i & 7;
       const uint4 v = *reinterpret_cast<const uint4*>(qbase + (size_t)row * rs + (1 + part) * D + chunk * 8);
       *reinterpret_cast<uint4*>(cache + (size_t)(f0 + row) * krs + part * D + chunk * 8) = v;
@@ -367,14 +373,19 @@ attn_step32_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T2,
   }
   auto issue_tile = [&](int it, int buf) {
     const int k0 = it * KT, cnt = min(KT, T2 - k0);
-    load_tile_async(KVs + (buf * 2 + 0) * TILE_ELEMS, kbase, krs, k0, cnt, tid, qbase + D, rs, f0);
-    load_tile_async(KVs + (buf * 2 + 1) * TILE_ELEMS, vbase, krs, k0, cnt, tid, qbase + 2 * D, rs, f0);
+    load_tile_async(KVs + (buf * 2 + 0) * TILE_ELEMS, kbase, krs, k0, cnt, gtid, qbase + D, rs, f0);
+    load_tile_async(KVs + (buf * 2 + 1) * TILE_ELEMS, vbase, krs, k0, cnt, gtid, qbase + 2 * D, rs, f0);
   };
-  load_tile_async(Qs, qbase, rs, 0, M, tid);
-  if (it_begin < it_end) issue_tile(it_begin, 0);
+  const int it_first = it_begin + grp;
+  if (grp == 0) load_tile_async(Qs, qbase, rs, 0, M, gtid);
+  if (it_first < it_end) issue_tile(it_first, 0);
   cp_async_commit();
+  if (NG > 1) {                        // Q comes from group 0's threads: everybody sees it before the first tile
+    cp_async_wait<0>();
+    __syncthreads();
+  }
 
-  uint32_t qf[2][4][4];
+  uint32_t qf[NG == 1 ? 2 : 1][4][4];
   float o[2][8][4];
 #pragma unroll
   for (int rb = 0; rb < 2; ++rb)
@@ -384,17 +395,18 @@ attn_step32_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T2,
 #pragma unroll
   for (int r = 0; r < 4; ++r) { m[r] = -INFINITY; l[r] = 0.f; }
 
-  for (int it = it_begin; it < it_end; ++it) {
-    const int buf = (it - it_begin) & 1;
-    if (it + 1 < it_end) {
-      issue_tile(it + 1, buf ^ 1);
+  int iter = 0;
+  for (int it = it_first; it < it_end; it += NG, ++iter) {
+    const int buf = iter & 1;
+    if (it + NG < it_end) {
+      issue_tile(it + NG, buf ^ 1);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
-    __syncthreads();
-    if (it == it_begin) {
+    group_sync();
+    if (NG == 1 && iter == 0) {
 #pragma unroll
       for (int rb = 0; rb < 2; ++rb) {
         const int row = rb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
@@ -419,8 +431,12 @@ attn_step32_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T2,
         ldsm_x4(smem_addr(Kt + sw(row, kk * 2 + (mi & 1))), kf);
 #pragma unroll
         for (int rb = 0; rb < 2; ++rb) {
-          mma_bf16(sc[rb][0], qf[rb][kk], kf[0], kf[1]);
-          mma_bf16(sc[rb][1], qf[rb][kk], kf[2], kf[3]);
+          if (NG > 1) {
+            const int qrow = rb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+            ldsm_x4(smem_addr(Qs + sw(qrow, kk * 2 + (lane >> 4))), qf[0][kk]);
+          }
+          mma_bf16(sc[rb][0], qf[NG == 1 ? rb : 0][kk], kf[0], kf[1]);
+          mma_bf16(sc[rb][1], qf[NG == 1 ? rb : 0][kk], kf[2], kf[3]);
         }
       }
       // ---- keys past the end of the cache are masked; online softmax per row over this warp's keys
@@ -482,7 +498,7 @@ attn_step32_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T2,
         }
       }
     }
-    __syncthreads();  // tile `buf` fully consumed before the next iteration's prefetch overwrites it
+    group_sync();     // tile `buf` fully consumed before the next iteration's prefetch overwrites it
   }
   cp_async_wait<0>();
   __syncthreads();    // (an empty key range never entered the loop) nobody reads Q / K / V any more: Op may overwrite them
@@ -493,7 +509,7 @@ attn_step32_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T2,
     l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
     l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
   }
-  float* myO = Op + (size_t)warp * SQ * OP_LD;
+  float* myO = Op + (size_t)wall * SQ * OP_LD;
 #pragma unroll
   for (int rb = 0; rb < 2; ++rb) {
 #pragma unroll
@@ -502,22 +518,23 @@ attn_step32_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T2,
       *reinterpret_cast<float2*>(myO + (rb * 16 + g + 8) * OP_LD + j * 8 + 2 * t4) = make_float2(o[rb][j][2], o[rb][j][3]);
     }
     if (t4 == 0) {
-      s_ml[warp][rb * 16 + g][0] = m[rb * 2]; s_ml[warp][rb * 16 + g][1] = l[rb * 2];
-      s_ml[warp][rb * 16 + g + 8][0] = m[rb * 2 + 1]; s_ml[warp][rb * 16 + g + 8][1] = l[rb * 2 + 1];
+      s_ml[wall][rb * 16 + g][0] = m[rb * 2]; s_ml[wall][rb * 16 + g][1] = l[rb * 2];
+      s_ml[wall][rb * 16 + g + 8][0] = m[rb * 2 + 1]; s_ml[wall][rb * 16 + g + 8][1] = l[rb * 2 + 1];
     }
   }
   __syncthreads();
-  const int row = tid >> 2, c0 = (tid & 3) * 16;      // 32 rows x 4 column quarters
+  const int row = gtid >> 2, c0 = (gtid & 3) * 16;    // 32 rows x 4 column quarters (the first 128 threads merge)
+  const bool merger = tid < 128;
   float mxr = -INFINITY;
 #pragma unroll
-  for (int w = 0; w < 4; ++w) mxr = fmaxf(mxr, s_ml[w][row][0]);
+  for (int w = 0; w < 4 * NG; ++w) mxr = fmaxf(mxr, s_ml[w][row][0]);
   float acc[16], lsum = 0.f;
 #pragma unroll
   for (int c = 0; c < 16; ++c) acc[c] = 0.f;
 #pragma unroll
-  for (int w = 0; w < 4; ++w) {
+  for (int w = 0; w < 4 * NG; ++w) {
     const float mw = s_ml[w][row][0];
-    if (mw == -INFINITY) continue;
+    if (mw == -INFINITY || !merger) continue;
     const float wgt = exp2f((mw - mxr) * scale_log2);
     lsum = fmaf(s_ml[w][row][1], wgt, lsum);
     const float* src = Op + ((size_t)w * SQ + row) * OP_LD + c0;
@@ -529,7 +546,7 @@ attn_step32_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T2,
     }
   }
   if (n_splits == 1) {
-    if (row < M) {
+    if (row < M && merger) {
       const float inv = lsum > 0.f ? 1.0f / lsum : 0.f;
       bf16* dst = ctx + ((size_t)b * M + row) * D + (size_t)h * HD + c0;
 #pragma unroll
@@ -544,19 +561,21 @@ attn_step32_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T2,
   }
   // ---- split keys over CTAs: this CTA's state per row (layout of attn_mma_kernel: 64 rows x 66 floats per split);
   //      the CTA of this (stream, head) that finishes last merges the splits in a fixed order
-  const size_t grp = (size_t)b * gridDim.y + h;
-  float* P = partials + (grp * n_splits + split) * (size_t)(QT * 66);
+  const size_t bh = (size_t)b * gridDim.y + h;
+  float* P = partials + (bh * n_splits + split) * (size_t)(QT * 66);
+  if (merger) {
 #pragma unroll
-  for (int c = 0; c < 16; c += 2) *reinterpret_cast<float2*>(P + row * 66 + c0 + c) = make_float2(acc[c], acc[c + 1]);
-  if ((tid & 3) == 0) *reinterpret_cast<float2*>(P + row * 66 + 64) = make_float2(mxr, lsum);
+    for (int c = 0; c < 16; c += 2) *reinterpret_cast<float2*>(P + row * 66 + c0 + c) = make_float2(acc[c], acc[c + 1]);
+    if ((tid & 3) == 0) *reinterpret_cast<float2*>(P + row * 66 + 64) = make_float2(mxr, lsum);
+  }
   __threadfence();
   __syncthreads();
-  if (tid == 0) s_last = atomicAdd(counters + grp, 1u) == (unsigned)n_splits - 1;
+  if (tid == 0) s_last = atomicAdd(counters + bh, 1u) == (unsigned)n_splits - 1;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  const float* P0 = partials + grp * n_splits * (size_t)(QT * 66);
-  for (int idx = tid; idx < M * 8; idx += 128) {
+  const float* P0 = partials + bh * n_splits * (size_t)(QT * 66);
+  for (int idx = tid; idx < M * 8; idx += 128 * NG) {
     const int r = idx >> 3, chunk = idx & 7;
     float mx = -INFINITY;
     for (int sp = 0; sp < n_splits; ++sp) mx = fmaxf(mx, __ldcg(P0 + (size_t)sp * QT * 66 + r * 66 + 64));
@@ -580,7 +599,7 @@ attn_step32_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T2,
     v.z = pack_bf16x2(a8[4] * inv, a8[5] * inv); v.w = pack_bf16x2(a8[6] * inv, a8[7] * inv);
     *reinterpret_cast<uint4*>(ctx + ((size_t)b * M + r) * D + (size_t)h * HD + chunk * 8) = v;
   }
-  if (tid == 0) counters[grp] = 0u;            // ready for the next launch (stream order)
+  if (tid == 0) counters[bh] = 0u;            // ready for the next launch (stream order)
 }
 }  // namespace
 
@@ -606,8 +625,20 @@ w2vs_status_t launch_attention_mma(const AttnArgs& a, cudaStream_t st) {
 #define W2VS_ATTN_STEP32 1
 #endif
     if (W2VS_ATTN_STEP32 && a.n_step_q <= SQ) {     // the usual decision step: keys split over the warps of a CTA
+#ifndef W2VS_ATTN_STEP_GROUPS
+#define W2VS_ATTN_STEP_GROUPS 2
+#endif
+      constexpr int NG = W2VS_ATTN_STEP_GROUPS;
+      constexpr size_t smem32 = (size_t)(1 + 4 * NG) * TILE_ELEMS * 2;
+      static PerDeviceOnce attr_once;
+      bool& attr_done = attr_once.here();
+      if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(attn_step32_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+        if (e != cudaSuccess) { set_error("attn_step32 smem attribute: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
+        attr_done = true;
+      }
       dim3 grid32((unsigned)splits, (unsigned)a.heads, (unsigned)a.B);
-      launch_pdl(attn_step32_kernel, grid32, dim3(128), 0, st, (const bf16*)a.qkv, (bf16*)a.ctx, a.n_step_keys,
+      launch_pdl(attn_step32_kernel<NG>, grid32, dim3(128 * NG), smem32, st, (const bf16*)a.qkv, (bf16*)a.ctx, a.n_step_keys,
                  a.n_step_q, a.D, scale_log2, (const bf16*)a.kv_cache, a.kv_rows, splits, a.step_partials,
                  a.step_counters);
       W2VS_CHECK_LAUNCH("attn_step32_kernel");

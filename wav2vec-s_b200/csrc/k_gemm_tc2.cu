@@ -445,7 +445,7 @@ w2vs_status_t launch_typed(const GemmArgs& g, cudaStream_t st) {
   // in-place fp32 product with fewer 64-wide tiles than half the SM pairs: split K (see RED above).  Tile width 64 or
   // 128, whichever leaves the shorter K range per cluster (the chain of dependent TMA stages is what these products
   // cost): out_proj / fc2 of 16 streams run as 16 tiles of 128 columns x 4 ranges.
-  if (W2VS_GEMM_SPLITK && sizeof(TC) == 4 && g.residual != nullptr && g.batch <= 1 && g.N % 64 == 0 && g.K % BK == 0 &&
+  if (W2VS_GEMM_SPLITK && (g.flags & W2VS_EPI_SPLITK) && sizeof(TC) == 4 && g.residual != nullptr && g.batch <= 1 && g.N % 64 == 0 && g.K % BK == 0 &&
       g.K <= g.lda && m_tiles * (g.N / 64) * 2 <= clusters) {
     const int num_kb = g.K / BK;
     auto ranges = [&](int64_t tiles) {

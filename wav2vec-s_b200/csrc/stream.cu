@@ -223,11 +223,11 @@ w2vs_status_t block_step(const w2vs_config* cfg, const WeightLayout& wl, const S
       aa.step_partials = at<float>(d_ws, L.attn_part); aa.step_counters = at<unsigned>(d_state, L.sync);
       W2VS_TRY(launch_attention(0, aa, st));
     }
-    W2VS_TRY(gemm(ctx, D, lw.wo, lw.bo, X, X, D, W2VS_F32, 0));
+    W2VS_TRY(gemm(ctx, D, lw.wo, lw.bo, X, X, D, W2VS_F32, W2VS_EPI_SPLITK));
     if (pre_ln) W2VS_TRY(layer_norm(lw.ln2_w, lw.ln2_b, false));
     else W2VS_TRY(layer_norm(lw.ln1_w, lw.ln1_b, true));
     W2VS_TRY(gemm(Xa, D, lw.w1, lw.b1, nullptr, h, F, adt, W2VS_EPI_GELU, true));
-    W2VS_TRY(gemm(h, F, lw.w2, lw.b2, X, X, D, W2VS_F32, 0));
+    W2VS_TRY(gemm(h, F, lw.w2, lw.b2, X, X, D, W2VS_F32, W2VS_EPI_SPLITK));
     if (!pre_ln) W2VS_TRY(layer_norm(lw.ln2_w, lw.ln2_b, true));
   }
   FinalizeArgs f{};

@@ -28,7 +28,8 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
-def gemm(A, W, bias=None, residual=None, out_dtype=None, gelu=False, impl=cabi.GEMM_AUTO, M=None, K=None, lda=None):
+def gemm(A, W, bias=None, residual=None, out_dtype=None, gelu=False, impl=cabi.GEMM_AUTO, M=None, K=None, lda=None,
+         splitk=False):
     """C[M,N] = A[M,K] . W[N,K]^T + bias (+GELU) (+residual).  ``lda < K`` gives the overlapping-row
     (strided conv) view of a flat A buffer."""
     N = W.size(0)
@@ -43,7 +44,7 @@ def gemm(A, W, bias=None, residual=None, out_dtype=None, gelu=False, impl=cabi.G
         residual = Cm
     else:
         Cm = torch.empty((M, N), dtype=out_dtype, device=A.device)
-    flags = cabi.EPI_GELU if gelu else 0
+    flags = (cabi.EPI_GELU if gelu else 0) | (cabi.EPI_SPLITK if splitk else 0)
     cabi.check(cabi.lib().w2vs_op_gemm(impl, _dt(A), _dt(Cm), _ptr(A), lda, _ptr(W), _ptr(bias), _ptr(residual),
                                        _ptr(Cm), N, M, N, K, flags, _stream(A)), "w2vs_op_gemm")
     return Cm
