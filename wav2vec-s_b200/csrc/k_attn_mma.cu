@@ -625,22 +625,26 @@ w2vs_status_t launch_attention_mma(const AttnArgs& a, cudaStream_t st) {
 #define W2VS_ATTN_STEP32 1
 #endif
     if (W2VS_ATTN_STEP32 && a.n_step_q <= SQ) {     // the usual decision step: keys split over the warps of a CTA
-#ifndef W2VS_ATTN_STEP_GROUPS
-#define W2VS_ATTN_STEP_GROUPS 2
-#endif
-      constexpr int NG = W2VS_ATTN_STEP_GROUPS;
-      constexpr size_t smem32 = (size_t)(1 + 4 * NG) * TILE_ELEMS * 2;
+      // two tile groups per CTA while the CTAs do not fill the GPU (one stream through the chain: 1.38 -> 1.35 ms per
+      // step); with 256 CTAs (16 streams) one group is as fast (1.78 vs 1.79 ms) and leaves three CTAs per SM
+      dim3 grid32((unsigned)splits, (unsigned)a.heads, (unsigned)a.B);
+      const bool two = (int64_t)splits * a.heads * a.B <= 148;
+      constexpr size_t smem1 = (size_t)(1 + 4) * TILE_ELEMS * 2, smem2 = (size_t)(1 + 8) * TILE_ELEMS * 2;
       static PerDeviceOnce attr_once;
       bool& attr_done = attr_once.here();
       if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(attn_step32_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+        cudaError_t e = cudaFuncSetAttribute(attn_step32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
         if (e != cudaSuccess) { set_error("attn_step32 smem attribute: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
         attr_done = true;
       }
-      dim3 grid32((unsigned)splits, (unsigned)a.heads, (unsigned)a.B);
-      launch_pdl(attn_step32_kernel<NG>, grid32, dim3(128 * NG), smem32, st, (const bf16*)a.qkv, (bf16*)a.ctx, a.n_step_keys,
-                 a.n_step_q, a.D, scale_log2, (const bf16*)a.kv_cache, a.kv_rows, splits, a.step_partials,
-                 a.step_counters);
+      if (two)
+        launch_pdl(attn_step32_kernel<2>, grid32, dim3(256), smem2, st, (const bf16*)a.qkv, (bf16*)a.ctx, a.n_step_keys,
+                   a.n_step_q, a.D, scale_log2, (const bf16*)a.kv_cache, a.kv_rows, splits, a.step_partials,
+                   a.step_counters);
+      else
+        launch_pdl(attn_step32_kernel<1>, grid32, dim3(128), smem1, st, (const bf16*)a.qkv, (bf16*)a.ctx, a.n_step_keys,
+                   a.n_step_q, a.D, scale_log2, (const bf16*)a.kv_cache, a.kv_rows, splits, a.step_partials,
+                   a.step_counters);
       W2VS_CHECK_LAUNCH("attn_step32_kernel");
       return W2VS_OK;
     }
