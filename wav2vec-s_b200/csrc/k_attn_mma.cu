@@ -628,7 +628,7 @@ w2vs_status_t launch_attention_mma(const AttnArgs& a, cudaStream_t st) {
       // two tile groups per CTA while the CTAs do not fill the GPU (one stream through the chain: 1.38 -> 1.35 ms per
       // step); with 256 CTAs (16 streams) one group is as fast (1.78 vs 1.79 ms) and leaves three CTAs per SM
       dim3 grid32((unsigned)splits, (unsigned)a.heads, (unsigned)a.B);
-      const bool two = (int64_t)splits * a.heads * a.B <= 148;
+      const bool two = (int64_t)splits * a.heads * a.B <= num_sms();
       constexpr size_t smem1 = (size_t)(1 + 4) * TILE_ELEMS * 2, smem2 = (size_t)(1 + 8) * TILE_ELEMS * 2;
       static PerDeviceOnce attr_once;
       bool& attr_done = attr_once.here();
