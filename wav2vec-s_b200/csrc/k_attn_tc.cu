@@ -61,6 +61,10 @@ constexpr int P_BYTES = QT * KT * 2;         // 16 KB: bf16 P (A operand of PV),
 // at cfg3 (round 2, same box): 2 slots x 3 CTAs 466 us; 1 slot x 3 CTAs 500 us; 1 slot x 4 CTAs (96 registers,
 // 572 bytes of spills in the tile loop) 1066 us.  F2FP packing is not on the MUFU pipe (tools/mufu_bw.cu: ex2 alone
 // 16 / clk / SM, with one bf16x2 pack per two ex2 still 16), and cutting P to bf16 with PRMT instead changes nothing.
+// Skipping the row maximum on every tile but an item's first (the reference only has to keep 2^(s - m_ref) inside the
+// exponent range; a tile whose row sum overflows would be redone): 475 -> 459 us without the redo path, 552 us with it
+// (spills); the tile period of a softmax warp stays at ~2350 cycles either way -- the exponential phase stretches from
+// 1050 to 1210 cycles, i.e. the three warps of a sub-partition queue on the MUFU pipe in step.  Not kept.
 #ifndef W2VS_ATTN_NS
 #define W2VS_ATTN_NS 2
 #endif
