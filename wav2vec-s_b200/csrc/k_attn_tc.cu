@@ -65,6 +65,10 @@ constexpr int P_BYTES = QT * KT * 2;         // 16 KB: bf16 P (A operand of PV),
 // exponent range; a tile whose row sum overflows would be redone): 475 -> 459 us without the redo path, 552 us with it
 // (spills); the tile period of a softmax warp stays at ~2350 cycles either way -- the exponential phase stretches from
 // 1050 to 1210 cycles, i.e. the three warps of a sub-partition queue on the MUFU pipe in step.  Not kept.
+// Two passes over the scores in TMEM, 32 columns at a time (row maximum, then exponentials: 32 score registers, 96
+// registers per thread without spills, bit-identical output): 495 us at three CTAs per SM, 488 us at four -- four
+// CTAs only fit with one-slot K / V rings (50 KB each), and then PV(g-1) waits for its V tile: the softmax warps sit
+// ~1100 cycles per tile in the "PV retired" wait and the tile period per CTA grows from 2350 to 3400 cycles.  Not kept.
 #ifndef W2VS_ATTN_NS
 #define W2VS_ATTN_NS 2
 #endif
