@@ -69,6 +69,11 @@ constexpr int P_BYTES = QT * KT * 2;         // 16 KB: bf16 P (A operand of PV),
 // registers per thread without spills, bit-identical output): 495 us at three CTAs per SM, 488 us at four -- four
 // CTAs only fit with one-slot K / V rings (50 KB each), and then PV(g-1) waits for its V tile: the softmax warps sit
 // ~1100 cycles per tile in the "PV retired" wait and the tile period per CTA grows from 2350 to 3400 cycles.  Not kept.
+// The chain of ONE softmax warp, uncontended (one CTA per SM, W2VS_ATTN_CTAS=1): 1860 cycles per tile, of which the
+// exponential phase is 805 (64 MUFU.EX2 at 8 cycles each plus the dependent FFMA2 / FADD2 / F2FP), TMEM load 70, row
+// maximum 300-350, waits and fences ~500.  Per layer call: 929 us at one CTA per SM, 552 at two, 466 at three (tile
+// periods 1860 / 2140 / 2350 cycles): the kernel is latency bound per warp and every further resident pipeline still
+// adds throughput; starting the co-resident pipelines 600-800 cycles apart changes nothing (466.4 vs 466.5 us).
 #ifndef W2VS_ATTN_NS
 #define W2VS_ATTN_NS 2
 #endif
