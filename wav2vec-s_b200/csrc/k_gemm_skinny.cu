@@ -34,7 +34,14 @@ __global__ void __launch_bounds__(SK_THREADS)
 gemm_skinny_kernel(const bf16* __restrict__ A, int64_t lda, const bf16* __restrict__ W, const float* __restrict__ bias,
                    int has_residual, TC* C, int64_t ldc, int M, int N, int K, int gelu) {
   __shared__ float part[SK_WARPS][MT * 16][8 + 1];
-  pdl_launch_dependents();
+  // No griddepcontrol.launch_dependents here: the successors of a product (LayerNorm, step attention) have nothing
+  // to fetch ahead of their dependency, and released early they only get in the way -- one stream through the chain
+  // 1.354 -> 1.263 ms per step without it (same finding as for the tcgen05 products).  The kernels in
+  // FRONT of a product (LayerNorm, attention) do release early: this kernel's weight loads below run ahead of its wait.
+#ifndef W2VS_SKINNY_TRIGGER
+#define W2VS_SKINNY_TRIGGER 0
+#endif
+  if (W2VS_SKINNY_TRIGGER) pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
   const int n0 = blockIdx.x * 8;
