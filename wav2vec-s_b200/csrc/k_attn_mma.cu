@@ -343,7 +343,7 @@ attn_step32_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T2,
   bf16* Qs = reinterpret_cast<bf16*>(sm_raw);
   float* Op = reinterpret_cast<float*>(sm_raw);                            // [4 * NG warps][SQ][OP_LD]
   static_assert(4 * NG * SQ * OP_LD * 4 <= (1 + 4 * NG) * TILE_ELEMS * 2, "partial O does not fit");
-  pdl_prologue();
+  pdl_launch_dependents();
 
   const int tid = threadIdx.x, wall = tid >> 5, lane = tid & 31;
   const int grp = wall >> 2, warp = wall & 3, gtid = tid & 127;      // tile group, key quarter inside a tile
@@ -356,14 +356,6 @@ attn_step32_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T2,
   const bf16* kbase = kv_cache + (size_t)b * kv_rows * krs + (size_t)h * HD;
   const bf16* vbase = kbase + D;
   const int f0 = T2 - M;               // keys at or past f0 are this step's own tokens (read from qkv)
-  if (blockIdx.x == 0) {               // append this step's K / V to the cache for later steps
-    bf16* cache = const_cast<bf16*>(kv_cache) + (size_t)b * kv_rows * krs + (size_t)h * HD;
-    for (int i = tid; i < M * 16; i += 128 * NG) {
-      const int row = i >> 4, part = (i >> 3) & 1, chunk = i & 7;
-      const uint4 v = *reinterpret_cast<const uint4*>(qbase + (size_t)row * rs + (1 + part) * D + chunk * 8);
-      *reinterpret_cast<uint4*>(cache + (size_t)(f0 + row) * krs + part * D + chunk * 8) = v;
-    }
-  }
   const int n_kt = (T2 + KT - 1) / KT;
   int it_begin = 0, it_end = n_kt;
   if (n_splits > 1) {
@@ -377,8 +369,21 @@ attn_step32_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T2,
     load_tile_async(KVs + (buf * 2 + 1) * TILE_ELEMS, vbase, krs, k0, cnt, gtid, qbase + 2 * D, rs, f0);
   };
   const int it_first = it_begin + grp;
+  // Keys before f0 were cached by earlier steps: a first tile made of those alone is requested before this kernel
+  // waits for its predecessor (the QKV product), everything that reads this step's qkv rows after.
+  const bool early = it_first < it_end && (it_first + 1) * KT <= f0;
+  if (early) issue_tile(it_first, 0);
+  pdl_wait();
+  if (blockIdx.x == 0) {               // append this step's K / V to the cache for later steps
+    bf16* cache = const_cast<bf16*>(kv_cache) + (size_t)b * kv_rows * krs + (size_t)h * HD;
+    for (int i = tid; i < M * 16; i += 128 * NG) {
+      const int row = i >> 4, part = (i >> 3) & 1, chunk = i & 7;
+      const uint4 v = *reinterpret_cast<const uint4*>(qbase + (size_t)row * rs + (1 + part) * D + chunk * 8);
+      *reinterpret_cast<uint4*>(cache + (size_t)(f0 + row) * krs + part * D + chunk * 8) = v;
+    }
+  }
   if (grp == 0) load_tile_async(Qs, qbase, rs, 0, M, gtid);
-  if (it_first < it_end) issue_tile(it_first, 0);
+  if (!early && it_first < it_end) issue_tile(it_first, 0);
   cp_async_commit();
   if (NG > 1) {                        // Q comes from group 0's threads: everybody sees it before the first tile
     cp_async_wait<0>();
