@@ -332,7 +332,10 @@ constexpr int OP_LD = 68;              // floats per row of a warp's partial O i
 // NG groups of four warps walk the key tiles in turns (group q takes tiles q, q + NG, ...), each with its own two-stage
 // K/V ring, so NG tiles are in flight per CTA; all 4 * NG warp states are merged at the end.  NG = 2 keeps the Q
 // fragments in shared memory (128 registers per thread for two CTAs of 256 threads per SM).
-template <int NG>
+// NSTG: depth of a group's K/V ring (cp.async groups, NSTG - 1 tiles in flight ahead of the one being consumed): with
+// 256 CTAs of one group (16 streams) two stages keep ~28 KB per SM in flight, less than half of what the HBM latency
+// needs (the kernel read 76 MB at 36 % of the DRAM peak); four stages are used there.
+template <int NG, int NSTG>
 __global__ void __launch_bounds__(128 * NG, NG == 1 ? 3 : 2)
 attn_step32_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T2, int M, int D, float scale_log2,
                    const bf16* __restrict__ kv_cache, int64_t kv_rows, int n_splits, float* __restrict__ partials,
@@ -342,14 +345,14 @@ attn_step32_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T2,
   __shared__ int s_last;
   bf16* Qs = reinterpret_cast<bf16*>(sm_raw);
   float* Op = reinterpret_cast<float*>(sm_raw);                            // [4 * NG warps][SQ][OP_LD]
-  static_assert(4 * NG * SQ * OP_LD * 4 <= (1 + 4 * NG) * TILE_ELEMS * 2, "partial O does not fit");
+  static_assert(4 * NG * SQ * OP_LD * 4 <= (1 + 2 * NSTG * NG) * TILE_ELEMS * 2, "partial O does not fit");
   pdl_launch_dependents();
 
   const int tid = threadIdx.x, wall = tid >> 5, lane = tid & 31;
   const int grp = wall >> 2, warp = wall & 3, gtid = tid & 127;      // tile group, key quarter inside a tile
   const int g = lane >> 2, t4 = lane & 3;
   const int h = blockIdx.y, b = blockIdx.z, split = blockIdx.x;
-  bf16* KVs = Qs + TILE_ELEMS + (size_t)grp * 4 * TILE_ELEMS;          // this group's [stage][K | V][64 x 64]
+  bf16* KVs = Qs + TILE_ELEMS + (size_t)grp * 2 * NSTG * TILE_ELEMS;   // this group's [stage][K | V][64 x 64]
   auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); };
   const int64_t rs = 3 * (int64_t)D, krs = 2 * (int64_t)D;
   const bf16* qbase = qkv + (size_t)b * M * rs + (size_t)h * HD;
@@ -385,6 +388,11 @@ attn_step32_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T2,
   if (grp == 0) load_tile_async(Qs, qbase, rs, 0, M, gtid);
   if (!early && it_first < it_end) issue_tile(it_first, 0);
   cp_async_commit();
+#pragma unroll
+  for (int st = 1; st < NSTG - 1; ++st) {          // the ring's other leading stages, one cp.async group each
+    if (it_first + st * NG < it_end) issue_tile(it_first + st * NG, st);
+    cp_async_commit();
+  }
   if (NG > 1) {                        // Q comes from group 0's threads: everybody sees it before the first tile
     cp_async_wait<0>();
     __syncthreads();
@@ -402,14 +410,10 @@ attn_step32_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int T2,
 
   int iter = 0;
   for (int it = it_first; it < it_end; it += NG, ++iter) {
-    const int buf = iter & 1;
-    if (it + NG < it_end) {
-      issue_tile(it + NG, buf ^ 1);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
+    const int buf = iter % NSTG;
+    if (it + (NSTG - 1) * NG < it_end) issue_tile(it + (NSTG - 1) * NG, (iter + NSTG - 1) % NSTG);
+    cp_async_commit();                 // (possibly empty: the group count is what cp.async.wait_group counts)
+    cp_async_wait<NSTG - 1>();         // tile `it` has landed
     group_sync();
     if (NG == 1 && iter == 0) {
 #pragma unroll
@@ -634,20 +638,26 @@ w2vs_status_t launch_attention_mma(const AttnArgs& a, cudaStream_t st) {
       // step); with 256 CTAs (16 streams) one group is as fast (1.78 vs 1.79 ms) and leaves three CTAs per SM
       dim3 grid32((unsigned)splits, (unsigned)a.heads, (unsigned)a.B);
       const bool two = (int64_t)splits * a.heads * a.B <= num_sms();
-      constexpr size_t smem1 = (size_t)(1 + 4) * TILE_ELEMS * 2, smem2 = (size_t)(1 + 8) * TILE_ELEMS * 2;
+#ifndef W2VS_ATTN_STEP_STAGES
+#define W2VS_ATTN_STEP_STAGES 4
+#endif
+      constexpr int NSTG1 = W2VS_ATTN_STEP_STAGES;
+      constexpr size_t smem1 = (size_t)(1 + 2 * NSTG1) * TILE_ELEMS * 2, smem2 = (size_t)(1 + 8) * TILE_ELEMS * 2;
       static PerDeviceOnce attr_once;
       bool& attr_done = attr_once.here();
       if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(attn_step32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        cudaError_t e = cudaFuncSetAttribute(attn_step32_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e == cudaSuccess)
+          e = cudaFuncSetAttribute(attn_step32_kernel<1, NSTG1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e != cudaSuccess) { set_error("attn_step32 smem attribute: %s", cudaGetErrorString(e)); return W2VS_CUDA_ERROR; }
         attr_done = true;
       }
       if (two)
-        launch_pdl(attn_step32_kernel<2>, grid32, dim3(256), smem2, st, (const bf16*)a.qkv, (bf16*)a.ctx, a.n_step_keys,
+        launch_pdl(attn_step32_kernel<2, 2>, grid32, dim3(256), smem2, st, (const bf16*)a.qkv, (bf16*)a.ctx, a.n_step_keys,
                    a.n_step_q, a.D, scale_log2, (const bf16*)a.kv_cache, a.kv_rows, splits, a.step_partials,
                    a.step_counters);
       else
-        launch_pdl(attn_step32_kernel<1>, grid32, dim3(128), smem1, st, (const bf16*)a.qkv, (bf16*)a.ctx, a.n_step_keys,
+        launch_pdl(attn_step32_kernel<1, NSTG1>, grid32, dim3(128), smem1, st, (const bf16*)a.qkv, (bf16*)a.ctx, a.n_step_keys,
                    a.n_step_q, a.D, scale_log2, (const bf16*)a.kv_cache, a.kv_rows, splits, a.step_partials,
                    a.step_counters);
       W2VS_CHECK_LAUNCH("attn_step32_kernel");
