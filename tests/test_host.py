@@ -33,6 +33,38 @@ def test_library_exports_every_declared_symbol():
     assert cabi.lib().w2vs_status_string(0) == b"ok"
 
 
+def test_binding_constants_match_the_header():
+    """Every #define and enumerator of include/w2vs.h the ctypes binding mirrors has the header's value."""
+    src = open(os.path.join(ROOT, "include", "w2vs.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    defines = {k: int(v) for k, v in re.findall(r"#define\s+(W2VS_[A-Z0-9_]+)\s+(\d+)\b", src)}
+    enums = {}
+    for body in re.findall(r"typedef\s+enum\s*\{(.*?)\}", src, flags=re.S):
+        nxt = 0
+        for item in body.split(","):
+            item = item.strip()
+            if not item:
+                continue
+            name, _, val = item.partition("=")
+            nxt = int(val) if val.strip() else nxt
+            enums[name.strip()] = nxt
+            nxt += 1
+    want = {
+        "W2VS_MAX_CONV": cabi.W2VS_MAX_CONV, "W2VS_ABI_VERSION": cabi.W2VS_ABI_VERSION,
+        "W2VS_EPI_GELU": cabi.EPI_GELU, "W2VS_EPI_SPLITK": cabi.EPI_SPLITK,
+    }
+    for k, v in want.items():
+        assert defines[k] == v, k
+    want_enum = {
+        "W2VS_OK": cabi.OK, "W2VS_INVALID_VALUE": cabi.INVALID_VALUE, "W2VS_UNSUPPORTED": cabi.UNSUPPORTED,
+        "W2VS_WORKSPACE_TOO_SMALL": cabi.WORKSPACE_TOO_SMALL, "W2VS_CUDA_ERROR": cabi.CUDA_ERROR,
+        "W2VS_GEMM_AUTO": cabi.GEMM_AUTO, "W2VS_GEMM_SIMT": cabi.GEMM_SIMT,
+        "W2VS_GEMM_TCGEN05_2CTA": cabi.GEMM_TCGEN05_2CTA, "W2VS_GEMM_SKINNY": cabi.GEMM_SKINNY,
+    }
+    for k, v in want_enum.items():
+        assert enums[k] == v, k
+
+
 @pytest.mark.parametrize("cfg", [O.base_cfg(), O.large_cfg(), cases.tiny(), cases.tiny(main_context=8, right_context=4)])
 def test_geometry_bit_exact(cfg):
     m = W.Wav2VecSModel(cfg)
